@@ -1,0 +1,246 @@
+// Device contexts, error slot and the stand-alone C-ABI entry points of include/p2g.h (host buffers in/out).
+#include <string.h>
+
+#include "internal.h"
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+
+extern "C" const char* p2g_last_error(void) { return g_last_error.c_str(); }
+extern "C" int p2g_version(void) { return P2G_VERSION; }
+extern "C" int p2g_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static std::mutex g_ctx_mu;
+static std::map<int, DevCtx*> g_ctx;
+
+DevCtx* get_ctx(int device) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) {
+        CUDA_CHECK(cudaSetDevice(device));
+        return it->second;
+    }
+    int n = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) throw p2g_error(P2G_EBADARG, "no such CUDA device");
+    CUDA_CHECK(cudaSetDevice(device));
+    DevCtx* c = new DevCtx();
+    c->device = device;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    g_ctx[device] = c;
+    return c;
+}
+
+StageTimer::StageTimer(DevCtx* ctx, float* accum) : c(ctx), acc(accum) {
+    if (!c->timing) return;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+}
+StageTimer::~StageTimer() {
+    if (!a) return;
+    cudaEventRecord(b, c->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    *acc += ms;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+}
+
+int guard(const std::function<void()>& f) {
+    try {
+        f();
+        return P2G_OK;
+    } catch (const p2g_error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_last_error("host allocation failed");
+        return P2G_ENOMEM;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return P2G_ECUDA;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stand-alone kernels (parity tests, micro-benchmarks)
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int p2g_ifft(const uint64_t* values, uint64_t* coeffs, uint32_t log_n, uint32_t ncols, int device) {
+    return guard([&] {
+        if (!values || !coeffs || log_n > 26) throw p2g_error(P2G_EBADARG, "p2g_ifft: bad argument");
+        DevCtx* c = get_ctx(device);
+        size_t n = (size_t)1 << log_n, tot = n * ncols;
+        dbuf<u64> in(tot), out(tot);
+        CUDA_CHECK(cudaMemcpyAsync(in.p, values, tot * 8, cudaMemcpyHostToDevice, c->stream));
+        ntt_ifft(c, in.p, n, out.p, n, log_n, ncols);
+        CUDA_CHECK(cudaMemcpyAsync(coeffs, out.p, tot * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+extern "C" int p2g_lde(const uint64_t* coeffs, uint64_t* lde, uint32_t log_n, uint32_t rate_bits, uint32_t ncols, int device) {
+    return guard([&] {
+        if (!coeffs || !lde || log_n + rate_bits > 28 || rate_bits > 5) throw p2g_error(P2G_EBADARG, "p2g_lde: bad argument");
+        DevCtx* c = get_ctx(device);
+        size_t n = (size_t)1 << log_n, m = n << rate_bits;
+        dbuf<u64> in(n * ncols), out(m * ncols);
+        CUDA_CHECK(cudaMemcpyAsync(in.p, coeffs, n * ncols * 8, cudaMemcpyHostToDevice, c->stream));
+        ntt_lde(c, in.p, n, out.p, m, log_n, rate_bits, ncols, GL_GEN);
+        CUDA_CHECK(cudaMemcpyAsync(lde, out.p, m * ncols * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+extern "C" int p2g_coset_ifft_leaforder(const uint64_t* values, uint64_t* coeffs, uint32_t log_n, uint32_t ncols, int device) {
+    return guard([&] {
+        if (!values || !coeffs || log_n > 28) throw p2g_error(P2G_EBADARG, "p2g_coset_ifft_leaforder: bad argument");
+        DevCtx* c = get_ctx(device);
+        size_t n = (size_t)1 << log_n, tot = n * ncols;
+        dbuf<u64> buf(tot);
+        CUDA_CHECK(cudaMemcpyAsync(buf.p, values, tot * 8, cudaMemcpyHostToDevice, c->stream));
+        if (log_n == 0) {
+            // single point: the value is the constant coefficient
+        } else {
+            ntt_coset_ifft_leaforder(c, buf.p, n, log_n, ncols, GL_GEN);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(coeffs, buf.p, tot * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+// digests leave the library in the reference's serialised width (25 or 32 bytes each)
+void pack_digests(int hasher, const digest_t* src, size_t n, uint8_t* dst) {
+    int hs = hasher_bytes(hasher);
+    for (size_t i = 0; i < n; i++) memcpy(dst + i * hs, &src[i], hs);
+}
+
+extern "C" int p2g_merkle_cap(const uint64_t* leaves_colmajor, uint32_t log_leaves, uint32_t ncols, uint32_t cap_height,
+                              uint32_t hasher, uint8_t* cap_out, uint8_t* digests_out, int device) {
+    return guard([&] {
+        if (!leaves_colmajor || !cap_out || log_leaves > 28 || hasher > 1 || ncols == 0)
+            throw p2g_error(P2G_EBADARG, "p2g_merkle_cap: bad argument");
+        DevCtx* c = get_ctx(device);
+        size_t nl = (size_t)1 << log_leaves;
+        dbuf<u64> in(nl * ncols);
+        CUDA_CHECK(cudaMemcpyAsync(in.p, leaves_colmajor, nl * ncols * 8, cudaMemcpyHostToDevice, c->stream));
+        MerkleTree t;
+        merkle_build(c, &t, in.p, nl, (int)log_leaves, (int)ncols, (int)cap_height, (int)hasher);
+        std::vector<digest_t> cap(t.ncap());
+        CUDA_CHECK(cudaMemcpyAsync(cap.data(), t.cap(), sizeof(digest_t) * cap.size(), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<digest_t> lv;
+        if (digests_out) {
+            lv.resize(nl);
+            CUDA_CHECK(cudaMemcpyAsync(lv.data(), t.levels[0].p, sizeof(digest_t) * nl, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        pack_digests((int)hasher, cap.data(), cap.size(), cap_out);
+        if (digests_out) pack_digests((int)hasher, lv.data(), nl, digests_out);
+    });
+}
+
+namespace {
+__global__ void k_poseidon_permute(const u64* in, u64* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = in[12 * i + k];
+    poseidon_permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) out[12 * i + k] = s[k];
+}
+__global__ void k_keccak256(const u8* msgs, size_t msg_len, size_t n, u8* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u8* m = msgs + i * msg_len;
+    keccak_sponge sp;
+    sp.init();
+    size_t full = msg_len / 8;
+    for (size_t k = 0; k < full; k++) {
+        u64 wd = 0;
+        for (int b = 0; b < 8; b++) wd |= (u64)m[8 * k + b] << (8 * b);
+        sp.absorb_word(wd);
+    }
+    int tail_n = (int)(msg_len - 8 * full);
+    u64 tail = 0;
+    for (int b = 0; b < tail_n; b++) tail |= (u64)m[8 * full + b] << (8 * b);
+    sp.finish(tail, tail_n);
+    for (int k = 0; k < 4; k++)
+        for (int b = 0; b < 8; b++) out[32 * i + 8 * k + b] = (u8)(sp.A[k] >> (8 * b));
+}
+}  // namespace
+
+extern "C" int p2g_poseidon_permute(const uint64_t* in, uint64_t* out, size_t n, int device) {
+    return guard([&] {
+        if (!in || !out) throw p2g_error(P2G_EBADARG, "p2g_poseidon_permute: null pointer");
+        DevCtx* c = get_ctx(device);
+        if (!n) return;
+        dbuf<u64> a(12 * n), b(12 * n);
+        CUDA_CHECK(cudaMemcpyAsync(a.p, in, 96 * n, cudaMemcpyHostToDevice, c->stream));
+        k_poseidon_permute<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(a.p, b.p, n);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(out, b.p, 96 * n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+extern "C" int p2g_keccak256(const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* out, int device) {
+    return guard([&] {
+        if (!msgs || !out) throw p2g_error(P2G_EBADARG, "p2g_keccak256: null pointer");
+        DevCtx* c = get_ctx(device);
+        if (!n) return;
+        dbuf<u8> a(std::max<size_t>(1, msg_len * n)), b(32 * n);
+        CUDA_CHECK(cudaMemcpyAsync(a.p, msgs, msg_len * n, cudaMemcpyHostToDevice, c->stream));
+        k_keccak256<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(a.p, msg_len, n, b.p);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(out, b.p, 32 * n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+// ---- host-side twins of the device primitives (the transcript runs on the host); exported for CPU-only tests ----
+extern "C" void p2g_host_keccak256(const uint8_t* msg, size_t msg_len, uint8_t* out32) {
+    keccak_sponge sp;
+    sp.init();
+    size_t full = msg_len / 8;
+    for (size_t k = 0; k < full; k++) {
+        u64 wd;
+        memcpy(&wd, msg + 8 * k, 8);
+        sp.absorb_word(wd);
+    }
+    u64 tail = 0;
+    memcpy(&tail, msg + 8 * full, msg_len - 8 * full);
+    sp.finish(tail, (int)(msg_len - 8 * full));
+    memcpy(out32, sp.A, 32);
+}
+extern "C" void p2g_host_poseidon_permute(const uint64_t* in, uint64_t* out) {
+    u64 s[12];
+    memcpy(s, in, 96);
+    poseidon_permute(s);
+    memcpy(out, s, 96);
+}
+// runs a challenger: observe `n_obs` elements, then squeeze `n_out` challenges
+extern "C" void p2g_host_challenger(uint32_t hasher, const uint64_t* obs, size_t n_obs, uint64_t* out, size_t n_out) {
+    challenger_t ch;
+    ch.init((int)hasher);
+    ch.observe_many(obs, n_obs);
+    for (size_t i = 0; i < n_out; i++) out[i] = ch.get();
+}
+extern "C" void p2g_host_two_to_one(uint32_t hasher, const uint8_t* l, const uint8_t* r, uint8_t* out) {
+    digest_t a = {}, b = {};
+    int hs = hasher_bytes((int)hasher);
+    memcpy(&a, l, hs);
+    memcpy(&b, r, hs);
+    digest_t o = two_to_one((int)hasher, a, b);
+    memcpy(out, &o, hs);
+}
+extern "C" uint64_t p2g_host_gl_mul(uint64_t a, uint64_t b) { return gl_mul(a, b); }

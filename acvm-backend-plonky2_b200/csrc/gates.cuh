@@ -1,0 +1,272 @@
+// Device-side constraint evaluators for the 12 gate kinds of include/p2g.h (the 13 gates reachable from the reference's
+// translators; BaseSum<2> and BaseSum<4> share a kind), evaluated in the base field at one LDE point per thread.
+//
+// Replaces `Gate::eval_unfiltered_base_batch` / `eval_unfiltered_base_packed`:
+//   * custom gates, from the reference itself -- plonky2-backend/src/plonky2_ecdsa/biguint/gates/
+//       arithmetic_u32.rs:289-348, add_many_u32.rs:151-192, subtraction_u32.rs:234-271, range_check_u32.rs:95-117,
+//       comparison.rs:337-415 (wire layouts at arithmetic_u32.rs:50-87, add_many_u32.rs:50-87, subtraction_u32.rs:45-79,
+//       range_check_u32.rs:43-51, comparison.rs:52-96);
+//   * plonky2 0.2.2 built-ins (noop, constant, public_input, arithmetic_base, base_sum, poseidon, random_access) per
+//     SURVEY.md App. B.
+// Constraints are emitted in the reference's order into a Sink (the quotient kernel folds them into the alpha-weighted sum
+// on the fly; the stand-alone entry point stores them), so no per-point constraint vector is ever materialised.
+#pragma once
+#include "hash.cuh"
+#include "../../include/p2g.h"
+
+struct GateDev {
+    u32 kind;
+    u32 params[4];
+    u32 selector_index, group_lo, group_hi, num_constraints;
+};
+
+// l (l-1)(l-2)(l-3): the base-4 limb range check shared by the u32 gates
+__device__ __forceinline__ u64 limb4_check(u64 l) {
+    u64 r = gl_mul(l, gl_sub(l, 1));
+    r = gl_mul(r, gl_sub(l, 2));
+    return gl_mul(r, gl_sub(l, 3));
+}
+// prod_{v < base} (l - v)
+__device__ __forceinline__ u64 limb_range_product(u64 l, u32 base) {
+    u64 r = l;
+    for (u32 v = 1; v < base; v++) r = gl_mul(r, gl_sub(l, v));
+    return r;
+}
+
+// W: callable u64(int wire); K: callable u64(int gate_local_constant); S: sink with emit(u64)
+template <class W, class K, class S>
+__device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, const u64* pi_hash, S& sink) {
+    const u32* p = g.params;
+    switch (g.kind) {
+    case P2G_GATE_NOOP:
+        break;
+    case P2G_GATE_CONSTANT:
+        for (u32 i = 0; i < p[0]; i++) sink.emit(gl_sub(c(i), w(i)));
+        break;
+    case P2G_GATE_PUBLIC_INPUT:
+        for (int i = 0; i < 4; i++) sink.emit(gl_sub(w(i), pi_hash[i]));
+        break;
+    case P2G_GATE_ARITHMETIC: {
+        const u64 c0 = c(0), c1 = c(1);
+        for (u32 i = 0; i < p[0]; i++) {
+            u64 prod = gl_mul(gl_mul(w(4 * i), w(4 * i + 1)), c0);
+            sink.emit(gl_sub(w(4 * i + 3), gl_add(prod, gl_mul(w(4 * i + 2), c1))));
+        }
+        break;
+    }
+    case P2G_GATE_BASE_SUM: {
+        const u32 base = p[0], nl = p[1];
+        u64 acc = 0;
+        for (int k = (int)nl - 1; k >= 0; k--) acc = gl_add(gl_mul_small(acc, base), w(1 + k));
+        sink.emit(gl_sub(acc, w(0)));
+        for (u32 k = 0; k < nl; k++) sink.emit(limb_range_product(w(1 + k), base));
+        break;
+    }
+    case P2G_GATE_POSEIDON: {
+        // wires: in 0..12, out 12..24, swap 24, delta 25..29, full-round-0 sbox inputs 29..65 (rounds 1-3),
+        // partial sbox inputs 65..87, full-round-1 sbox inputs 87..135
+        const u64 swap = w(24);
+        sink.emit(gl_mul(swap, gl_sub(swap, 1)));
+        u64 st[12];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            u64 lhs = w(i), rhs = w(i + 4), delta = w(25 + i);
+            sink.emit(gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), delta));
+            st[i] = gl_add(lhs, delta);
+            st[i + 4] = gl_sub(rhs, delta);
+        }
+#pragma unroll
+        for (int i = 8; i < 12; i++) st[i] = w(i);
+        int rnd = 0;
+#pragma unroll 1
+        for (int r = 0; r < 4; r++, rnd++) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC(12 * rnd + i));
+            if (r != 0) {
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    u64 sb = w(29 + 12 * (r - 1) + i);
+                    sink.emit(gl_sub(st[i], sb));
+                    st[i] = sb;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 12; i++) st[i] = poseidon_sbox(st[i]);
+            poseidon_mds(st);
+        }
+#pragma unroll 1
+        for (int r = 0; r < 22; r++, rnd++) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC(12 * rnd + i));
+            u64 sb = w(65 + r);
+            sink.emit(gl_sub(st[0], sb));
+            st[0] = poseidon_sbox(sb);
+            poseidon_mds(st);
+        }
+#pragma unroll 1
+        for (int r = 0; r < 4; r++, rnd++) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC(12 * rnd + i));
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                u64 sb = w(87 + 12 * r + i);
+                sink.emit(gl_sub(st[i], sb));
+                st[i] = sb;
+            }
+#pragma unroll
+            for (int i = 0; i < 12; i++) st[i] = poseidon_sbox(st[i]);
+            poseidon_mds(st);
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) sink.emit(gl_sub(st[i], w(12 + i)));
+        break;
+    }
+    case P2G_GATE_RANDOM_ACCESS: {
+        const u32 bits = p[0], copies = p[1], extra = p[2];
+        const u32 vec = 1u << bits;
+        const u32 routed_used = (2 + vec) * copies + extra;
+        for (u32 cp = 0; cp < copies; cp++) {
+            const u32 base = (2 + vec) * cp;
+            const u32 bw = routed_used + cp * bits;
+            u64 rec = 0;
+            for (u32 i = 0; i < bits; i++) {
+                u64 b = w(bw + i);
+                sink.emit(gl_mul(b, gl_sub(b, 1)));
+            }
+            for (int i = (int)bits - 1; i >= 0; i--) rec = gl_add(gl_dbl(rec), w(bw + i));
+            sink.emit(gl_sub(rec, w(base)));
+            // fold the list by the index bits, LSB first: x + b (y - x); vec <= 64 items in local registers/stack
+            u64 items[64];
+            for (u32 i = 0; i < vec; i++) items[i] = w(base + 2 + i);
+            u32 len = vec;
+            for (u32 b = 0; b < bits; b++) {
+                u64 bit = w(bw + b);
+                len >>= 1;
+                for (u32 i = 0; i < len; i++)
+                    items[i] = gl_add(items[2 * i], gl_mul(bit, gl_sub(items[2 * i + 1], items[2 * i])));
+            }
+            sink.emit(gl_sub(items[0], w(base + 1)));
+        }
+        for (u32 i = 0; i < extra; i++) sink.emit(gl_sub(c(i), w((2 + vec) * copies + i)));
+        break;
+    }
+    case P2G_GATE_U32_ARITHMETIC: {
+        const u32 ops = p[0];
+        for (u32 i = 0; i < ops; i++) {
+            const u32 q = 6 * i;
+            u64 computed = gl_add(gl_mul(w(q), w(q + 1)), w(q + 2));
+            u64 lo = w(q + 3), hi = w(q + 4), inv = w(q + 5);
+            u64 hi_not_max = gl_sub(gl_mul(inv, gl_sub(0xFFFFFFFFULL, hi)), 1);
+            sink.emit(gl_mul(hi_not_max, lo));
+            sink.emit(gl_sub(gl_add(gl_mul(hi, 1ULL << 32), lo), computed));
+            u64 comb_lo = 0, comb_hi = 0;
+            const u32 lw = 6 * ops + 32 * i;
+            for (int j = 31; j >= 0; j--) {
+                u64 limb = w(lw + j);
+                sink.emit(limb4_check(limb));
+                if (j < 16) comb_lo = gl_add(gl_mul_small(comb_lo, 4), limb);
+                else comb_hi = gl_add(gl_mul_small(comb_hi, 4), limb);
+            }
+            sink.emit(gl_sub(comb_lo, lo));
+            sink.emit(gl_sub(comb_hi, hi));
+        }
+        break;
+    }
+    case P2G_GATE_U32_ADD_MANY: {
+        const u32 na = p[0], ops = p[1];
+        for (u32 i = 0; i < ops; i++) {
+            const u32 q = (na + 3) * i;
+            u64 computed = 0;
+            for (u32 j = 0; j <= na; j++) computed = gl_add(computed, w(q + j));  // addends then carry-in
+            u64 res = w(q + na + 1), carry = w(q + na + 2);
+            sink.emit(gl_sub(gl_add(gl_mul(carry, 1ULL << 32), res), computed));
+            u64 comb_res = 0, comb_carry = 0;
+            const u32 lw = (na + 3) * ops + 18 * i;
+            for (int j = 17; j >= 0; j--) {
+                u64 limb = w(lw + j);
+                sink.emit(limb4_check(limb));
+                if (j < 16) comb_res = gl_add(gl_mul_small(comb_res, 4), limb);
+                else comb_carry = gl_add(gl_mul_small(comb_carry, 4), limb);
+            }
+            sink.emit(gl_sub(comb_res, res));
+            sink.emit(gl_sub(comb_carry, carry));
+        }
+        break;
+    }
+    case P2G_GATE_U32_SUBTRACTION: {
+        const u32 ops = p[0];
+        for (u32 i = 0; i < ops; i++) {
+            const u32 q = 5 * i;
+            u64 initial = gl_sub(gl_sub(w(q), w(q + 1)), w(q + 2));
+            u64 res = w(q + 3), bout = w(q + 4);
+            sink.emit(gl_sub(res, gl_add(initial, gl_mul(bout, 1ULL << 32))));
+            u64 comb = 0;
+            const u32 lw = 5 * ops + 16 * i;
+            for (int j = 15; j >= 0; j--) {
+                u64 limb = w(lw + j);
+                sink.emit(limb4_check(limb));
+                comb = gl_add(gl_mul_small(comb, 4), limb);
+            }
+            sink.emit(gl_sub(comb, res));
+            sink.emit(gl_mul(bout, gl_sub(1, bout)));
+        }
+        break;
+    }
+    case P2G_GATE_U32_RANGE_CHECK: {
+        const u32 nl = p[0];
+        for (u32 i = 0; i < nl; i++) {
+            const u32 aw = nl + 16 * i;
+            u64 acc = 0;
+            for (int j = 15; j >= 0; j--) acc = gl_add(gl_mul_small(acc, 4), w(aw + j));
+            sink.emit(gl_sub(acc, w(i)));
+            for (int j = 0; j < 16; j++) sink.emit(limb4_check(w(aw + j)));
+        }
+        break;
+    }
+    case P2G_GATE_COMPARISON: {
+        const u32 nb = p[0], nc = p[1];
+        const u32 cb = (nb + nc - 1) / nc, cs = 1u << cb;
+        const u32 W_FC = 4, W_SC = 4 + nc, W_EQD = 4 + 2 * nc, W_CHEQ = 4 + 3 * nc, W_INT = 4 + 4 * nc, W_BITS = 4 + 5 * nc;
+        u64 fcomb = 0, scomb = 0;
+        for (int i = (int)nc - 1; i >= 0; i--) {
+            fcomb = gl_add(gl_mul_small(fcomb, cs), w(W_FC + i));
+            scomb = gl_add(gl_mul_small(scomb, cs), w(W_SC + i));
+        }
+        sink.emit(gl_sub(fcomb, w(0)));
+        sink.emit(gl_sub(scomb, w(1)));
+        u64 msd = 0;
+        for (u32 i = 0; i < nc; i++) {
+            u64 f = w(W_FC + i), s = w(W_SC + i);
+            sink.emit(limb_range_product(f, cs));
+            sink.emit(limb_range_product(s, cs));
+            u64 diff = gl_sub(s, f);
+            u64 eqd = w(W_EQD + i), cheq = w(W_CHEQ + i), inter = w(W_INT + i);
+            sink.emit(gl_sub(gl_mul(diff, eqd), gl_sub(1, cheq)));
+            sink.emit(gl_mul(cheq, diff));
+            sink.emit(gl_sub(inter, gl_mul(cheq, msd)));
+            msd = gl_add(inter, gl_mul(gl_sub(1, cheq), diff));
+        }
+        sink.emit(gl_sub(w(3), msd));
+        u64 bcomb = 0;
+        for (u32 i = 0; i <= cb; i++) {
+            u64 b = w(W_BITS + i);
+            sink.emit(gl_mul(b, gl_sub(1, b)));
+        }
+        for (int i = (int)cb; i >= 0; i--) bcomb = gl_add(gl_dbl(bcomb), w(W_BITS + i));
+        sink.emit(gl_sub(gl_add(w(3), cs), bcomb));
+        sink.emit(gl_sub(w(2), w(W_BITS + cb)));
+        break;
+    }
+    default:
+        break;
+    }
+}
+
+// filter_g(s) = prod_{i in group, i != row} (i - s) * [several selectors: (UNUSED_SELECTOR - s)]   (plonky2 gates/gate.rs)
+__device__ __forceinline__ u64 gate_filter(const GateDev& g, u32 row, u64 s, bool many_selectors) {
+    u64 r = 1;
+    for (u32 i = g.group_lo; i < g.group_hi; i++)
+        if (i != row) r = gl_mul(r, gl_sub((u64)i, s));
+    if (many_selectors) r = gl_mul(r, gl_sub(0xFFFFFFFFULL, s));
+    return r;
+}

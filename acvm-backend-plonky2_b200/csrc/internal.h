@@ -1,0 +1,116 @@
+// Internal interfaces of libp2g (not part of the C ABI in include/p2g.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/p2g.h"
+#include "hash.cuh"
+
+struct p2g_error : std::runtime_error {
+    int code;
+    p2g_error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                                                              \
+    do {                                                                                                              \
+        cudaError_t e__ = (expr);                                                                                     \
+        if (e__ != cudaSuccess)                                                                                       \
+            throw p2g_error(e__ == cudaErrorMemoryAllocation ? P2G_ENOMEM : P2G_ECUDA,                                \
+                            std::string(#expr) + ": " + cudaGetErrorString(e__));                                     \
+    } while (0)
+
+// Owning device buffer
+template <class T>
+struct dbuf {
+    T* p = nullptr;
+    size_t n = 0;
+    dbuf() {}
+    explicit dbuf(size_t count) { alloc(count); }
+    dbuf(const dbuf&) = delete;
+    dbuf& operator=(const dbuf&) = delete;
+    dbuf(dbuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    dbuf& operator=(dbuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~dbuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        if (count) CUDA_CHECK(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+// Per-device context: one stream, cached twiddle / twist / coset-power tables, launch counters and stage timers.
+struct DevCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    // key: (log size, inverse) -> omega_{2^log}^{+-j}, j < 2^(log-1)        (smem-staged butterfly table)
+    std::map<std::pair<int, int>, dbuf<u64>> tw;
+    // key: (log B, inverse) -> [lo table 2^split | hi table 2^(b-split)] of omega_B^{+-k}   (twist between passes)
+    std::map<std::pair<int, int>, dbuf<u64>> twist;
+    // key: (log n, base, premul) -> [lo 2^split | hi 2^(n-split)] of premul * base^i        (coset scaling)
+    std::map<std::tuple<int, u64, u64>, dbuf<u64>> powtab;
+    // accounting of the current prove call
+    unsigned launches = 0;
+    double ntt_bytes = 0, merkle_bytes = 0;
+    float ntt_ms = 0, merkle_ms = 0;
+    bool timing = false;  // when set, NTT / Merkle entry points bracket themselves with events (adds syncs)
+
+    const u64* get_tw(int log, bool inverse);
+    const u64* get_twist(int logB, bool inverse, int* split);
+    const u64* get_powtab(int logn, u64 base, u64 premul, int* split);
+};
+DevCtx* get_ctx(int device);
+
+struct StageTimer {  // RAII: accumulates elapsed ms of a stream segment into *acc when ctx->timing is on
+    DevCtx* c;
+    float* acc;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(DevCtx* ctx, float* accum);
+    ~StageTimer();
+};
+
+// ---- ntt.cu: transforms over column-major batches (column c at base + c*col_stride) ----
+// values on <omega_N> in natural order -> coefficients in natural order (PolynomialValues::ifft)
+void ntt_ifft(DevCtx* c, const u64* d_values, size_t in_cs, u64* d_coeffs, size_t out_cs, int logn, int ncols);
+// coefficients (natural, N) -> values on shift*<omega_{N<<rate_bits}> in LEAF order (index j <-> point shift*omega^bitrev(j))
+// (PolynomialBatch::lde_values followed by reverse_index_bits_in_place)
+void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t out_cs, int logn, int rate_bits, int ncols,
+             u64 shift);
+// leaf-order values on shift*<omega_N> -> natural coefficients, in place (coset_ifft)
+void ntt_coset_ifft_leaforder(DevCtx* c, u64* d_data, size_t cs, int logn, int ncols, u64 shift);
+
+// ---- merkle.cu ----
+struct MerkleTree {
+    int log_leaves = 0, cap_height = 0, hasher = 0;
+    // levels[0] = leaf digests (2^log_leaves), levels[k] = 2^(log_leaves-k) digests, last level = cap
+    std::vector<dbuf<digest_t>> levels;
+    const digest_t* cap() const { return levels.back().p; }
+    int ncap() const { return 1 << cap_height; }
+};
+// leaves: column-major [ncols][nleaves] (leaf j = {col_0[j], col_1[j], ...}); interleave2: leaf = `ncols/2` consecutive
+// (c0,c1) pairs taken from two columns re/im at positions [j*ncols/2, (j+1)*ncols/2)  (FRI layer leaves)
+void merkle_build(DevCtx* c, MerkleTree* t, const u64* d_leaves, size_t col_stride, int log_leaves, int ncols,
+                  int cap_height, int hasher, bool fri_layout = false);
+
+// ---- launch helper ----
+inline void count_launch(DevCtx* c, unsigned n = 1) { c->launches += n; }
+
+// ---- ctx.cu ----
+void set_last_error(const std::string& s);
+int guard(const std::function<void()>& f);  // runs f, maps exceptions to P2G_* codes + p2g_last_error
+void pack_digests(int hasher, const digest_t* src, size_t n, uint8_t* dst);

@@ -1,0 +1,527 @@
+// Goldilocks NTT / LDE kernels for sm_100a.
+//
+// Replaces plonky2_field 0.2.2 fft.rs (fft_classic / ifft) and plonky2 fri/oracle.rs PolynomialBatch::{from_values,lde_values},
+// reached from the reference at plonky2-backend/src/actions/prove_action.rs:96.
+//
+// Design (B200-first, not a translation of the radix-2 CPU loop):
+//  * column-major batches, one grid covers every column (grid.y) and every LDE coset (grid.z) of a commitment;
+//  * a transform of size 2^n is split into <= 3 passes; each pass moves a [A x Q] tile (A = sub-transform length, Q = 64-byte
+//    runs of consecutive elements, so strided passes still read/write whole sectors) into shared memory, runs log2(A)
+//    butterfly stages there, applies the inter-pass twist on the way out and writes the tile back -- HBM sees each element
+//    once per pass;
+//  * the per-stage twiddle tile (stage-major, conflict-free) is staged into shared memory by a TMA bulk copy
+//    (cp.async.bulk + mbarrier) overlapped with the tile load;
+//  * forward transforms are decimation-in-frequency (natural in -> bit-reversed out), which IS plonky2's leaf order, so the
+//    reference's transpose + reverse_index_bits pass disappears; the rate-8 LDE is 8 independent size-N coset transforms
+//    (leaves [r*N,(r+1)*N) = coset shift*omega_{8N}^{bitrev3(r)}), never a zero-padded size-8N transform;
+//  * inverse transforms are decimation-in-time (bit-reversed in -> natural out); for natural-order input (the witness) the
+//    first pass gathers bit-reversed 64-byte runs, so no separate permutation pass exists either.
+#include "internal.h"
+
+namespace {
+
+struct PassArgs {
+    const u64* in;
+    u64* out;
+    size_t in_cs, out_cs;      // column strides (elements)
+    size_t in_zs, out_zs;      // per-coset (grid.z) offsets (elements)
+    int logn;                  // column transform length
+    int logB;                  // strided pass: current block length (A * S)
+    int loga;                  // sub-transform length A
+    int logq;                  // strided: tile width Q; contiguous: log2(blocks per tile)
+    const u64* tw;             // stage-major twiddles of size A: stage u at offset A - (A >> u), (A >> (u+1)) entries
+    const u64* twist;          // [lo 2^split | hi] of omega_B^{+-k}, or null
+    int twist_split;
+    const u64* stab;           // [lo 2^split | hi] index-power table applied on load (forward) / store (inverse), or null
+    int stab_split;
+    size_t stab_zs;            // per-coset table stride
+    u64 scale;                 // constant multiplier on store (1 = none)
+    int gather;                // contiguous inverse pass: input is in natural order, gather bit-reversed runs
+};
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+// TMA bulk copy global -> shared of the twiddle tile, completion on an mbarrier (SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ void tma_load_tw(u64* dst, const u64* src, u32 bytes, u64* mbar) {
+    u32 bar = smem_u32(mbar), d = smem_u32(dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(u64* mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* mbar, u32 phase) {
+    u32 bar = smem_u32(mbar), ok = 0;
+    for (int spin = 0; spin < (1 << 26) && !ok; spin++) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(bar), "r"(phase)
+            : "memory");
+    }
+    if (!ok) __trap();
+}
+
+// stage the twiddle tile: TMA when it is at least 16 bytes, plain loads otherwise
+__device__ __forceinline__ void stage_tw_begin(u64* s_tw, const u64* g_tw, int A, u64* mbar) {
+    if (A >= 4) {
+        if (threadIdx.x == 0) mbar_init(mbar);
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_tw(s_tw, g_tw, (u32)(A * 8), mbar);
+    } else {
+        if (threadIdx.x < A) s_tw[threadIdx.x] = g_tw[threadIdx.x];
+    }
+}
+__device__ __forceinline__ void stage_tw_end(int A, u64* mbar) {
+    if (A >= 4) mbar_wait(mbar, 0);
+    __syncthreads();
+}
+
+__device__ __forceinline__ u64 tab_pow(const u64* tab, int split, u32 i) {
+    u64 lo = __ldg(tab + (i & ((1u << split) - 1)));
+    u64 hi = __ldg(tab + (1u << split) + (i >> split));
+    return gl_mul(lo, hi);
+}
+
+// log2(A) butterfly stages over `rows` independent rows; element (m, r) lives at s[m * sm_m + r * sm_r]
+template <bool INV>
+__device__ __forceinline__ void smem_butterflies(u64* s, const u64* s_tw, int loga, int logr, int sm_m, int sm_r, bool r_fast) {
+    const int A = 1 << loga;
+    const int total = (A >> 1) << logr;
+    for (int st = 0; st < loga; st++) {
+        const int u = INV ? (loga - 1 - st) : st;
+        const int lh = loga - 1 - u;  // log2(half)
+        const int half = 1 << lh;
+        const u64* twu = s_tw + (A - (A >> u));
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            int p, r;
+            if (r_fast) {
+                r = e & ((1 << logr) - 1);
+                p = e >> logr;
+            } else {
+                p = e & ((A >> 1) - 1);
+                r = e >> (loga - 1);
+            }
+            int j = p & (half - 1);
+            int lo = ((p >> lh) << (lh + 1)) | j;
+            u64* x0 = s + lo * sm_m + r * sm_r;
+            u64* x1 = x0 + half * sm_m;
+            u64 a = *x0, b = *x1, w = twu[j];
+            if (INV) {
+                b = gl_mul(b, w);
+                *x0 = gl_add(a, b);
+                *x1 = gl_sub(a, b);
+            } else {
+                *x0 = gl_add(a, b);
+                *x1 = gl_mul(gl_sub(a, b), w);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Strided pass: tile [A][Q], element (m, qq) at column index blk*B + m*S + q0 + qq.
+template <bool INV>
+__global__ void __launch_bounds__(512) k_pass_strided(PassArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const int A = 1 << a.loga, Q = 1 << a.logq;
+    const int logS = a.logB - a.loga;
+    u64* s_tw = sm + (A << a.logq);
+    u64* mbar = s_tw + A;
+    const u32 tiles_per_blk = 1u << (logS - a.logq);
+    const u32 blk = blockIdx.x / tiles_per_blk;
+    const u32 q0 = (blockIdx.x % tiles_per_blk) << a.logq;
+    const u64* in = a.in + (size_t)blockIdx.y * a.in_cs + (size_t)blockIdx.z * a.in_zs;
+    u64* out = a.out + (size_t)blockIdx.y * a.out_cs + (size_t)blockIdx.z * a.out_zs;
+    const u64* stab = a.stab ? a.stab + (size_t)blockIdx.z * a.stab_zs : nullptr;
+    const size_t base = ((size_t)blk << a.logB) + q0;
+
+    stage_tw_begin(s_tw, a.tw, A, mbar);
+    const int total = A << a.logq;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        int qq = e & (Q - 1), m = e >> a.logq;
+        size_t idx = base + ((size_t)m << logS) + qq;
+        u64 v = in[idx];
+        if (!INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
+        if (INV && a.twist) v = gl_mul(v, tab_pow(a.twist, a.twist_split, (q0 + qq) * bitrev32(m, a.loga)));
+        sm[e] = v;
+    }
+    stage_tw_end(A, mbar);
+    smem_butterflies<INV>(sm, s_tw, a.loga, a.logq, Q, 1, true);
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        int qq = e & (Q - 1), m = e >> a.logq;
+        size_t idx = base + ((size_t)m << logS) + qq;
+        u64 v = sm[e];
+        if (!INV && a.twist) v = gl_mul(v, tab_pow(a.twist, a.twist_split, (q0 + qq) * bitrev32(m, a.loga)));
+        if (INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
+        if (a.scale != 1) v = gl_mul(v, a.scale);
+        out[idx] = v;
+    }
+}
+
+// Contiguous pass: tile = 2^logq consecutive blocks of A elements (rows padded by one word when there are several).
+template <bool INV>
+__global__ void __launch_bounds__(512) k_pass_contig(PassArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const int A = 1 << a.loga, NB = 1 << a.logq;
+    const int AP = A + (NB > 1 ? 1 : 0);
+    u64* s_tw = sm + ((NB * AP + 1) & ~1);
+    u64* mbar = s_tw + A;
+    const u64* in = a.in + (size_t)blockIdx.y * a.in_cs + (size_t)blockIdx.z * a.in_zs;
+    u64* out = a.out + (size_t)blockIdx.y * a.out_cs + (size_t)blockIdx.z * a.out_zs;
+    const u64* stab = a.stab ? a.stab + (size_t)blockIdx.z * a.stab_zs : nullptr;
+    const int lognb = a.logn - a.loga;  // log2(#blocks in the column)
+    const u32 c0 = blockIdx.x << a.logq;
+
+    stage_tw_begin(s_tw, a.tw, A, mbar);
+    const int total = A << a.logq;
+    if (INV && a.gather) {
+        // virtual bit-reversed array: block b = bitrev(c), element m' <- natural index bitrev_a(m') * (N/A) + c
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            int c = e & (NB - 1), m = e >> a.logq;
+            size_t idx = ((size_t)bitrev32(m, a.loga) << lognb) + c0 + c;
+            sm[c * AP + m] = in[idx];
+        }
+    } else {
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            int bb = e >> a.loga, m = e & (A - 1);
+            size_t idx = ((size_t)(c0 + bb) << a.loga) + m;
+            u64 v = in[idx];
+            if (!INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
+            sm[bb * AP + m] = v;
+        }
+    }
+    stage_tw_end(A, mbar);
+    smem_butterflies<INV>(sm, s_tw, a.loga, a.logq, 1, AP, false);
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        int bb = e >> a.loga, m = e & (A - 1);
+        u32 blk = (INV && a.gather) ? bitrev32(c0 + bb, lognb) : (c0 + bb);
+        size_t idx = ((size_t)blk << a.loga) + m;
+        u64 v = sm[bb * AP + m];
+        if (INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
+        if (a.scale != 1) v = gl_mul(v, a.scale);
+        out[idx] = v;
+    }
+}
+
+// out[i] = premul * base^(i * step) for i < n
+__global__ void k_fill_pow(u64* out, u32 n, u64 base, u64 step, u64 premul) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = gl_mul(premul, gl_pow(base, (u64)i * step));
+}
+// stage-major twiddle tile of size A = 2^loga: stage u holds root^(j << u), j < A >> (u+1)
+__global__ void k_fill_tw(u64* out, int loga, u64 root) {
+    int A = 1 << loga;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    if (i == A - 1) {
+        out[i] = 0;
+        return;
+    }
+    // find stage u with A - (A >> u) <= i < A - (A >> (u+1))
+    int u = 0;
+    while (i >= A - (A >> (u + 1))) u++;
+    int j = i - (A - (A >> u));
+    out[i] = gl_pow(root, (u64)j << u);
+}
+
+const int MAX_CONTIG_LOG = 11;
+const int MAX_STRIDED_LOG = 10;
+
+// forward-order pass plan: strided passes (largest block first) then one contiguous pass
+std::vector<int> make_plan(int logn) {
+    std::vector<int> plan;
+    if (logn <= MAX_CONTIG_LOG) {
+        plan.push_back(logn);
+        return plan;
+    }
+    int last = 10;
+    int rem = logn - last;
+    int cnt = (rem + MAX_STRIDED_LOG - 1) / MAX_STRIDED_LOG;
+    for (int i = 0; i < cnt; i++) {
+        int a = (rem + (cnt - i) - 1) / (cnt - i);
+        plan.push_back(a);
+        rem -= a;
+    }
+    plan.push_back(last);
+    return plan;
+}
+
+size_t strided_smem(int loga, int logq) { return ((size_t)(1 << loga) << logq) * 8 + (size_t)(1 << loga) * 8 + 16; }
+size_t contig_smem(int loga, int logq) {
+    int A = 1 << loga, NB = 1 << logq, AP = A + (NB > 1 ? 1 : 0);
+    return (size_t)((NB * AP + 1) & ~1) * 8 + (size_t)A * 8 + 16;
+}
+
+void set_smem_attrs() {
+    static bool done = false;
+    if (done) return;
+    const int lim = 160 * 1024;
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    done = true;
+}
+
+int pick_threads(size_t tile_elems) { return tile_elems >= 8192 ? 512 : (tile_elems >= 512 ? 256 : 64); }
+
+// run the passes of one direction.  fwd: in -> out (first pass), then in place on out.
+struct XformDesc {
+    const u64* in;
+    size_t in_cs, in_zs;
+    u64* out;
+    size_t out_cs, out_zs;
+    int logn, ncols, nz;
+    const u64* stab;
+    int stab_split;
+    size_t stab_zs;
+    u64 scale;
+    bool natural_input;  // inverse only
+};
+
+void run_forward(DevCtx* c, const XformDesc& d) {
+    set_smem_attrs();
+    std::vector<int> plan = make_plan(d.logn);
+    int done = 0;
+    for (size_t pi = 0; pi < plan.size(); pi++) {
+        bool first = pi == 0, last = pi + 1 == plan.size();
+        PassArgs a = {};
+        a.in = first ? d.in : d.out;
+        a.in_cs = first ? d.in_cs : d.out_cs;
+        a.in_zs = first ? d.in_zs : d.out_zs;
+        a.out = d.out;
+        a.out_cs = d.out_cs;
+        a.out_zs = d.out_zs;
+        a.logn = d.logn;
+        a.loga = plan[pi];
+        a.tw = c->get_tw(a.loga, false);
+        a.scale = 1;
+        if (first) {
+            a.stab = d.stab;
+            a.stab_split = d.stab_split;
+            a.stab_zs = d.stab_zs;
+        }
+        if (!last) {
+            a.logB = d.logn - done;
+            int logS = a.logB - a.loga;
+            a.logq = std::min(logS, std::max(3, 12 - a.loga));
+            a.twist = c->get_twist(a.logB, false, &a.twist_split);
+            size_t tiles = (size_t)1 << (d.logn - a.loga - a.logq);
+            dim3 grid((unsigned)tiles, d.ncols, d.nz);
+            int th = pick_threads((size_t)1 << (a.loga + a.logq));
+            k_pass_strided<false><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
+        } else {
+            int lognb = d.logn - a.loga;
+            a.logq = std::min(lognb, std::max(0, 12 - a.loga));
+            size_t tiles = (size_t)1 << (lognb - a.logq);
+            dim3 grid((unsigned)tiles, d.ncols, d.nz);
+            int th = pick_threads((size_t)1 << (a.loga + a.logq));
+            k_pass_contig<false><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
+        }
+        count_launch(c);
+        done += plan[pi];
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void run_inverse(DevCtx* c, const XformDesc& d) {
+    set_smem_attrs();
+    std::vector<int> plan = make_plan(d.logn);
+    int np = (int)plan.size();
+    // inverse order: contiguous pass first, then strided passes with growing blocks
+    int done = 0;
+    for (int pi = np - 1; pi >= 0; pi--) {
+        bool first = pi == np - 1, last = pi == 0;
+        PassArgs a = {};
+        a.in = first ? d.in : d.out;
+        a.in_cs = first ? d.in_cs : d.out_cs;
+        a.in_zs = first ? d.in_zs : d.out_zs;
+        a.out = d.out;
+        a.out_cs = d.out_cs;
+        a.out_zs = d.out_zs;
+        a.logn = d.logn;
+        a.loga = plan[pi];
+        a.tw = c->get_tw(a.loga, true);
+        a.scale = last ? d.scale : 1;
+        if (last) {
+            a.stab = d.stab;
+            a.stab_split = d.stab_split;
+            a.stab_zs = d.stab_zs;
+        }
+        if (first) {
+            int lognb = d.logn - a.loga;
+            a.gather = d.natural_input ? 1 : 0;
+            int want = a.gather ? 3 : 0;
+            a.logq = std::min(lognb, std::max(want, 12 - a.loga));
+            size_t tiles = (size_t)1 << (lognb - a.logq);
+            dim3 grid((unsigned)tiles, d.ncols, d.nz);
+            int th = pick_threads((size_t)1 << (a.loga + a.logq));
+            k_pass_contig<true><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
+        } else {
+            a.logB = done + a.loga;
+            int logS = a.logB - a.loga;
+            a.logq = std::min(logS, std::max(3, 12 - a.loga));
+            a.twist = c->get_twist(a.logB, true, &a.twist_split);
+            size_t tiles = (size_t)1 << (d.logn - a.loga - a.logq);
+            dim3 grid((unsigned)tiles, d.ncols, d.nz);
+            int th = pick_threads((size_t)1 << (a.loga + a.logq));
+            k_pass_strided<true><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
+        }
+        count_launch(c);
+        done += plan[pi];
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// table caches
+// ---------------------------------------------------------------------------------------------------------------------
+const u64* DevCtx::get_tw(int log, bool inverse) {
+    auto key = std::make_pair(log, (int)inverse);
+    auto it = tw.find(key);
+    if (it != tw.end()) return it->second.p;
+    int A = 1 << log;
+    dbuf<u64> t((size_t)std::max(A, 2));
+    u64 root = gl_root_of_unity(log);
+    if (inverse) root = gl_inv(root);
+    k_fill_tw<<<(A + 255) / 256, 256, 0, stream>>>(t.p, log, root);
+    CUDA_CHECK(cudaGetLastError());
+    const u64* p = t.p;
+    tw.emplace(key, std::move(t));
+    return p;
+}
+
+const u64* DevCtx::get_twist(int logB, bool inverse, int* split) {
+    int sp = (logB + 1) / 2;
+    *split = sp;
+    auto key = std::make_pair(logB, (int)inverse);
+    auto it = twist.find(key);
+    if (it != twist.end()) return it->second.p;
+    u32 nlo = 1u << sp, nhi = 1u << (logB - sp);
+    dbuf<u64> t((size_t)nlo + nhi);
+    u64 root = gl_root_of_unity(logB);
+    if (inverse) root = gl_inv(root);
+    k_fill_pow<<<(nlo + 255) / 256, 256, 0, stream>>>(t.p, nlo, root, 1, 1);
+    k_fill_pow<<<(nhi + 255) / 256, 256, 0, stream>>>(t.p + nlo, nhi, root, (u64)nlo, 1);
+    CUDA_CHECK(cudaGetLastError());
+    const u64* p = t.p;
+    twist.emplace(key, std::move(t));
+    return p;
+}
+
+const u64* DevCtx::get_powtab(int logn, u64 base, u64 premul, int* split) {
+    int sp = (logn + 1) / 2;
+    *split = sp;
+    auto key = std::make_tuple(logn, base, premul);
+    auto it = powtab.find(key);
+    if (it != powtab.end()) return it->second.p;
+    u32 nlo = 1u << sp, nhi = 1u << (logn - sp);
+    dbuf<u64> t((size_t)nlo + nhi);
+    k_fill_pow<<<(nlo + 255) / 256, 256, 0, stream>>>(t.p, nlo, base, 1, 1);
+    k_fill_pow<<<(nhi + 255) / 256, 256, 0, stream>>>(t.p + nlo, nhi, base, (u64)nlo, premul);
+    CUDA_CHECK(cudaGetLastError());
+    const u64* p = t.p;
+    powtab.emplace(key, std::move(t));
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// public transforms
+// ---------------------------------------------------------------------------------------------------------------------
+void ntt_ifft(DevCtx* c, const u64* d_values, size_t in_cs, u64* d_coeffs, size_t out_cs, int logn, int ncols) {
+    if (ncols <= 0) return;
+    StageTimer tm(c, &c->ntt_ms);
+    XformDesc d = {};
+    d.in = d_values;
+    d.in_cs = in_cs;
+    d.out = d_coeffs;
+    d.out_cs = out_cs;
+    d.logn = logn;
+    d.ncols = ncols;
+    d.nz = 1;
+    d.scale = gl_inv((u64)1 << logn);
+    d.natural_input = true;
+    if (logn == 0) {
+        CUDA_CHECK(cudaMemcpy2DAsync(d_coeffs, out_cs * 8, d_values, in_cs * 8, 8, ncols, cudaMemcpyDeviceToDevice, c->stream));
+        return;
+    }
+    run_inverse(c, d);
+    c->ntt_bytes += 16.0 * (double)((size_t)1 << logn) * ncols;
+}
+
+void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t out_cs, int logn, int rate_bits, int ncols,
+             u64 shift) {
+    if (ncols <= 0) return;
+    StageTimer tm(c, &c->ntt_ms);
+    const int nz = 1 << rate_bits;
+    const size_t n = (size_t)1 << logn;
+    // per-coset index-power tables: coset z covers leaves [z*N, (z+1)*N) = shift * omega_{N*nz}^{bitrev(z)} * <omega_N>
+    int split = (logn + 1) / 2;
+    size_t tab_len = ((size_t)1 << split) + ((size_t)1 << (logn - split));
+    u64 wl = gl_root_of_unity(logn + rate_bits);
+    // one contiguous buffer holding the nz tables, cached under (logn, shift, rate_bits marker)
+    auto key = std::make_tuple(logn + 64 * (rate_bits + 1), shift, (u64)0);
+    const u64* tabs;
+    {
+        auto it = c->powtab.find(key);
+        if (it == c->powtab.end()) {
+            dbuf<u64> t(tab_len * nz);
+            for (int z = 0; z < nz; z++) {
+                u64 s = gl_mul(shift, gl_pow(wl, bitrev32((u32)z, rate_bits)));
+                u32 nlo = 1u << split, nhi = 1u << (logn - split);
+                k_fill_pow<<<(nlo + 255) / 256, 256, 0, c->stream>>>(t.p + z * tab_len, nlo, s, 1, 1);
+                k_fill_pow<<<(nhi + 255) / 256, 256, 0, c->stream>>>(t.p + z * tab_len + nlo, nhi, s, (u64)nlo, 1);
+            }
+            CUDA_CHECK(cudaGetLastError());
+            it = c->powtab.emplace(key, std::move(t)).first;
+        }
+        tabs = it->second.p;
+    }
+    XformDesc d = {};
+    d.in = d_coeffs;
+    d.in_cs = in_cs;
+    d.in_zs = 0;
+    d.out = d_lde;
+    d.out_cs = out_cs;
+    d.out_zs = n;
+    d.logn = logn;
+    d.ncols = ncols;
+    d.nz = nz;
+    d.stab = tabs;
+    d.stab_split = split;
+    d.stab_zs = tab_len;
+    d.scale = 1;
+    if (logn == 0) {
+        // constant polynomials: every coset value equals the coefficient
+        for (int z = 0; z < nz; z++)
+            CUDA_CHECK(cudaMemcpy2DAsync(d_lde + z, out_cs * 8, d_coeffs, in_cs * 8, 8, ncols, cudaMemcpyDeviceToDevice, c->stream));
+        return;
+    }
+    run_forward(c, d);
+    c->ntt_bytes += (8.0 + 8.0 * nz) * (double)n * ncols;
+}
+
+void ntt_coset_ifft_leaforder(DevCtx* c, u64* d_data, size_t cs, int logn, int ncols, u64 shift) {
+    if (ncols <= 0 || logn == 0) return;
+    StageTimer tm(c, &c->ntt_ms);
+    XformDesc d = {};
+    d.in = d_data;
+    d.in_cs = cs;
+    d.out = d_data;
+    d.out_cs = cs;
+    d.logn = logn;
+    d.ncols = ncols;
+    d.nz = 1;
+    d.natural_input = false;
+    d.scale = 1;
+    // coefficient i is multiplied by shift^-i / N
+    d.stab = c->get_powtab(logn, gl_inv(shift), gl_inv((u64)1 << logn), &d.stab_split);
+    run_inverse(c, d);
+    c->ntt_bytes += 16.0 * (double)((size_t)1 << logn) * ncols;
+}

@@ -1,0 +1,168 @@
+// Vanishing-polynomial / quotient evaluation on the LDE coset, sm_100a: one thread per LDE point, every constraint folded
+// into the two alpha-weighted sums as it is produced (no per-point constraint vector), then divided by Z_H.
+//
+// Replaces plonky2 0.2.2 plonk/prover.rs compute_quotient_polys + plonk/vanishing_poly.rs eval_vanishing_poly_base_batch +
+// evaluate_gate_constraints_base_batch, which call back into the reference's custom gates
+// (plonky2-backend/src/plonky2_ecdsa/biguint/gates/*.rs; see gates.cuh).  SURVEY.md App. A.8.
+//
+// Reads are column-major in leaf order: thread j touches [col][j], so every wire / constant / sigma / Z column load of a
+// warp is one coalesced 256-byte run.  "next row" of Z is index +8 in natural order = same coset, bit-reversed neighbour.
+#include "gates.cuh"
+#include "internal.h"
+#include "quotient.h"
+
+__constant__ QuotientParams d_qp;
+
+namespace {
+
+struct WeightedSink {  // folds constraint k into sum_c += v * alpha_c^(off + k)
+    u64 s0, s1;
+    int k;
+    __device__ __forceinline__ void emit(u64 v) {
+        s0 = gl_add(s0, gl_mul(v, d_qp.apow[0][k]));
+        s1 = gl_add(s1, gl_mul(v, d_qp.apow[1][k]));
+        k++;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_quotient(const u64* __restrict__ cs, const u64* __restrict__ wires,
+                                                  const u64* __restrict__ zpp, const u64* __restrict__ xs,
+                                                  const u64* __restrict__ l0s, u64* __restrict__ out, size_t j0, size_t count) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const QuotientParams& P = d_qp;
+    const size_t j = j0 + t;
+    const size_t L = (size_t)1 << (P.logn + P.rate_bits);
+    const int NC = P.num_challenges, NPP = P.num_partial_products, R = P.num_routed, C = P.num_constants;
+    const int nzp = NC * (1 + NPP);
+    // next row: natural index + 2^rate_bits  <=>  same coset, k -> k + 1 (k = bitrev_n(j mod N))
+    const u32 nmask = (1u << P.logn) - 1;
+    const u32 k = bitrev32((u32)j & nmask, P.logn);
+    const size_t jn = (j & ~(size_t)nmask) | bitrev32((k + 1) & nmask, P.logn);
+    const u64 x = xs[j];
+    u64 acc[2] = {0, 0};
+
+    // L_0(x) (Z_c(x) - 1)
+    {
+        const u64 l0 = l0s[j];
+        for (int c = 0; c < NC; c++) {
+            u64 tz = gl_mul(l0, gl_sub(zpp[(size_t)c * L + j], 1));
+            acc[0] = gl_add(acc[0], gl_mul(tz, P.apow[0][c]));
+            acc[1] = gl_add(acc[1], gl_mul(tz, P.apow[1][c]));
+        }
+    }
+    // partial products: prev * prod(num) - next * prod(den) per chunk of `qdf` routed wires
+    {
+        const int chunk = P.qdf;
+        for (int c = 0; c < NC; c++) {
+            u64 prev = zpp[(size_t)c * L + j];
+            const u64 gamma = P.gammas[c], beta = P.betas[c];
+            int term = NC + c * (NPP + 1);
+            for (int m = 0; m <= NPP; m++) {
+                u64 pn = 1, pd = 1;
+                int hi = min((m + 1) * chunk, R);
+                for (int r = m * chunk; r < hi; r++) {
+                    u64 wv = wires[(size_t)r * L + j];
+                    u64 sg = cs[(size_t)(C + r) * L + j];
+                    u64 base = gl_add(wv, gamma);
+                    pn = gl_mul(pn, gl_add(base, gl_mul(P.beta_k[c][r], x)));
+                    pd = gl_mul(pd, gl_add(base, gl_mul(beta, sg)));
+                }
+                u64 next = (m < NPP) ? zpp[(size_t)(NC + c * NPP + m) * L + j] : zpp[(size_t)c * L + jn];
+                u64 tv = gl_sub(gl_mul(prev, pn), gl_mul(next, pd));
+                acc[0] = gl_add(acc[0], gl_mul(tv, P.apow[0][term + m]));
+                acc[1] = gl_add(acc[1], gl_mul(tv, P.apow[1][term + m]));
+                prev = next;
+            }
+        }
+    }
+    // gate constraints
+    {
+        const int off = NC + NC * (NPP + 1);
+        auto wire = [&](int i) -> u64 { return wires[(size_t)i * L + j]; };
+        auto konst = [&](int i) -> u64 { return cs[(size_t)(P.num_selectors + i) * L + j]; };
+        const bool many = P.num_selectors > 1;
+        for (int g = 0; g < P.num_gates; g++) {
+            const GateDev& gd = P.gates[g];
+            if (gd.num_constraints == 0) continue;
+            u64 f = gate_filter(gd, g, cs[(size_t)gd.selector_index * L + j], many);
+            WeightedSink sink = {0, 0, off};
+            eval_gate_unfiltered(gd, wire, konst, P.pi_hash, sink);
+            acc[0] = gl_add(acc[0], gl_mul(f, sink.s0));
+            acc[1] = gl_add(acc[1], gl_mul(f, sink.s1));
+        }
+    }
+    const u64 zhi = P.zh_inv[bitrev32((u32)(j >> P.logn), P.rate_bits)];
+    for (int c = 0; c < NC; c++) out[(size_t)c * L + j] = gl_mul(acc[c], zhi);
+}
+
+struct StoreSink {  // stand-alone entry point: out[k][pt] += filter * constraint_k
+    u64* out;
+    size_t np, pt;
+    u64 filter;
+    int k;
+    __device__ __forceinline__ void emit(u64 v) {
+        u64* o = out + (size_t)k * np + pt;
+        *o = gl_add(*o, gl_mul(v, filter));
+        k++;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_eval_gates(const u64* __restrict__ consts, const u64* __restrict__ wires, u64* out,
+                                                    size_t np) {
+    size_t pt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= np) return;
+    const QuotientParams& P = d_qp;
+    auto wire = [&](int i) -> u64 { return wires[(size_t)i * np + pt]; };
+    auto konst = [&](int i) -> u64 { return consts[(size_t)(P.num_selectors + i) * np + pt]; };
+    const bool many = P.num_selectors > 1;
+    for (int g = 0; g < P.num_gates; g++) {
+        const GateDev& gd = P.gates[g];
+        StoreSink sink = {out, np, pt, gate_filter(gd, g, consts[(size_t)gd.selector_index * np + pt], many), 0};
+        eval_gate_unfiltered(gd, wire, konst, P.pi_hash, sink);
+    }
+}
+
+// x_j = shift * omega_{8N}^{bitrev(j)} and L_0(x_j) = (x_j^N - 1) / (N (x_j - 1)) for every leaf j, once per circuit
+__global__ void k_points(u64* xs, u64* l0s, int logn, int rate_bits, u64 shift, u64 w_lde, u64 n_as_field, const u64* zh) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t L = (size_t)1 << (logn + rate_bits);
+    if (j >= L) return;
+    u64 x = gl_mul(shift, gl_pow(w_lde, bitrev32((u32)j, logn + rate_bits)));
+    xs[j] = x;
+    u64 z = zh[bitrev32((u32)(j >> logn), rate_bits)];
+    l0s[j] = gl_mul(z, gl_inv(gl_mul(n_as_field, gl_sub(x, 1))));
+}
+
+}  // namespace
+
+void quotient_upload_params(DevCtx* c, const QuotientParams& p) {
+    CUDA_CHECK(cudaMemcpyToSymbolAsync(d_qp, &p, sizeof(QuotientParams), 0, cudaMemcpyHostToDevice, c->stream));
+}
+
+void quotient_points(DevCtx* c, u64* d_xs, u64* d_l0s, int logn, int rate_bits, const u64* h_zh) {
+    size_t L = (size_t)1 << (logn + rate_bits);
+    dbuf<u64> zh(1 << rate_bits);
+    CUDA_CHECK(cudaMemcpyAsync(zh.p, h_zh, 8 << rate_bits, cudaMemcpyHostToDevice, c->stream));
+    k_points<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(d_xs, d_l0s, logn, rate_bits, GL_GEN,
+                                                                  gl_root_of_unity(logn + rate_bits), ((u64)1 << logn) % GL_P,
+                                                                  zh.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    count_launch(c);
+}
+
+void quotient_eval(DevCtx* c, const u64* d_cs, const u64* d_wires, const u64* d_zpp, const u64* d_xs, const u64* d_l0s,
+                   u64* d_out, size_t j0, size_t count) {
+    const int TH = 128;
+    k_quotient<<<(unsigned)((count + TH - 1) / TH), TH, 0, c->stream>>>(d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, j0, count);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch(c);
+}
+
+void gates_eval_standalone(DevCtx* c, const u64* d_consts, const u64* d_wires, u64* d_out, size_t npoints) {
+    const int TH = 128;
+    k_eval_gates<<<(unsigned)((npoints + TH - 1) / TH), TH, 0, c->stream>>>(d_consts, d_wires, d_out, npoints);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch(c);
+}
