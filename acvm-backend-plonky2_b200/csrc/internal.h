@@ -67,7 +67,9 @@ struct DevCtx {
     // accounting of the current prove call
     unsigned launches = 0;
     double ntt_bytes = 0, merkle_bytes = 0;
-    float ntt_ms = 0, merkle_ms = 0;
+    float ntt_ms = 0, merkle_ms = 0, leaf_ms = 0, lde_ms = 0;
+    double leaf_bytes = 0, lde_bytes = 0;
+    unsigned leaf_launches = 0, lde_launches = 0;
     bool timing = false;  // when set, NTT / Merkle entry points bracket themselves with events (adds syncs)
 
     const u64* get_tw(int log, bool inverse);

@@ -108,12 +108,17 @@ void merkle_build(DevCtx* c, MerkleTree* t, const u64* d_leaves, size_t col_stri
     t->cap_height = cap_height;
     t->hasher = hasher;
     int nlevels = log_leaves - cap_height + 1;
-    t->levels.clear();
-    t->levels.resize(nlevels);
+    if ((int)t->levels.size() != nlevels) {
+        t->levels.clear();
+        t->levels.resize(nlevels);
+    }
     size_t nl = (size_t)1 << log_leaves;
-    for (int k = 0; k < nlevels; k++) t->levels[k].alloc(nl >> k);
+    for (int k = 0; k < nlevels; k++)
+        if (t->levels[k].n != (nl >> k)) t->levels[k].alloc(nl >> k);
     const int TH = 128;
     unsigned grid = (unsigned)((nl + TH - 1) / TH);
+    {
+    StageTimer tl(c, &c->leaf_ms);
     if (hasher == P2G_H_KECCAK25) {
         if (fri_layout) k_leaf_keccak<true><<<grid, TH, 0, c->stream>>>(d_leaves, col_stride, ncols, nl, t->levels[0].p);
         else k_leaf_keccak<false><<<grid, TH, 0, c->stream>>>(d_leaves, col_stride, ncols, nl, t->levels[0].p);
@@ -121,6 +126,9 @@ void merkle_build(DevCtx* c, MerkleTree* t, const u64* d_leaves, size_t col_stri
         if (fri_layout) k_leaf_poseidon<true><<<grid, TH, 0, c->stream>>>(d_leaves, col_stride, ncols, nl, t->levels[0].p);
         else k_leaf_poseidon<false><<<grid, TH, 0, c->stream>>>(d_leaves, col_stride, ncols, nl, t->levels[0].p);
     }
+    }
+    c->leaf_launches++;
+    c->leaf_bytes += 8.0 * (double)nl * ncols;
     count_launch(c);
     for (int k = 1; k < nlevels; k++) {
         size_t cnt = nl >> k;

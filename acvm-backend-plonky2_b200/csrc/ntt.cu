@@ -503,7 +503,13 @@ void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t ou
             CUDA_CHECK(cudaMemcpy2DAsync(d_lde + z, out_cs * 8, d_coeffs, in_cs * 8, 8, ncols, cudaMemcpyDeviceToDevice, c->stream));
         return;
     }
-    run_forward(c, d);
+    {
+        StageTimer tl(c, &c->lde_ms);
+        unsigned before = c->launches;
+        run_forward(c, d);
+        c->lde_launches += c->launches - before;
+    }
+    c->lde_bytes += (8.0 + 8.0 * nz) * (double)n * ncols;
     c->ntt_bytes += (8.0 + 8.0 * nz) * (double)n * ncols;
 }
 

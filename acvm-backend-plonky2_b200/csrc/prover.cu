@@ -1,0 +1,1154 @@
+// The prover: p2g_circuit_create / p2g_prove and the kernels of the stages that are neither NTT nor Merkle nor gate
+// evaluation -- permutation argument (Z + partial products, prefix-product scan), openings, FRI batch combination with
+// synthetic division by (X - z) as a suffix scan, FRI folding, proof-of-work search, query gathers.
+//
+// Replaces plonky2 0.2.2 plonk/prover.rs prove_with_partition_witness, the function behind
+//     circuit_data.prove(witnesses).unwrap()       /root/reference/plonky2-backend/src/actions/prove_action.rs:96
+// step for step: the Fiat-Shamir transcript runs on the host (challenger_t in hash.cuh), every
+// data-parallel stage on the device.  Output: plonky2's uncompressed ProofWithPublicInputs::to_bytes layout (App. A.12).
+#include <string.h>
+
+#include "internal.h"
+#include "quotient.h"
+
+namespace {
+
+__device__ __forceinline__ u64 tab_pow_d(const u64* tab, int split, u32 i) {
+    return gl_mul(__ldg(tab + (i & ((1u << split) - 1))), __ldg(tab + (1u << split) + (i >> split)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Z and partial products (plonk/prover.rs all_wires_permutation_partial_products)
+// ---------------------------------------------------------------------------------------------------------------------
+struct ZppParams {
+    int logn, num_routed, chunk, nchunk, num_challenges;
+    u64 betas[2], gammas[2];
+    u64 beta_k[2][P2G_MAX_ROUTED];
+};
+__constant__ ZppParams d_zp;
+
+#define ZPP_MAX_CHUNKS 16
+
+// q[c][m][i] = prod_{r in chunk m} (w_r + beta k_r x + gamma) / (w_r + beta sigma_r + gamma) at row i
+__global__ void __launch_bounds__(128) k_zpp_chunks(const u64* __restrict__ wires, size_t wires_cs, const u64* __restrict__ sigmas,
+                                                    const u64* __restrict__ xtab, int xsplit, u64* __restrict__ q) {
+    const ZppParams& P = d_zp;
+    const size_t n = (size_t)1 << P.logn;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = blockIdx.y;
+    const u64 x = tab_pow_d(xtab, xsplit, (u32)i);
+    const u64 beta = P.betas[c], gamma = P.gammas[c];
+    u64 nums[ZPP_MAX_CHUNKS], dens[ZPP_MAX_CHUNKS];
+    for (int m = 0; m < P.nchunk; m++) {
+        u64 pn = 1, pd = 1;
+        int hi = min((m + 1) * P.chunk, P.num_routed);
+        for (int r = m * P.chunk; r < hi; r++) {
+            u64 base = gl_add(wires[(size_t)r * wires_cs + i], gamma);
+            pn = gl_mul(pn, gl_add(base, gl_mul(P.beta_k[c][r], x)));
+            pd = gl_mul(pd, gl_add(base, gl_mul(beta, sigmas[(size_t)r * n + i])));
+        }
+        nums[m] = pn;
+        dens[m] = pd;
+    }
+    // one inversion for the whole row (Montgomery's trick over the chunk denominators)
+    u64 pre[ZPP_MAX_CHUNKS];
+    u64 acc = 1;
+    for (int m = 0; m < P.nchunk; m++) {
+        pre[m] = acc;
+        acc = gl_mul(acc, dens[m]);
+    }
+    u64 inv = gl_inv(acc);
+    for (int m = P.nchunk - 1; m >= 0; m--) {
+        u64 dinv = gl_mul(inv, pre[m]);
+        inv = gl_mul(inv, dens[m]);
+        q[((size_t)c * P.nchunk + m) * n + i] = gl_mul(nums[m], dinv);
+    }
+}
+
+#define SCAN_CH 16  // rows per thread in the scans
+
+// phase 1: totals[c][t] = prod over rows of chunk t of prod_m q[c][m][row]
+__global__ void k_zscan_totals(const u64* __restrict__ q, u64* __restrict__ totals, size_t nt) {
+    const ZppParams& P = d_zp;
+    const size_t n = (size_t)1 << P.logn;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const int c = blockIdx.y;
+    u64 acc = 1;
+    size_t hi = min(n, (t + 1) * SCAN_CH);
+    for (size_t i = t * SCAN_CH; i < hi; i++)
+        for (int m = 0; m < P.nchunk; m++) acc = gl_mul(acc, q[((size_t)c * P.nchunk + m) * n + i]);
+    totals[(size_t)c * nt + t] = acc;
+}
+// phase 2: exclusive prefix product of totals, one block per challenge
+__global__ void __launch_bounds__(1024) k_scan_mul_excl(u64* totals, size_t nt) {
+    __shared__ u64 sh[1024];
+    u64* tt = totals + (size_t)blockIdx.x * nt;
+    const int T = blockDim.x;
+    size_t per = (nt + T - 1) / T;
+    size_t lo = min(nt, threadIdx.x * per), hi = min(nt, lo + per);
+    u64 acc = 1;
+    for (size_t i = lo; i < hi; i++) acc = gl_mul(acc, tt[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = 1; d < T; d <<= 1) {  // Hillis-Steele inclusive scan over the per-thread products
+        u64 v = threadIdx.x >= d ? sh[threadIdx.x - d] : 1;
+        __syncthreads();
+        sh[threadIdx.x] = gl_mul(sh[threadIdx.x], v);
+        __syncthreads();
+    }
+    u64 carry = threadIdx.x ? sh[threadIdx.x - 1] : 1;
+    for (size_t i = lo; i < hi; i++) {
+        u64 v = tt[i];
+        tt[i] = carry;
+        carry = gl_mul(carry, v);
+    }
+}
+// phase 3: write Z (column c) and the partial products (column NC + c*NPP + m)
+__global__ void k_zscan_apply(const u64* __restrict__ q, const u64* __restrict__ totals, size_t nt, u64* __restrict__ out) {
+    const ZppParams& P = d_zp;
+    const size_t n = (size_t)1 << P.logn;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const int c = blockIdx.y, NC = P.num_challenges, NPP = P.nchunk - 1;
+    u64 z = totals[(size_t)c * nt + t];
+    size_t hi = min(n, (t + 1) * SCAN_CH);
+    for (size_t i = t * SCAN_CH; i < hi; i++) {
+        out[(size_t)c * n + i] = z;
+        u64 acc = z;
+        for (int m = 0; m < P.nchunk; m++) {
+            acc = gl_mul(acc, q[((size_t)c * P.nchunk + m) * n + i]);
+            if (m < NPP) out[(size_t)(NC + c * NPP + m) * n + i] = acc;
+        }
+        z = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// openings: sum_i c_i z^i in F_{p^2} against a table of powers (plonk/proof.rs OpeningSet::new; App. A.9)
+// ---------------------------------------------------------------------------------------------------------------------
+// tab[0..n) = re(z^i), tab[n..2n) = im(z^i)
+__global__ void k_e2_powers(u64* tab, size_t n, e2 z) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    e2 p = e2_pow(z, i);
+    tab[i] = p.c0;
+    tab[n + i] = p.c1;
+}
+
+#define EVAL_SPLIT 16384  // coefficients per block
+// partial[(col * nsplit + s)] = sum over the s-th slice
+__global__ void __launch_bounds__(256) k_eval_polys(const u64* __restrict__ coeffs, size_t cs, size_t n, const u64* __restrict__ ptab,
+                                                    e2* __restrict__ partial, int nsplit) {
+    __shared__ u64 s0[256], s1[256];
+    const int col = blockIdx.x, sp = blockIdx.y;
+    const u64* cf = coeffs + (size_t)col * cs;
+    size_t lo = (size_t)sp * EVAL_SPLIT, hi = min(n, lo + EVAL_SPLIT);
+    u64 a0 = 0, a1 = 0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        u64 cv = cf[i];
+        a0 = gl_add(a0, gl_mul(cv, ptab[i]));
+        a1 = gl_add(a1, gl_mul(cv, ptab[n + i]));
+    }
+    s0[threadIdx.x] = a0;
+    s1[threadIdx.x] = a1;
+    __syncthreads();
+    for (int d = blockDim.x / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            s0[threadIdx.x] = gl_add(s0[threadIdx.x], s0[threadIdx.x + d]);
+            s1[threadIdx.x] = gl_add(s1[threadIdx.x], s1[threadIdx.x + d]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)col * nsplit + sp] = e2_make(s0[0], s1[0]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FRI batch combination + division by (X - z)   (fri/oracle.rs prove_openings; App. A.10)
+// ---------------------------------------------------------------------------------------------------------------------
+struct CombineArgs {
+    const u64* coeffs[4];
+    int ncols[4];
+    size_t cs[4];
+    int num_challenges;
+    int logn;
+};
+// u[b][0/1][k] = (sum_j alpha^j poly_{b,j}[k]) * z_b^k ;  batch 0 = every polynomial, batch 1 = the Z polynomials
+__global__ void __launch_bounds__(128) k_fri_combine(CombineArgs a, const e2* __restrict__ apow, const u64* __restrict__ ztab0,
+                                                     const u64* __restrict__ ztab1, u64* __restrict__ u) {
+    const size_t n = (size_t)1 << a.logn;
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    u64 r0 = 0, r1 = 0, z0 = 0, z1 = 0;
+    int j = 0;
+    for (int o = 0; o < 4; o++) {
+        const u64* base = a.coeffs[o] + k;
+        for (int col = 0; col < a.ncols[o]; col++, j++) {
+            u64 cv = base[(size_t)col * a.cs[o]];
+            e2 ap = apow[j];
+            r0 = gl_add(r0, gl_mul(cv, ap.c0));
+            r1 = gl_add(r1, gl_mul(cv, ap.c1));
+            if (o == 2 && col < a.num_challenges) {
+                e2 aq = apow[col];
+                z0 = gl_add(z0, gl_mul(cv, aq.c0));
+                z1 = gl_add(z1, gl_mul(cv, aq.c1));
+            }
+        }
+    }
+    e2 p0 = e2_mul(e2_make(r0, r1), e2_make(ztab0[k], ztab0[n + k]));
+    e2 p1 = e2_mul(e2_make(z0, z1), e2_make(ztab1[k], ztab1[n + k]));
+    u[k] = p0.c0;
+    u[n + k] = p0.c1;
+    u[2 * n + k] = p1.c0;
+    u[3 * n + k] = p1.c1;
+}
+// additive suffix scan over the 4 component arrays u[comp][k] (independent field sums), chunked like the Z scan
+__global__ void k_sscan_totals(const u64* __restrict__ u, u64* __restrict__ totals, size_t n, size_t nt) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const u64* a = u + (size_t)blockIdx.y * n;
+    u64 acc = 0;
+    size_t hi = min(n, (t + 1) * SCAN_CH);
+    for (size_t i = t * SCAN_CH; i < hi; i++) acc = gl_add(acc, a[i]);
+    totals[(size_t)blockIdx.y * nt + t] = acc;
+}
+// exclusive suffix sums of the totals (totals[t] <- sum of totals[t'] for t' > t), one block per component
+__global__ void __launch_bounds__(1024) k_scan_add_suffix_excl(u64* totals, size_t nt) {
+    __shared__ u64 sh[1024];
+    u64* tt = totals + (size_t)blockIdx.x * nt;
+    const int T = blockDim.x;
+    size_t per = (nt + T - 1) / T;
+    size_t lo = min(nt, threadIdx.x * per), hi = min(nt, lo + per);
+    u64 acc = 0;
+    for (size_t i = lo; i < hi; i++) acc = gl_add(acc, tt[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = 1; d < T; d <<= 1) {  // inclusive suffix scan across threads
+        u64 v = threadIdx.x + d < T ? sh[threadIdx.x + d] : 0;
+        __syncthreads();
+        sh[threadIdx.x] = gl_add(sh[threadIdx.x], v);
+        __syncthreads();
+    }
+    u64 carry = threadIdx.x + 1 < T ? sh[threadIdx.x + 1] : 0;
+    for (size_t i = hi; i-- > lo;) {
+        u64 v = tt[i];
+        tt[i] = carry;
+        carry = gl_add(carry, v);
+    }
+}
+// T_k = sum_{i >= k} u_i ;  q_b[k-1] = T_k * z_b^{-k} ;  final[k-1] = q_0[k-1] * alpha^NC + q_1[k-1] ;  final[n-1] = 0
+__global__ void k_sscan_apply(const u64* __restrict__ u, const u64* __restrict__ totals, size_t n, size_t nt,
+                              const u64* __restrict__ zinv0, const u64* __restrict__ zinv1, e2 alpha_nc, u64* __restrict__ fin) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    u64 c[4];
+    for (int k = 0; k < 4; k++) c[k] = totals[(size_t)k * nt + t];
+    size_t lo = t * SCAN_CH, hi = min(n, (t + 1) * SCAN_CH);
+    for (size_t i = hi; i-- > lo;) {
+        for (int k = 0; k < 4; k++) c[k] = gl_add(c[k], u[(size_t)k * n + i]);
+        if (i >= 1) {
+            e2 q0 = e2_mul(e2_make(c[0], c[1]), e2_make(zinv0[i], zinv0[n + i]));
+            e2 q1 = e2_mul(e2_make(c[2], c[3]), e2_make(zinv1[i], zinv1[n + i]));
+            e2 f = e2_add(e2_mul(q0, alpha_nc), q1);
+            fin[i - 1] = f.c0;
+            fin[n + i - 1] = f.c1;
+        }
+    }
+    if (t == nt - 1) {
+        fin[n - 1] = 0;
+        fin[2 * n - 1] = 0;
+    }
+}
+
+// coeffs'[k] = sum_{i < arity} coeffs[arity k + i] beta^i   (fri/prover.rs fri_committed_trees)
+__global__ void k_fri_fold(const u64* __restrict__ in, size_t n_in, u64* __restrict__ out, size_t n_out, int arity, e2 beta) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_out) return;
+    e2 acc = e2_make(0, 0);
+    for (int i = arity - 1; i >= 0; i--) {
+        size_t idx = (size_t)arity * k + i;
+        acc = e2_add(e2_mul(acc, beta), e2_make(in[idx], in[n_in + idx]));
+    }
+    out[k] = acc.c0;
+    out[n_out + k] = acc.c1;
+}
+
+// proof of work: smallest witness w in [start, start + count) with >= pow_bits leading zero bits in the response
+__global__ void k_pow_search(challenger_t base, u64 start, u64 count, int pow_bits, unsigned long long* best) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    challenger_t ch = base;
+    ch.observe(start + t);
+    u64 r = ch.get();
+    if (pow_bits == 0 || (r >> (64 - pow_bits)) == 0) atomicMin(best, (unsigned long long)(start + t));
+}
+
+// query phase gathers
+__global__ void k_gather_rows(const u64* __restrict__ lde, size_t cs, int ncols, const u32* __restrict__ idx, int nq,
+                              u64* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * ncols) return;
+    int q = t / ncols, c = t % ncols;
+    out[t] = lde[(size_t)c * cs + idx[q]];
+}
+__global__ void k_gather_fri_rows(const u64* __restrict__ vals, size_t cs, int arity, const u32* __restrict__ idx, int nq, int shift,
+                                  u64* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int w = 2 * arity;
+    if (t >= nq * w) return;
+    int q = t / w, k = t % w;
+    size_t leaf = idx[q] >> shift;
+    out[t] = vals[(size_t)(k & 1) * cs + leaf * arity + (k >> 1)];
+}
+__global__ void k_gather_paths(const digest_t* const* __restrict__ levels, int nlev, const u32* __restrict__ idx, int nq, int shift,
+                               digest_t* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * nlev) return;
+    int q = t / nlev, k = t % nlev;
+    size_t leaf = idx[q] >> shift;
+    out[t] = levels[k][(leaf >> k) ^ 1];
+}
+
+struct PolyBatch {
+    int ncols = 0, logn = 0;
+    dbuf<u64> coeffs;  // [ncols][N]
+    dbuf<u64> lde;     // [ncols][N << rate_bits], leaf order
+    MerkleTree tree;
+    dbuf<const digest_t*> d_levels;  // device array of level pointers (query gathers)
+};
+
+}  // namespace
+
+struct p2g_circuit {
+    p2g_circuit_desc d;
+    std::vector<p2g_gate> gates;
+    std::vector<u64> k_is;
+    DevCtx* ctx = nullptr;
+    int logn = 0, loglde = 0, hs = 0, h = 0;
+    size_t n = 0, lde = 0;
+    dbuf<u64> sigma_values;  // [R][N], natural row order (Z computation)
+    dbuf<u64> wires_values;  // [W][N] staging for p2g_prove (host trace upload)
+    PolyBatch cs, wires, zpp, quot;
+    dbuf<u64> xs, l0s;
+    u64 zh[1 << P2G_MAX_RATE], zh_inv[1 << P2G_MAX_RATE];
+    digest_t digest;
+    std::vector<digest_t> cs_cap;
+    std::mutex mu;
+    // dumps of the last prove
+    dbuf<u64> zpp_values;
+    std::vector<u64> challenges;
+    std::vector<u64> final_poly;  // c0,c1 interleaved
+    std::vector<digest_t> fri_caps;
+    bool proved = false;
+    // sharding (one process per GPU); world == 1: single device
+    int rank = 0, world = 1;
+    p2g_allgather_fn allgather = nullptr;
+    void* allgather_user = nullptr;
+};
+
+namespace {
+
+void upload_level_ptrs(DevCtx* c, PolyBatch& b) {
+    int nlev = (int)b.tree.levels.size() - 1;
+    if (nlev <= 0) return;
+    std::vector<const digest_t*> p(nlev);
+    for (int k = 0; k < nlev; k++) p[k] = b.tree.levels[k].p;
+    if (b.d_levels.n != (size_t)nlev) b.d_levels.alloc(nlev);
+    CUDA_CHECK(cudaMemcpyAsync(b.d_levels.p, p.data(), sizeof(void*) * nlev, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// coefficients already in b.coeffs: LDE + Merkle
+void commit_from_coeffs(p2g_circuit* C, PolyBatch& b) {
+    DevCtx* c = C->ctx;
+    size_t want = (size_t)b.ncols * C->lde;
+    if (b.lde.n != want) b.lde.alloc(want);
+    ntt_lde(c, b.coeffs.p, C->n, b.lde.p, C->lde, C->logn, C->d.rate_bits, b.ncols, GL_GEN);
+    merkle_build(c, &b.tree, b.lde.p, C->lde, C->loglde, b.ncols, C->d.cap_height, C->h);
+    upload_level_ptrs(c, b);
+}
+void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs) {
+    size_t want = (size_t)b.ncols * C->n;
+    if (b.coeffs.n != want) b.coeffs.alloc(want);
+    ntt_ifft(C->ctx, d_values, values_cs, b.coeffs.p, C->n, C->logn, b.ncols);
+    commit_from_coeffs(C, b);
+}
+std::vector<digest_t> read_cap(p2g_circuit* C, const MerkleTree& t) {
+    std::vector<digest_t> cap(t.ncap());
+    CUDA_CHECK(cudaMemcpyAsync(cap.data(), t.cap(), sizeof(digest_t) * cap.size(), cudaMemcpyDeviceToHost, C->ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));
+    return cap;
+}
+
+struct Writer {
+    uint8_t* p;
+    size_t len = 0, cap;
+    Writer(uint8_t* out, size_t capacity) : p(out), cap(out ? capacity : 0) {}
+    void put(const void* src, size_t nbytes) {
+        if (len + nbytes <= cap) memcpy(p + len, src, nbytes);
+        len += nbytes;
+    }
+    void u64v(u64 x) { put(&x, 8); }
+    void e2v(e2 x) {
+        u64v(x.c0);
+        u64v(x.c1);
+    }
+    void u8v(uint8_t x) { put(&x, 1); }
+    void digest(const digest_t& d, int hs) { put(&d, hs); }
+};
+
+void validate_desc(const p2g_circuit_desc* d) {
+    auto bad = [](const char* m) { throw p2g_error(P2G_EBADARG, std::string("p2g_circuit_create: ") + m); };
+    if (!d) bad("null descriptor");
+    if (d->struct_size != sizeof(p2g_circuit_desc)) bad("struct_size mismatch (ABI)");
+    if (d->degree_bits > 24) bad("degree_bits > 24");
+    if (d->num_challenges < 1 || d->num_challenges > 2) bad("num_challenges must be 1 or 2");
+    if (d->rate_bits < 1 || d->rate_bits > P2G_MAX_RATE) bad("rate_bits out of range");
+    if (d->quotient_degree_factor != (1u << d->rate_bits)) bad("quotient_degree_factor must equal 2^rate_bits");
+    if (d->num_routed_wires == 0 || d->num_routed_wires > P2G_MAX_ROUTED || d->num_routed_wires > d->num_wires) bad("num_routed_wires");
+    if (d->num_gates == 0 || d->num_gates > P2G_MAX_GATES || !d->gates) bad("gate table");
+    if (d->hasher > 1) bad("hasher");
+    if (d->num_fri_layers > P2G_MAX_FRI_LAYERS) bad("num_fri_layers");
+    if (!d->constants_sigmas || !d->k_is) bad("null preprocessed data");
+    u32 nchunk = (d->num_routed_wires + d->quotient_degree_factor - 1) / d->quotient_degree_factor;
+    if (d->num_partial_products + 1 != nchunk || nchunk > ZPP_MAX_CHUNKS) bad("num_partial_products");
+    u32 nterms = d->num_challenges * (2 + d->num_partial_products) + d->num_gate_constraints;
+    if (nterms > P2G_MAX_TERMS) bad("too many constraint terms");
+    u32 red = 0;
+    for (u32 i = 0; i < d->num_fri_layers; i++) {
+        if (d->reduction_arity_bits[i] < 1 || d->reduction_arity_bits[i] > 6) bad("reduction_arity_bits");
+        red += d->reduction_arity_bits[i];
+    }
+    if (red > d->degree_bits) bad("FRI schedule longer than the polynomial");
+    for (u32 g = 0; g < d->num_gates; g++) {
+        const p2g_gate& gt = d->gates[g];
+        if (gt.kind >= P2G_GATE_KIND_COUNT) bad("unknown gate kind");
+        if (gt.selector_index >= d->num_selectors || gt.group_lo > g || gt.group_hi <= g || gt.group_hi > d->num_gates) bad("selector data");
+        if (gt.num_constraints > d->num_gate_constraints) bad("gate num_constraints > num_gate_constraints");
+        if (gt.kind == P2G_GATE_RANDOM_ACCESS && gt.params[0] > 6) bad("RandomAccessGate bits > 6");
+    }
+}
+
+void fill_gates(QuotientParams& qp, const p2g_circuit* C) {
+    qp.num_gates = (int)C->gates.size();
+    for (size_t g = 0; g < C->gates.size(); g++) {
+        GateDev& o = qp.gates[g];
+        const p2g_gate& s = C->gates[g];
+        o.kind = s.kind;
+        for (int k = 0; k < 4; k++) o.params[k] = s.params[k];
+        o.selector_index = s.selector_index;
+        o.group_lo = s.group_lo;
+        o.group_hi = s.group_hi;
+        o.num_constraints = s.num_constraints;
+    }
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// circuit handle
+// =====================================================================================================================
+extern "C" int p2g_circuit_create(const p2g_circuit_desc* desc, int device, p2g_circuit** out) {
+    if (out) *out = nullptr;
+    p2g_circuit* C = nullptr;
+    int rc = guard([&] {
+        if (!out) throw p2g_error(P2G_EBADARG, "p2g_circuit_create: null out");
+        validate_desc(desc);
+        DevCtx* c = get_ctx(device);
+        C = new p2g_circuit();
+        C->d = *desc;
+        C->ctx = c;
+        C->gates.assign(desc->gates, desc->gates + desc->num_gates);
+        C->k_is.assign(desc->k_is, desc->k_is + desc->num_routed_wires);
+        C->d.gates = C->gates.data();
+        C->d.k_is = C->k_is.data();
+        C->d.constants_sigmas = nullptr;
+        C->d.circuit_digest = nullptr;
+        C->logn = desc->degree_bits;
+        C->loglde = desc->degree_bits + desc->rate_bits;
+        C->n = (size_t)1 << C->logn;
+        C->lde = (size_t)1 << C->loglde;
+        C->h = desc->hasher;
+        C->hs = hasher_bytes(C->h);
+        const int Cc = desc->num_constants, R = desc->num_routed_wires, P = Cc + R;
+        const size_t n = C->n;
+        for (size_t i = 0; i < (size_t)P * n; i++)
+            if (desc->constants_sigmas[i] >= GL_P) throw p2g_error(P2G_EBADARG, "p2g_circuit_create: non-canonical preprocessed value");
+        // preprocessed commitment (what CircuitBuilder::build() does, circuit_translation/mod.rs:81)
+        dbuf<u64> vals((size_t)P * n);
+        CUDA_CHECK(cudaMemcpyAsync(vals.p, desc->constants_sigmas, (size_t)P * n * 8, cudaMemcpyHostToDevice, c->stream));
+        C->sigma_values.alloc((size_t)R * n);
+        CUDA_CHECK(cudaMemcpyAsync(C->sigma_values.p, vals.p + (size_t)Cc * n, (size_t)R * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        C->cs.ncols = P;
+        commit_from_values(C, C->cs, vals.p, n);
+        C->cs_cap = read_cap(C, C->cs.tree);
+        // Z_H on the 2^rate_bits cosets: (shift * omega_lde^r)^N - 1 = shift^N * omega_{2^rate}^r - 1
+        u64 gn = gl_pow(GL_GEN, (u64)n), wr = gl_root_of_unity(desc->rate_bits);
+        for (u32 r = 0; r < (1u << desc->rate_bits); r++) {
+            C->zh[r] = gl_sub(gl_mul(gn, gl_pow(wr, r)), 1);
+            C->zh_inv[r] = gl_inv(C->zh[r]);
+        }
+        C->xs.alloc(C->lde);
+        C->l0s.alloc(C->lde);
+        quotient_points(c, C->xs.p, C->l0s.p, C->logn, desc->rate_bits, C->zh);
+        if (desc->circuit_digest) {
+            memset(&C->digest, 0, sizeof(digest_t));
+            memcpy(&C->digest, desc->circuit_digest, C->hs);
+        } else {
+            // H.hash_no_pad(cap.flatten() || H.hash_pad([]).to_vec() || [degree_bits])   
+            std::vector<u64> parts;
+            u64 e[4];
+            for (const digest_t& dg : C->cs_cap) {
+                digest_to_elems(C->h, dg, e);
+                parts.insert(parts.end(), e, e + 4);
+            }
+            const u64 pad[8] = {1, 0, 0, 0, 0, 0, 0, 1};
+            digest_to_elems(C->h, hash_no_pad(C->h, pad, 8), e);
+            parts.insert(parts.end(), e, e + 4);
+            parts.push_back(desc->degree_bits);
+            C->digest = hash_no_pad(C->h, parts.data(), parts.size());
+        }
+        // persistent buffers of the per-proof commitments
+        const int W = desc->num_wires, NC = desc->num_challenges, nzp = NC * (1 + desc->num_partial_products),
+                  nq = NC * desc->quotient_degree_factor;
+        C->wires.ncols = W;
+        C->wires.coeffs.alloc((size_t)W * n);
+        C->wires.lde.alloc((size_t)W * C->lde);
+        C->zpp.ncols = nzp;
+        C->zpp.coeffs.alloc((size_t)nzp * n);
+        C->zpp.lde.alloc((size_t)nzp * C->lde);
+        C->zpp_values.alloc((size_t)nzp * n);
+        C->quot.ncols = nq;
+        C->quot.coeffs.alloc((size_t)nq * n);
+        C->quot.lde.alloc((size_t)nq * C->lde);
+        *out = C;
+    });
+    if (rc != P2G_OK && C) delete C;
+    return rc;
+}
+
+extern "C" void p2g_circuit_destroy(p2g_circuit* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    delete c;
+}
+
+extern "C" int p2g_circuit_cap(const p2g_circuit* c, uint8_t* cap_out, size_t cap_len, uint8_t* digest_out, size_t digest_len) {
+    return guard([&] {
+        if (!c) throw p2g_error(P2G_EBADARG, "p2g_circuit_cap: null handle");
+        size_t need = c->cs_cap.size() * c->hs;
+        if (cap_out) {
+            if (cap_len < need) throw p2g_error(P2G_ESMALLBUF, "p2g_circuit_cap: cap buffer too small");
+            pack_digests(c->h, c->cs_cap.data(), c->cs_cap.size(), cap_out);
+        }
+        if (digest_out) {
+            if (digest_len < (size_t)c->hs) throw p2g_error(P2G_ESMALLBUF, "p2g_circuit_cap: digest buffer too small");
+            memcpy(digest_out, &c->digest, c->hs);
+        }
+    });
+}
+
+extern "C" size_t p2g_proof_size_bound(const p2g_circuit* c) {
+    if (!c) return 0;
+    const p2g_circuit_desc& d = c->d;
+    size_t hs = c->hs, ncap = (size_t)1 << d.cap_height;
+    size_t P = d.num_constants + d.num_routed_wires, W = d.num_wires, nzp = d.num_challenges * (1 + d.num_partial_products),
+           nq = d.num_challenges * d.quotient_degree_factor;
+    size_t sz = 3 * ncap * hs + 16 * (P + W + nzp + d.num_challenges + nq) + d.num_fri_layers * ncap * hs;
+    size_t path = 1 + hs * (size_t)c->loglde;
+    size_t per_q = 8 * (P + W + nzp + nq) + 4 * path;
+    for (u32 l = 0; l < d.num_fri_layers; l++) per_q += 16 * ((size_t)1 << d.reduction_arity_bits[l]) + path;
+    sz += d.num_query_rounds * per_q;
+    sz += 16 * c->n + 8 + 8 * d.num_public_inputs;
+    return sz;
+}
+
+extern "C" int p2g_circuit_set_sharding(p2g_circuit* c, int rank, int world, p2g_allgather_fn allgather, void* user) {
+    return guard([&] {
+        if (!c || world < 1 || rank < 0 || rank >= world) throw p2g_error(P2G_EBADARG, "p2g_circuit_set_sharding: bad argument");
+        if (world > 1) throw p2g_error(P2G_EBADARG, "p2g_circuit_set_sharding: intra-proof sharding is not built yet; run one proof per GPU");
+        c->rank = rank;
+        c->world = world;
+        c->allgather = allgather;
+        c->allgather_user = user;
+    });
+}
+
+// =====================================================================================================================
+// prove
+// =====================================================================================================================
+static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inputs, size_t n_pi, const u64* forced_pow,
+                       uint8_t* out, size_t* out_len, p2g_timings* tm, cudaEvent_t ev_start) {
+    DevCtx* c = C->ctx;
+    const p2g_circuit_desc& d = C->d;
+    const size_t n = C->n, lde = C->lde;
+    const int logn = C->logn, W = d.num_wires, R = d.num_routed_wires, Cc = d.num_constants, NC = d.num_challenges;
+    const int NPP = d.num_partial_products, QDF = d.quotient_degree_factor, nchunk = NPP + 1;
+    const int nzp = NC * (1 + NPP), nq = NC * QDF, P = Cc + R;
+    const int h = C->h, hs = C->hs;
+    cudaStream_t st = c->stream;
+    cudaEvent_t ev[7];
+    for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() { for (int i = 0; i < 7; i++) cudaEventDestroy(e[i]); }
+    } evg{ev};
+    CUDA_CHECK(cudaEventRecord(ev[0], st));
+
+    // 1. public inputs hash (InnerHasher = Poseidon for both configs)
+    u64 pi_hash[4] = {0, 0, 0, 0};
+    if (n_pi) {
+        digest_t ph = hash_no_pad(P2G_H_POSEIDON, public_inputs, n_pi);
+        memcpy(pi_hash, ph.w, 32);
+    }
+
+    // 2. wires commitment
+    commit_from_values(C, C->wires, d_wires, n);
+    std::vector<digest_t> wires_cap = read_cap(C, C->wires.tree);
+    CUDA_CHECK(cudaEventRecord(ev[1], st));
+
+    // 3-4. transcript
+    challenger_t ch;
+    ch.init(h);
+    ch.observe_digest(C->digest);
+    ch.observe_many(pi_hash, 4);
+    for (auto& dg : wires_cap) ch.observe_digest(dg);
+    u64 betas[2] = {0, 0}, gammas[2] = {0, 0}, alphas[2] = {0, 0};
+    for (int i = 0; i < NC; i++) betas[i] = ch.get();
+    for (int i = 0; i < NC; i++) gammas[i] = ch.get();
+
+    // 5. Z and partial products
+    {
+        ZppParams zp = {};
+        zp.logn = logn;
+        zp.num_routed = R;
+        zp.chunk = QDF;
+        zp.nchunk = nchunk;
+        zp.num_challenges = NC;
+        for (int cc = 0; cc < NC; cc++) {
+            zp.betas[cc] = betas[cc];
+            zp.gammas[cc] = gammas[cc];
+            for (int r = 0; r < R; r++) zp.beta_k[cc][r] = gl_mul(betas[cc], C->k_is[r]);
+        }
+        CUDA_CHECK(cudaMemcpyToSymbolAsync(d_zp, &zp, sizeof(zp), 0, cudaMemcpyHostToDevice, st));
+        int xsplit;
+        const u64* xtab = c->get_powtab(logn, gl_root_of_unity(logn), 1, &xsplit);
+        dbuf<u64> q((size_t)NC * nchunk * n);
+        size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
+        dbuf<u64> totals((size_t)NC * nt);
+        dim3 g1((unsigned)((n + 127) / 128), NC);
+        k_zpp_chunks<<<g1, 128, 0, st>>>(d_wires, n, C->sigma_values.p, xtab, xsplit, q.p);
+        dim3 g2((unsigned)((nt + 127) / 128), NC);
+        k_zscan_totals<<<g2, 128, 0, st>>>(q.p, totals.p, nt);
+        k_scan_mul_excl<<<NC, 1024, 0, st>>>(totals.p, nt);
+        k_zscan_apply<<<g2, 128, 0, st>>>(q.p, totals.p, nt, C->zpp_values.p);
+        count_launch(c, 4);
+        CUDA_CHECK(cudaGetLastError());
+        commit_from_values(C, C->zpp, C->zpp_values.p, n);
+    }
+    std::vector<digest_t> zpp_cap = read_cap(C, C->zpp.tree);
+    for (auto& dg : zpp_cap) ch.observe_digest(dg);
+    CUDA_CHECK(cudaEventRecord(ev[2], st));
+
+    // 6. alphas
+    for (int i = 0; i < NC; i++) alphas[i] = ch.get();
+
+    // 7. quotient
+    float quotient_kernel_ms = 0;
+    {
+        static thread_local QuotientParams qp;
+        memset(&qp, 0, sizeof(qp));
+        qp.logn = logn;
+        qp.rate_bits = d.rate_bits;
+        qp.num_challenges = NC;
+        qp.num_partial_products = NPP;
+        qp.num_routed = R;
+        qp.num_constants = Cc;
+        qp.num_selectors = d.num_selectors;
+        qp.qdf = QDF;
+        for (int cc = 0; cc < NC; cc++) {
+            qp.betas[cc] = betas[cc];
+            qp.gammas[cc] = gammas[cc];
+            for (int r = 0; r < R; r++) qp.beta_k[cc][r] = gl_mul(betas[cc], C->k_is[r]);
+            int nterms = NC * (2 + NPP) + d.num_gate_constraints;
+            u64 a = 1;
+            for (int k = 0; k < nterms; k++) {
+                qp.apow[cc][k] = a;
+                a = gl_mul(a, alphas[cc]);
+            }
+        }
+        for (u32 r = 0; r < (1u << d.rate_bits); r++) qp.zh_inv[r] = C->zh_inv[r];
+        memcpy(qp.pi_hash, pi_hash, 32);
+        fill_gates(qp, C);
+        quotient_upload_params(c, qp);
+        // quotient values land in quot.lde's first NC columns region?  No: they are transformed in place into the
+        // chunk coefficients, so evaluate straight into quot.coeffs viewed as [NC][8N]
+        u64* qv = C->quot.coeffs.p;
+        cudaEvent_t qa, qb;
+        CUDA_CHECK(cudaEventCreate(&qa));
+        CUDA_CHECK(cudaEventCreate(&qb));
+        CUDA_CHECK(cudaEventRecord(qa, st));
+        quotient_eval(c, C->cs.lde.p, C->wires.lde.p, C->zpp.lde.p, C->xs.p, C->l0s.p, qv, 0, lde);
+        CUDA_CHECK(cudaEventRecord(qb, st));
+        ntt_coset_ifft_leaforder(c, qv, lde, C->loglde, NC, GL_GEN);
+        CUDA_CHECK(cudaEventSynchronize(qb));
+        cudaEventElapsedTime(&quotient_kernel_ms, qa, qb);
+        cudaEventDestroy(qa);
+        cudaEventDestroy(qb);
+        // [NC][8N] coefficients == [NC*QDF][N] chunk polynomials
+        commit_from_coeffs(C, C->quot);
+    }
+    std::vector<digest_t> quot_cap = read_cap(C, C->quot.tree);
+    for (auto& dg : quot_cap) ch.observe_digest(dg);
+    CUDA_CHECK(cudaEventRecord(ev[3], st));
+
+    // 8. zeta
+    e2 zeta = ch.get_e2();
+    if (e2_eq(e2_pow(zeta, (u64)n), e2_make(1, 0))) throw p2g_error(P2G_EUNSAT, "Opening point is in the subgroup.");
+    if (zeta.c0 == 0 && zeta.c1 == 0) throw p2g_error(P2G_EUNSAT, "Opening point is zero.");
+    const u64 g = gl_root_of_unity(logn);
+    e2 zeta_next = e2_mul_base(zeta, g);
+
+    // 9. openings
+    PolyBatch* oracles[4] = {&C->cs, &C->wires, &C->zpp, &C->quot};
+    const int widths[4] = {P, W, nzp, nq};
+    const int total = P + W + nzp + nq;
+    dbuf<u64> ztab0(2 * n), ztab1(2 * n);
+    k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0.p, n, zeta);
+    k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1.p, n, zeta_next);
+    count_launch(c, 2);
+    const int nsplit = (int)((n + EVAL_SPLIT - 1) / EVAL_SPLIT);
+    std::vector<e2> op(total), zs_next(NC);
+    {
+        dbuf<e2> partial((size_t)(total + NC) * nsplit);
+        int off = 0;
+        for (int o = 0; o < 4; o++) {
+            dim3 grid(widths[o], nsplit);
+            k_eval_polys<<<grid, 256, 0, st>>>(oracles[o]->coeffs.p, n, n, ztab0.p, partial.p + (size_t)off * nsplit, nsplit);
+            off += widths[o];
+        }
+        dim3 grid(NC, nsplit);
+        k_eval_polys<<<grid, 256, 0, st>>>(C->zpp.coeffs.p, n, n, ztab1.p, partial.p + (size_t)total * nsplit, nsplit);
+        count_launch(c, 5);
+        CUDA_CHECK(cudaGetLastError());
+        std::vector<e2> hp((size_t)(total + NC) * nsplit);
+        CUDA_CHECK(cudaMemcpyAsync(hp.data(), partial.p, hp.size() * sizeof(e2), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int i = 0; i < total + NC; i++) {
+            e2 s = e2_make(0, 0);
+            for (int k = 0; k < nsplit; k++) s = e2_add(s, hp[(size_t)i * nsplit + k]);
+            if (i < total) op[i] = s;
+            else zs_next[i - total] = s;
+        }
+    }
+    for (int i = 0; i < total; i++) ch.observe_e2(op[i]);
+    for (int i = 0; i < NC; i++) ch.observe_e2(zs_next[i]);
+    CUDA_CHECK(cudaEventRecord(ev[4], st));
+
+    // 10. FRI
+    e2 fri_alpha = ch.get_e2();
+    const int nl = d.num_fri_layers;
+    dbuf<u64> fin(2 * n);  // final polynomial, re | im
+    {
+        std::vector<e2> apow(total);
+        e2 a = e2_make(1, 0);
+        for (int j = 0; j < total; j++) {
+            apow[j] = a;
+            a = e2_mul(a, fri_alpha);
+        }
+        dbuf<e2> d_apow(total);
+        CUDA_CHECK(cudaMemcpyAsync(d_apow.p, apow.data(), sizeof(e2) * total, cudaMemcpyHostToDevice, st));
+        CombineArgs ca = {};
+        for (int o = 0; o < 4; o++) {
+            ca.coeffs[o] = oracles[o]->coeffs.p;
+            ca.ncols[o] = widths[o];
+            ca.cs[o] = n;
+        }
+        ca.num_challenges = NC;
+        ca.logn = logn;
+        dbuf<u64> u(4 * n);
+        k_fri_combine<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ca, d_apow.p, ztab0.p, ztab1.p, u.p);
+        // tables of inverse powers (reuse the forward tables' storage after the combine)
+        e2 zi0, zi1;  // inverse in F_{p^2}: z^-1 = conj(z) / norm(z)
+        {
+            auto inv2 = [](e2 z) {
+                u64 nrm = gl_sub(gl_sqr(z.c0), gl_mul_small(gl_sqr(z.c1), 7));
+                u64 ni = gl_inv(nrm);
+                return e2_make(gl_mul(z.c0, ni), gl_neg(gl_mul(z.c1, ni)));
+            };
+            zi0 = inv2(zeta);
+            zi1 = inv2(zeta_next);
+        }
+        k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0.p, n, zi0);
+        k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1.p, n, zi1);
+        size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
+        dbuf<u64> totals(4 * nt);
+        dim3 g2((unsigned)((nt + 127) / 128), 4);
+        k_sscan_totals<<<g2, 128, 0, st>>>(u.p, totals.p, n, nt);
+        k_scan_add_suffix_excl<<<4, 1024, 0, st>>>(totals.p, nt);
+        e2 alpha_nc = e2_pow(fri_alpha, (u64)NC);
+        k_sscan_apply<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(u.p, totals.p, n, nt, ztab0.p, ztab1.p, alpha_nc, fin.p);
+        count_launch(c, 6);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    // commit phase
+    struct Layer {
+        dbuf<u64> values;  // [2][cur] leaf order
+        PolyBatch tree;
+        size_t cur;
+        int logcur, ab;
+    };
+    std::vector<Layer> layers(nl);
+    std::vector<e2> fri_betas(nl);
+    C->fri_caps.clear();
+    dbuf<u64> coeffs_a(2 * n), coeffs_b;
+    CUDA_CHECK(cudaMemcpyAsync(coeffs_a.p, fin.p, 16 * n, cudaMemcpyDeviceToDevice, st));
+    u64* cur_coeffs = coeffs_a.p;
+    size_t m = n;  // number of (possibly) non-zero coefficients
+    int logm = logn;
+    u64 shift = GL_GEN;
+    if (nl) coeffs_b.alloc(2 * (n >> d.reduction_arity_bits[0]) + 2);
+    for (int l = 0; l < nl; l++) {
+        Layer& L = layers[l];
+        L.ab = d.reduction_arity_bits[l];
+        L.logcur = logm + d.rate_bits;
+        L.cur = (size_t)1 << L.logcur;
+        L.values.alloc(2 * L.cur);
+        // values = coset_fft(coeffs.lde(rate_bits), shift), both components, leaf order
+        ntt_lde(c, cur_coeffs, m, L.values.p, L.cur, logm, d.rate_bits, 2, shift);
+        const int arity = 1 << L.ab;
+        merkle_build(c, &L.tree.tree, L.values.p, L.cur, L.logcur - L.ab, 2 * arity, d.cap_height, h, true);
+        upload_level_ptrs(c, L.tree);
+        std::vector<digest_t> cap = read_cap(C, L.tree.tree);
+        for (auto& dg : cap) ch.observe_digest(dg);
+        C->fri_caps.insert(C->fri_caps.end(), cap.begin(), cap.end());
+        e2 beta = ch.get_e2();
+        fri_betas[l] = beta;
+        size_t m2 = m >> L.ab;
+        u64* nxt = (cur_coeffs == coeffs_a.p) ? coeffs_b.p : coeffs_a.p;
+        k_fri_fold<<<(unsigned)((m2 + 127) / 128), 128, 0, st>>>(cur_coeffs, m, nxt, m2, arity, beta);
+        count_launch(c);
+        CUDA_CHECK(cudaGetLastError());
+        cur_coeffs = nxt;
+        m = m2;
+        logm -= L.ab;
+        shift = gl_pow(shift, (u64)arity);
+    }
+    // final polynomial
+    C->final_poly.assign(2 * m, 0);
+    {
+        std::vector<u64> tmp(2 * m);
+        CUDA_CHECK(cudaMemcpyAsync(tmp.data(), cur_coeffs, 8 * m, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(tmp.data() + m, cur_coeffs + m, 8 * m, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < m; i++) {
+            C->final_poly[2 * i] = tmp[i];
+            C->final_poly[2 * i + 1] = tmp[m + i];
+        }
+    }
+    for (size_t i = 0; i < m; i++) ch.observe_e2(e2_make(C->final_poly[2 * i], C->final_poly[2 * i + 1]));
+
+    // proof of work
+    u64 pow_witness = 0;
+    if (forced_pow) {
+        pow_witness = *forced_pow;
+    } else {
+        dbuf<unsigned long long> best(1);
+        const u64 batch = (u64)1 << 20;
+        for (u64 start = 0;; start += batch) {
+            CUDA_CHECK(cudaMemsetAsync(best.p, 0xff, 8, st));
+            k_pow_search<<<(unsigned)(batch / 128), 128, 0, st>>>(ch, start, batch, d.pow_bits, best.p);
+            count_launch(c);
+            unsigned long long hb = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&hb, best.p, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            if (hb != ~0ULL) {
+                pow_witness = hb;
+                break;
+            }
+            if (start > ((u64)1 << 40)) throw p2g_error(P2G_EUNSAT, "proof-of-work search exhausted");
+        }
+    }
+    ch.observe(pow_witness);
+    {
+        u64 resp = ch.get();
+        if (d.pow_bits && (resp >> (64 - d.pow_bits)) != 0) throw p2g_error(P2G_EUNSAT, "forced pow_witness is invalid");
+    }
+    const int NQ = d.num_query_rounds;
+    std::vector<u32> indices(NQ);
+    for (int q = 0; q < NQ; q++) indices[q] = (u32)(ch.get() % (u64)lde);
+    CUDA_CHECK(cudaEventRecord(ev[5], st));
+
+    // challenges dump (P2G_BUF_CHALLENGES)
+    C->challenges.clear();
+    for (int i = 0; i < NC; i++) C->challenges.push_back(betas[i]);
+    for (int i = 0; i < NC; i++) C->challenges.push_back(gammas[i]);
+    for (int i = 0; i < NC; i++) C->challenges.push_back(alphas[i]);
+    C->challenges.push_back(zeta.c0);
+    C->challenges.push_back(zeta.c1);
+    C->challenges.push_back(fri_alpha.c0);
+    C->challenges.push_back(fri_alpha.c1);
+    for (int l = 0; l < nl; l++) {
+        C->challenges.push_back(fri_betas[l].c0);
+        C->challenges.push_back(fri_betas[l].c1);
+    }
+    C->challenges.push_back(pow_witness);
+    for (int q = 0; q < NQ; q++) C->challenges.push_back(indices[q]);
+
+    // query rounds: gather opened rows and Merkle paths on the device, one D2H
+    dbuf<u32> d_idx(NQ);
+    CUDA_CHECK(cudaMemcpyAsync(d_idx.p, indices.data(), 4 * NQ, cudaMemcpyHostToDevice, st));
+    size_t row_words = 0, path_digests = 0;
+    size_t row_off[4 + P2G_MAX_FRI_LAYERS], path_off[4 + P2G_MAX_FRI_LAYERS];
+    int path_len[4 + P2G_MAX_FRI_LAYERS];
+    for (int o = 0; o < 4; o++) {
+        row_off[o] = row_words;
+        row_words += (size_t)NQ * widths[o];
+        path_off[o] = path_digests;
+        path_len[o] = (int)oracles[o]->tree.levels.size() - 1;
+        path_digests += (size_t)NQ * path_len[o];
+    }
+    for (int l = 0; l < nl; l++) {
+        row_off[4 + l] = row_words;
+        row_words += (size_t)NQ * 2 * (1 << layers[l].ab);
+        path_off[4 + l] = path_digests;
+        path_len[4 + l] = (int)layers[l].tree.tree.levels.size() - 1;
+        path_digests += (size_t)NQ * path_len[4 + l];
+    }
+    dbuf<u64> d_rows(row_words);
+    dbuf<digest_t> d_paths(path_digests + 1);
+    for (int o = 0; o < 4; o++) {
+        int cnt = NQ * widths[o];
+        k_gather_rows<<<(cnt + 127) / 128, 128, 0, st>>>(oracles[o]->lde.p, lde, widths[o], d_idx.p, NQ, d_rows.p + row_off[o]);
+        if (path_len[o] > 0) {
+            int pc = NQ * path_len[o];
+            k_gather_paths<<<(pc + 127) / 128, 128, 0, st>>>(oracles[o]->d_levels.p, path_len[o], d_idx.p, NQ, 0, d_paths.p + path_off[o]);
+        }
+        count_launch(c, 2);
+    }
+    {
+        int sh = 0;
+        for (int l = 0; l < nl; l++) {
+            sh += layers[l].ab;
+            int arity = 1 << layers[l].ab;
+            int cnt = NQ * 2 * arity;
+            k_gather_fri_rows<<<(cnt + 127) / 128, 128, 0, st>>>(layers[l].values.p, layers[l].cur, arity, d_idx.p, NQ, sh,
+                                                                 d_rows.p + row_off[4 + l]);
+            if (path_len[4 + l] > 0) {
+                int pc = NQ * path_len[4 + l];
+                k_gather_paths<<<(pc + 127) / 128, 128, 0, st>>>(layers[l].tree.d_levels.p, path_len[4 + l], d_idx.p, NQ, sh,
+                                                                 d_paths.p + path_off[4 + l]);
+            }
+            count_launch(c, 2);
+        }
+    }
+    CUDA_CHECK(cudaGetLastError());
+    std::vector<u64> h_rows(row_words);
+    std::vector<digest_t> h_paths(path_digests + 1);
+    CUDA_CHECK(cudaMemcpyAsync(h_rows.data(), d_rows.p, 8 * row_words, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_paths.data(), d_paths.p, sizeof(digest_t) * path_digests, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+
+    // serialise: Proof || public_inputs   (App. A.12, uncompressed)
+    Writer wb(out, out ? *out_len : 0);
+    for (auto& dg : wires_cap) wb.digest(dg, hs);
+    for (auto& dg : zpp_cap) wb.digest(dg, hs);
+    for (auto& dg : quot_cap) wb.digest(dg, hs);
+    {
+        // OpeningSet: constants | sigmas | wires | zs | zs_next | partial_products | quotient
+        const int o_w = P, o_z = P + W, o_q = P + W + nzp;
+        for (int i = 0; i < o_w; i++) wb.e2v(op[i]);
+        for (int i = 0; i < W; i++) wb.e2v(op[o_w + i]);
+        for (int i = 0; i < NC; i++) wb.e2v(op[o_z + i]);
+        for (int i = 0; i < NC; i++) wb.e2v(zs_next[i]);
+        for (int i = NC; i < nzp; i++) wb.e2v(op[o_z + i]);
+        for (int i = 0; i < nq; i++) wb.e2v(op[o_q + i]);
+    }
+    for (auto& dg : C->fri_caps) wb.digest(dg, hs);
+    for (int q = 0; q < NQ; q++) {
+        for (int o = 0; o < 4 + nl; o++) {
+            size_t wdt = o < 4 ? (size_t)widths[o] : (size_t)2 * (1 << layers[o - 4].ab);
+            wb.put(h_rows.data() + row_off[o] + (size_t)q * wdt, 8 * wdt);
+            wb.u8v((uint8_t)path_len[o]);
+            for (int k = 0; k < path_len[o]; k++) wb.digest(h_paths[path_off[o] + (size_t)q * path_len[o] + k], hs);
+        }
+    }
+    for (size_t i = 0; i < m; i++) {
+        wb.u64v(C->final_poly[2 * i]);
+        wb.u64v(C->final_poly[2 * i + 1]);
+    }
+    wb.u64v(pow_witness);
+    for (size_t i = 0; i < n_pi; i++) wb.u64v(public_inputs[i]);
+    CUDA_CHECK(cudaEventRecord(ev[6], st));
+    CUDA_CHECK(cudaEventSynchronize(ev[6]));
+    C->proved = true;
+
+    if (tm) {
+        float t;
+        cudaEventElapsedTime(&t, ev[0], ev[1]); tm->wires_commit_ms = t;
+        cudaEventElapsedTime(&t, ev[1], ev[2]); tm->zs_pp_ms = t;
+        cudaEventElapsedTime(&t, ev[2], ev[3]); tm->quotient_ms = t;
+        cudaEventElapsedTime(&t, ev[3], ev[4]); tm->openings_ms = t;
+        cudaEventElapsedTime(&t, ev[4], ev[5]); tm->fri_ms = t;
+        cudaEventElapsedTime(&t, ev[5], ev[6]); tm->d2h_ms = t;
+        cudaEventElapsedTime(&t, ev_start ? ev_start : ev[0], ev[6]); tm->total_ms = t;
+        if (ev_start) { cudaEventElapsedTime(&t, ev_start, ev[0]); tm->h2d_ms = t; } else tm->h2d_ms = 0;
+        tm->quotient_kernel_ms = quotient_kernel_ms;
+        tm->ntt_ms = c->ntt_ms;
+        tm->merkle_ms = c->merkle_ms;
+        tm->ntt_bytes = c->ntt_bytes;
+        tm->merkle_bytes = c->merkle_bytes;
+        tm->kernel_launches = c->launches;
+        tm->leaf_hash_launches = c->leaf_launches;
+        tm->leaf_hash_ms = c->leaf_ms;
+        tm->lde_ms = c->lde_ms;
+        tm->leaf_hash_bytes = c->leaf_bytes;
+        tm->lde_bytes = c->lde_bytes;
+        tm->lde_launches = c->lde_launches;
+    }
+    size_t need = wb.len;
+    bool small = !out || need > wb.cap;
+    *out_len = need;
+    if (small) throw p2g_error(P2G_ESMALLBUF, "output buffer too small");
+}
+
+static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u64* public_inputs, size_t n_pi,
+                       const u64* forced_pow, uint8_t* out, size_t* out_len, p2g_timings* tm) {
+    return guard([&] {
+        if (!C || !wires || !out_len || (n_pi && !public_inputs)) throw p2g_error(P2G_EBADARG, "p2g_prove: null argument");
+        if (n_pi != C->d.num_public_inputs) throw p2g_error(P2G_EBADARG, "p2g_prove: public input count");
+        for (size_t i = 0; i < n_pi; i++)
+            if (public_inputs[i] >= GL_P) throw p2g_error(P2G_EBADARG, "p2g_prove: non-canonical public input");
+        std::lock_guard<std::mutex> lk(C->mu);
+        DevCtx* c = C->ctx;
+        CUDA_CHECK(cudaSetDevice(c->device));
+        c->launches = 0;
+        c->ntt_bytes = c->merkle_bytes = c->leaf_bytes = c->lde_bytes = 0;
+        c->ntt_ms = c->merkle_ms = c->leaf_ms = c->lde_ms = 0;
+        c->leaf_launches = c->lde_launches = 0;
+        c->timing = tm != nullptr;
+        if (tm) memset(tm, 0, sizeof(*tm));
+        struct TimingOff {
+            DevCtx* c;
+            ~TimingOff() { c->timing = false; }
+        } toff{c};
+        const u64* d_wires = wires;
+        cudaEvent_t ev_start = nullptr;
+        if (!on_device) {
+            size_t cnt = (size_t)C->d.num_wires * C->n;
+            if (C->wires_values.n != cnt) C->wires_values.alloc(cnt);
+            CUDA_CHECK(cudaEventCreate(&ev_start));
+            CUDA_CHECK(cudaEventRecord(ev_start, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p, wires, cnt * 8, cudaMemcpyHostToDevice, c->stream));
+            d_wires = C->wires_values.p;
+        }
+        struct EvDel {
+            cudaEvent_t e;
+            ~EvDel() { if (e) cudaEventDestroy(e); }
+        } evd{ev_start};
+        prove_impl(C, d_wires, public_inputs, n_pi, forced_pow, out, out_len, tm, ev_start);
+    });
+}
+
+extern "C" int p2g_prove(p2g_circuit* c, const uint64_t* wires, const uint64_t* public_inputs, size_t num_public_inputs,
+                         const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len, p2g_timings* timings) {
+    return prove_entry(c, wires, false, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings);
+}
+extern "C" int p2g_prove_device(p2g_circuit* c, const uint64_t* d_wires, const uint64_t* public_inputs, size_t num_public_inputs,
+                                const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len, p2g_timings* timings) {
+    return prove_entry(c, d_wires, true, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings);
+}
+
+extern "C" int p2g_circuit_read(p2g_circuit* C, int what, void* out, size_t* len) {
+    return guard([&] {
+        if (!C || !len) throw p2g_error(P2G_EBADARG, "p2g_circuit_read: null argument");
+        std::lock_guard<std::mutex> lk(C->mu);
+        DevCtx* c = C->ctx;
+        CUDA_CHECK(cudaSetDevice(c->device));
+        const p2g_circuit_desc& d = C->d;
+        const int NC = d.num_challenges, nzp = NC * (1 + d.num_partial_products), nq = NC * d.quotient_degree_factor;
+        const void* dsrc = nullptr;   // device source
+        const void* hsrc = nullptr;   // host source
+        std::vector<uint8_t> packed;
+        size_t sz = 0;
+        auto cap_of = [&](const MerkleTree& t) {
+            std::vector<digest_t> cap = read_cap(C, t);
+            packed.resize(cap.size() * C->hs);
+            pack_digests(C->h, cap.data(), cap.size(), packed.data());
+            hsrc = packed.data();
+            sz = packed.size();
+        };
+        if (what != P2G_BUF_CS_CAP && !C->proved) throw p2g_error(P2G_EBADARG, "p2g_circuit_read: no proof has been produced yet");
+        switch (what) {
+        case P2G_BUF_WIRES_CAP: cap_of(C->wires.tree); break;
+        case P2G_BUF_ZS_PP_CAP: cap_of(C->zpp.tree); break;
+        case P2G_BUF_QUOTIENT_CAP: cap_of(C->quot.tree); break;
+        case P2G_BUF_CS_CAP: cap_of(C->cs.tree); break;
+        case P2G_BUF_ZS_PP_VALUES: dsrc = C->zpp_values.p; sz = (size_t)nzp * C->n * 8; break;
+        case P2G_BUF_QUOTIENT_CHUNKS: dsrc = C->quot.coeffs.p; sz = (size_t)nq * C->n * 8; break;
+        case P2G_BUF_WIRES_COEFFS: dsrc = C->wires.coeffs.p; sz = (size_t)d.num_wires * C->n * 8; break;
+        case P2G_BUF_CHALLENGES: hsrc = C->challenges.data(); sz = C->challenges.size() * 8; break;
+        case P2G_BUF_FINAL_POLY: hsrc = C->final_poly.data(); sz = C->final_poly.size() * 8; break;
+        case P2G_BUF_FRI_CAPS:
+            packed.resize(C->fri_caps.size() * C->hs);
+            pack_digests(C->h, C->fri_caps.data(), C->fri_caps.size(), packed.data());
+            hsrc = packed.data();
+            sz = packed.size();
+            break;
+        case P2G_BUF_WIRES_LDE: dsrc = C->wires.lde.p; sz = (size_t)d.num_wires * C->lde * 8; break;
+        default: throw p2g_error(P2G_EBADARG, "p2g_circuit_read: unknown buffer");
+        }
+        if (!out || *len < sz) {
+            *len = sz;
+            throw p2g_error(P2G_ESMALLBUF, "p2g_circuit_read: buffer too small");
+        }
+        *len = sz;
+        if (dsrc) {
+            CUDA_CHECK(cudaMemcpyAsync(out, dsrc, sz, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        } else if (sz) {
+            memcpy(out, hsrc, sz);
+        }
+    });
+}
+
+// filtered gate constraints at arbitrary points (evaluate_gate_constraints_base_batch), for gate-level parity tests
+extern "C" int p2g_eval_gate_constraints(const p2g_circuit_desc* desc, const uint64_t* constants, const uint64_t* wires,
+                                         const uint64_t* pi_hash, size_t npoints, uint64_t* out, int device) {
+    return guard([&] {
+        if (!desc || !constants || !wires || !out || !desc->gates) throw p2g_error(P2G_EBADARG, "p2g_eval_gate_constraints: null argument");
+        if (desc->num_gates == 0 || desc->num_gates > P2G_MAX_GATES) throw p2g_error(P2G_EBADARG, "p2g_eval_gate_constraints: gate table");
+        DevCtx* c = get_ctx(device);
+        if (!npoints) return;
+        static thread_local QuotientParams qp;
+        memset(&qp, 0, sizeof(qp));
+        qp.num_selectors = desc->num_selectors;
+        qp.num_constants = desc->num_constants;
+        qp.num_gates = desc->num_gates;
+        for (u32 g = 0; g < desc->num_gates; g++) {
+            const p2g_gate& s = desc->gates[g];
+            if (s.kind >= P2G_GATE_KIND_COUNT || s.num_constraints > desc->num_gate_constraints)
+                throw p2g_error(P2G_EBADARG, "p2g_eval_gate_constraints: bad gate");
+            GateDev& o = qp.gates[g];
+            o.kind = s.kind;
+            for (int k = 0; k < 4; k++) o.params[k] = s.params[k];
+            o.selector_index = s.selector_index;
+            o.group_lo = s.group_lo;
+            o.group_hi = s.group_hi;
+            o.num_constraints = s.num_constraints;
+        }
+        if (pi_hash) memcpy(qp.pi_hash, pi_hash, 32);
+        quotient_upload_params(c, qp);
+        size_t nc = (size_t)desc->num_constants * npoints, nw = (size_t)desc->num_wires * npoints,
+               no = (size_t)desc->num_gate_constraints * npoints;
+        dbuf<u64> dc(nc), dw(nw), dout(std::max<size_t>(no, 1));
+        CUDA_CHECK(cudaMemcpyAsync(dc.p, constants, nc * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(dw.p, wires, nw * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemsetAsync(dout.p, 0, no * 8, c->stream));
+        gates_eval_standalone(c, dc.p, dw.p, dout.p, npoints);
+        CUDA_CHECK(cudaMemcpyAsync(out, dout.p, no * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}

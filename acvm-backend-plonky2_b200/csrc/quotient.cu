@@ -34,7 +34,6 @@ __global__ void __launch_bounds__(128) k_quotient(const u64* __restrict__ cs, co
     const size_t j = j0 + t;
     const size_t L = (size_t)1 << (P.logn + P.rate_bits);
     const int NC = P.num_challenges, NPP = P.num_partial_products, R = P.num_routed, C = P.num_constants;
-    const int nzp = NC * (1 + NPP);
     // next row: natural index + 2^rate_bits  <=>  same coset, k -> k + 1 (k = bitrev_n(j mod N))
     const u32 nmask = (1u << P.logn) - 1;
     const u32 k = bitrev32((u32)j & nmask, P.logn);

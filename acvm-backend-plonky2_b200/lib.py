@@ -47,10 +47,12 @@ class TimingsS(C.Structure):
                 ("quotient_ms", C.c_float), ("openings_ms", C.c_float), ("fri_ms", C.c_float),
                 ("total_ms", C.c_float), ("ntt_ms", C.c_float), ("merkle_ms", C.c_float),
                 ("quotient_kernel_ms", C.c_float), ("ntt_bytes", C.c_double), ("merkle_bytes", C.c_double),
-                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("leaf_hash_launches", C.c_uint32),
+                ("leaf_hash_ms", C.c_float), ("lde_ms", C.c_float), ("leaf_hash_bytes", C.c_double),
+                ("lde_bytes", C.c_double), ("d2h_ms", C.c_float), ("lde_launches", C.c_uint32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)

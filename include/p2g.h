@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define P2G_VERSION 1
+#define P2G_VERSION 2
 
 /* ---- error codes (replace the reference's unwrap()/expect() panics; prove_action.rs:77,96) ---- */
 #define P2G_OK 0
@@ -117,7 +117,13 @@ typedef struct p2g_timings {
     double ntt_bytes;          /* algorithmic bytes moved by the NTT/LDE kernels                 */
     double merkle_bytes;       /* algorithmic bytes hashed                                                             */
     uint32_t kernel_launches;  /* launches of libp2g kernels inside the call                                           */
-    uint32_t reserved;
+    uint32_t leaf_hash_launches; /* launches of the Merkle leaf-hashing kernel (the dominant kernel)                   */
+    float leaf_hash_ms;        /* device time of those launches, CUDA events on the library's stream                   */
+    float lde_ms;              /* device time of the coset-LDE passes alone                                            */
+    double leaf_hash_bytes;    /* algorithmic bytes read by the leaf-hashing launches (8 * leaves * columns)           */
+    double lde_bytes;          /* algorithmic bytes of the LDE passes (8N read + 64N written per column)               */
+    float d2h_ms;              /* query-opening gather + proof assembly                                                */
+    uint32_t lde_launches;
 } p2g_timings;
 
 typedef struct p2g_circuit p2g_circuit;
