@@ -5,4 +5,5 @@ Host-side Python mirror of the reference interface for this path; all compute is
 from . import lib  # noqa: F401
 from .lib import P2GError, build  # noqa: F401
 from . import circuit  # noqa: F401,E402
+from . import synth  # noqa: F401,E402
 from .circuit import CircuitConfig, CircuitData, CommonCircuitData, Gate, ProofWithPublicInputs  # noqa: F401,E402
