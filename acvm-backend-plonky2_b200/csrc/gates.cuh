@@ -22,9 +22,8 @@ struct GateDev {
 
 // l (l-1)(l-2)(l-3): the base-4 limb range check shared by the u32 gates
 __device__ __forceinline__ u64 limb4_check(u64 l) {
-    u64 r = gl_mul(l, gl_sub(l, 1));
-    r = gl_mul(r, gl_sub(l, 2));
-    return gl_mul(r, gl_sub(l, 3));
+    u64 t = gl_mul(l, gl_sub(l, 3));   // l(l-3) = l^2 - 3l ;  (l-1)(l-2) = l^2 - 3l + 2
+    return gl_mul(t, gl_add(t, 2));
 }
 // prod_{v < base} (l - v)
 __device__ __forceinline__ u64 limb_range_product(u64 l, u32 base) {
@@ -33,11 +32,28 @@ __device__ __forceinline__ u64 limb_range_product(u64 l, u32 base) {
     return r;
 }
 
-// W: callable u64(int wire); K: callable u64(int gate_local_constant); S: sink with emit(u64)
-template <class W, class K, class S>
-__device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, const u64* pi_hash, S& sink) {
+// Number of independently evaluable "ops" of a gate (the unit the quotient kernel splits work by); 1 = indivisible.
+__host__ __device__ inline u32 gate_num_ops(u32 kind, const u32* p) {
+    switch (kind) {
+    case P2G_GATE_ARITHMETIC: return p[0];
+    case P2G_GATE_BASE_SUM: return p[1];          // one op per limb (op 0 also carries the sum constraint)
+    case P2G_GATE_RANDOM_ACCESS: return p[1];     // copies (the last one also carries the extra-constant constraints)
+    case P2G_GATE_U32_ARITHMETIC: return p[0];
+    case P2G_GATE_U32_ADD_MANY: return p[1];
+    case P2G_GATE_U32_SUBTRACTION: return p[0];
+    case P2G_GATE_U32_RANGE_CHECK: return p[0];
+    default: return 1;
+    }
+}
+
+// W: callable u64(int wire); K: callable u64(int gate_local_constant); S: sink with seek(int constraint_index), emit(u64).
+// Evaluates ops [op_lo, op_hi) of the gate (all of it for indivisible gates); constraints keep the reference's numbering.
+// KIND is a compile-time constant, so each instantiation contains the code of exactly one gate.
+template <int KIND, class W, class K, class S>
+__device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 op_hi, const W& w, const K& c, const u64* pi_hash,
+                                               S& sink) {
     const u32* p = g.params;
-    switch (g.kind) {
+    switch (KIND) {
     case P2G_GATE_NOOP:
         break;
     case P2G_GATE_CONSTANT:
@@ -48,7 +64,8 @@ __device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, c
         break;
     case P2G_GATE_ARITHMETIC: {
         const u64 c0 = c(0), c1 = c(1);
-        for (u32 i = 0; i < p[0]; i++) {
+        sink.seek(op_lo);
+        for (u32 i = op_lo; i < op_hi; i++) {
             u64 prod = gl_mul(gl_mul(w(4 * i), w(4 * i + 1)), c0);
             sink.emit(gl_sub(w(4 * i + 3), gl_add(prod, gl_mul(w(4 * i + 2), c1))));
         }
@@ -56,10 +73,14 @@ __device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, c
     }
     case P2G_GATE_BASE_SUM: {
         const u32 base = p[0], nl = p[1];
-        u64 acc = 0;
-        for (int k = (int)nl - 1; k >= 0; k--) acc = gl_add(gl_mul_small(acc, base), w(1 + k));
-        sink.emit(gl_sub(acc, w(0)));
-        for (u32 k = 0; k < nl; k++) sink.emit(limb_range_product(w(1 + k), base));
+        if (op_lo == 0) {
+            u64 acc = 0;
+            for (int k = (int)nl - 1; k >= 0; k--) acc = gl_add(gl_mul_small(acc, base), w(1 + k));
+            sink.seek(0);
+            sink.emit(gl_sub(acc, w(0)));
+        }
+        sink.seek(1 + op_lo);
+        for (u32 k = op_lo; k < op_hi; k++) sink.emit(limb_range_product(w(1 + k), base));
         break;
     }
     case P2G_GATE_POSEIDON: {
@@ -125,7 +146,8 @@ __device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, c
         const u32 bits = p[0], copies = p[1], extra = p[2];
         const u32 vec = 1u << bits;
         const u32 routed_used = (2 + vec) * copies + extra;
-        for (u32 cp = 0; cp < copies; cp++) {
+        sink.seek(op_lo * (bits + 2));
+        for (u32 cp = op_lo; cp < op_hi; cp++) {
             const u32 base = (2 + vec) * cp;
             const u32 bw = routed_used + cp * bits;
             u64 rec = 0;
@@ -147,12 +169,14 @@ __device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, c
             }
             sink.emit(gl_sub(items[0], w(base + 1)));
         }
-        for (u32 i = 0; i < extra; i++) sink.emit(gl_sub(c(i), w((2 + vec) * copies + i)));
+        if (op_hi == copies)
+            for (u32 i = 0; i < extra; i++) sink.emit(gl_sub(c(i), w((2 + vec) * copies + i)));
         break;
     }
     case P2G_GATE_U32_ARITHMETIC: {
         const u32 ops = p[0];
-        for (u32 i = 0; i < ops; i++) {
+        sink.seek(op_lo * 36);
+        for (u32 i = op_lo; i < op_hi; i++) {
             const u32 q = 6 * i;
             u64 computed = gl_add(gl_mul(w(q), w(q + 1)), w(q + 2));
             u64 lo = w(q + 3), hi = w(q + 4), inv = w(q + 5);
@@ -174,7 +198,8 @@ __device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, c
     }
     case P2G_GATE_U32_ADD_MANY: {
         const u32 na = p[0], ops = p[1];
-        for (u32 i = 0; i < ops; i++) {
+        sink.seek(op_lo * 21);
+        for (u32 i = op_lo; i < op_hi; i++) {
             const u32 q = (na + 3) * i;
             u64 computed = 0;
             for (u32 j = 0; j <= na; j++) computed = gl_add(computed, w(q + j));  // addends then carry-in
@@ -195,7 +220,8 @@ __device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, c
     }
     case P2G_GATE_U32_SUBTRACTION: {
         const u32 ops = p[0];
-        for (u32 i = 0; i < ops; i++) {
+        sink.seek(op_lo * 19);
+        for (u32 i = op_lo; i < op_hi; i++) {
             const u32 q = 5 * i;
             u64 initial = gl_sub(gl_sub(w(q), w(q + 1)), w(q + 2));
             u64 res = w(q + 3), bout = w(q + 4);
@@ -214,7 +240,8 @@ __device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, c
     }
     case P2G_GATE_U32_RANGE_CHECK: {
         const u32 nl = p[0];
-        for (u32 i = 0; i < nl; i++) {
+        sink.seek(op_lo * 17);
+        for (u32 i = op_lo; i < op_hi; i++) {
             const u32 aw = nl + 16 * i;
             u64 acc = 0;
             for (int j = 15; j >= 0; j--) acc = gl_add(gl_mul_small(acc, 4), w(aw + j));
@@ -259,6 +286,20 @@ __device__ void eval_gate_unfiltered(const GateDev& g, const W& w, const K& c, c
     }
     default:
         break;
+    }
+}
+
+// runtime-kind dispatch (stand-alone gate evaluation)
+template <class W, class K, class S>
+__device__ void eval_gate_unfiltered(const GateDev& g, u32 op_lo, u32 op_hi, const W& w, const K& c, const u64* pi_hash, S& sink) {
+    switch (g.kind) {
+#define P2G_GATE_CASE(KIND) case KIND: eval_gate_kind<KIND>(g, op_lo, op_hi, w, c, pi_hash, sink); break;
+        P2G_GATE_CASE(P2G_GATE_CONSTANT) P2G_GATE_CASE(P2G_GATE_PUBLIC_INPUT) P2G_GATE_CASE(P2G_GATE_ARITHMETIC)
+        P2G_GATE_CASE(P2G_GATE_BASE_SUM) P2G_GATE_CASE(P2G_GATE_POSEIDON) P2G_GATE_CASE(P2G_GATE_RANDOM_ACCESS)
+        P2G_GATE_CASE(P2G_GATE_U32_ARITHMETIC) P2G_GATE_CASE(P2G_GATE_U32_ADD_MANY) P2G_GATE_CASE(P2G_GATE_U32_SUBTRACTION)
+        P2G_GATE_CASE(P2G_GATE_U32_RANGE_CHECK) P2G_GATE_CASE(P2G_GATE_COMPARISON)
+#undef P2G_GATE_CASE
+    default: break;
     }
 }
 

@@ -11,7 +11,24 @@
 #include "internal.h"
 #include "quotient.h"
 
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
 namespace {
+
+// P2G_TRACE=1: host wall-clock trace of the prove stages on stderr (debugging aid)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0, last;
+    Trace() : on(getenv("P2G_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), last(t0) {}
+    void mark(const char* what) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[p2g] %-28s +%8.3f ms  (t=%9.3f)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
 
 __device__ __forceinline__ u64 tab_pow_d(const u64* tab, int split, u32 i) {
     return gl_mul(__ldg(tab + (i & ((1u << split) - 1))), __ldg(tab + (1u << split) + (i >> split)));
@@ -310,6 +327,12 @@ __global__ void k_gather_paths(const digest_t* const* __restrict__ levels, int n
     out[t] = levels[k][(leaf >> k) ^ 1];
 }
 
+template <class T>
+T* ensure(dbuf<T>& b, size_t count) {  // grow-only scratch: no cudaMalloc / cudaFree on the steady-state prove path
+    if (b.n < count) b.alloc(count);
+    return b.p;
+}
+
 struct PolyBatch {
     int ncols = 0, logn = 0;
     dbuf<u64> coeffs;  // [ncols][N]
@@ -341,6 +364,21 @@ struct p2g_circuit {
     std::vector<u64> final_poly;  // c0,c1 interleaved
     std::vector<digest_t> fri_caps;
     bool proved = false;
+    // scratch that survives between proofs
+    struct FriLayer {
+        dbuf<u64> values;  // [2][cur] leaf order
+        PolyBatch tree;
+        size_t cur = 0;
+        int logcur = 0, ab = 0;
+    };
+    struct {
+        dbuf<u64> q, totals, ztab0, ztab1, u, fin, coeffs_a, coeffs_b, rows;
+        dbuf<e2> partial, apow;
+        dbuf<unsigned long long> best;
+        dbuf<u32> idx;
+        dbuf<digest_t> paths;
+        std::vector<FriLayer> layers;
+    } ws;
     // sharding (one process per GPU); world == 1: single device
     int rank = 0, world = 1;
     p2g_allgather_fn allgather = nullptr;
@@ -595,6 +633,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         ~EvGuard() { for (int i = 0; i < 7; i++) cudaEventDestroy(e[i]); }
     } evg{ev};
     CUDA_CHECK(cudaEventRecord(ev[0], st));
+    Trace tr;
 
     // 1. public inputs hash (InnerHasher = Poseidon for both configs)
     u64 pi_hash[4] = {0, 0, 0, 0};
@@ -607,6 +646,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     commit_from_values(C, C->wires, d_wires, n);
     std::vector<digest_t> wires_cap = read_cap(C, C->wires.tree);
     CUDA_CHECK(cudaEventRecord(ev[1], st));
+    tr.mark("wires commit");
 
     // 3-4. transcript
     challenger_t ch;
@@ -634,9 +674,8 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         CUDA_CHECK(cudaMemcpyToSymbolAsync(d_zp, &zp, sizeof(zp), 0, cudaMemcpyHostToDevice, st));
         int xsplit;
         const u64* xtab = c->get_powtab(logn, gl_root_of_unity(logn), 1, &xsplit);
-        dbuf<u64> q((size_t)NC * nchunk * n);
         size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
-        dbuf<u64> totals((size_t)NC * nt);
+        struct { u64* p; } q = {ensure(C->ws.q, (size_t)NC * nchunk * n)}, totals = {ensure(C->ws.totals, 4 * nt)};
         dim3 g1((unsigned)((n + 127) / 128), NC);
         k_zpp_chunks<<<g1, 128, 0, st>>>(d_wires, n, C->sigma_values.p, xtab, xsplit, q.p);
         dim3 g2((unsigned)((nt + 127) / 128), NC);
@@ -645,11 +684,17 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         k_zscan_apply<<<g2, 128, 0, st>>>(q.p, totals.p, nt, C->zpp_values.p);
         count_launch(c, 4);
         CUDA_CHECK(cudaGetLastError());
+        tr.mark("zpp launches");
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        tr.mark("zpp kernels done");
         commit_from_values(C, C->zpp, C->zpp_values.p, n);
+        tr.mark("zpp commit launched");
     }
+    tr.mark("zpp frees");
     std::vector<digest_t> zpp_cap = read_cap(C, C->zpp.tree);
     for (auto& dg : zpp_cap) ch.observe_digest(dg);
     CUDA_CHECK(cudaEventRecord(ev[2], st));
+    tr.mark("zpp cap + observe");
 
     // 6. alphas
     for (int i = 0; i < NC; i++) alphas[i] = ch.get();
@@ -689,7 +734,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         CUDA_CHECK(cudaEventCreate(&qa));
         CUDA_CHECK(cudaEventCreate(&qb));
         CUDA_CHECK(cudaEventRecord(qa, st));
-        quotient_eval(c, C->cs.lde.p, C->wires.lde.p, C->zpp.lde.p, C->xs.p, C->l0s.p, qv, 0, lde);
+        quotient_eval(c, qp, C->cs.lde.p, C->wires.lde.p, C->zpp.lde.p, C->xs.p, C->l0s.p, qv, lde);
         CUDA_CHECK(cudaEventRecord(qb, st));
         ntt_coset_ifft_leaforder(c, qv, lde, C->loglde, NC, GL_GEN);
         CUDA_CHECK(cudaEventSynchronize(qb));
@@ -702,6 +747,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     std::vector<digest_t> quot_cap = read_cap(C, C->quot.tree);
     for (auto& dg : quot_cap) ch.observe_digest(dg);
     CUDA_CHECK(cudaEventRecord(ev[3], st));
+    tr.mark("quotient");
 
     // 8. zeta
     e2 zeta = ch.get_e2();
@@ -714,14 +760,14 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     PolyBatch* oracles[4] = {&C->cs, &C->wires, &C->zpp, &C->quot};
     const int widths[4] = {P, W, nzp, nq};
     const int total = P + W + nzp + nq;
-    dbuf<u64> ztab0(2 * n), ztab1(2 * n);
+    struct { u64* p; } ztab0 = {ensure(C->ws.ztab0, 2 * n)}, ztab1 = {ensure(C->ws.ztab1, 2 * n)};
     k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0.p, n, zeta);
     k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1.p, n, zeta_next);
     count_launch(c, 2);
     const int nsplit = (int)((n + EVAL_SPLIT - 1) / EVAL_SPLIT);
     std::vector<e2> op(total), zs_next(NC);
     {
-        dbuf<e2> partial((size_t)(total + NC) * nsplit);
+        struct { e2* p; } partial = {ensure(C->ws.partial, (size_t)(total + NC) * nsplit)};
         int off = 0;
         for (int o = 0; o < 4; o++) {
             dim3 grid(widths[o], nsplit);
@@ -745,11 +791,12 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     for (int i = 0; i < total; i++) ch.observe_e2(op[i]);
     for (int i = 0; i < NC; i++) ch.observe_e2(zs_next[i]);
     CUDA_CHECK(cudaEventRecord(ev[4], st));
+    tr.mark("openings");
 
     // 10. FRI
     e2 fri_alpha = ch.get_e2();
     const int nl = d.num_fri_layers;
-    dbuf<u64> fin(2 * n);  // final polynomial, re | im
+    struct { u64* p; } fin = {ensure(C->ws.fin, 2 * n)};  // final polynomial, re | im
     {
         std::vector<e2> apow(total);
         e2 a = e2_make(1, 0);
@@ -757,7 +804,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             apow[j] = a;
             a = e2_mul(a, fri_alpha);
         }
-        dbuf<e2> d_apow(total);
+        struct { e2* p; } d_apow = {ensure(C->ws.apow, total)};
         CUDA_CHECK(cudaMemcpyAsync(d_apow.p, apow.data(), sizeof(e2) * total, cudaMemcpyHostToDevice, st));
         CombineArgs ca = {};
         for (int o = 0; o < 4; o++) {
@@ -767,7 +814,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         }
         ca.num_challenges = NC;
         ca.logn = logn;
-        dbuf<u64> u(4 * n);
+        struct { u64* p; } u = {ensure(C->ws.u, 4 * n)};
         k_fri_combine<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ca, d_apow.p, ztab0.p, ztab1.p, u.p);
         // tables of inverse powers (reuse the forward tables' storage after the combine)
         e2 zi0, zi1;  // inverse in F_{p^2}: z^-1 = conj(z) / norm(z)
@@ -783,7 +830,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0.p, n, zi0);
         k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1.p, n, zi1);
         size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
-        dbuf<u64> totals(4 * nt);
+        struct { u64* p; } totals = {ensure(C->ws.totals, 4 * nt)};
         dim3 g2((unsigned)((nt + 127) / 128), 4);
         k_sscan_totals<<<g2, 128, 0, st>>>(u.p, totals.p, n, nt);
         k_scan_add_suffix_excl<<<4, 1024, 0, st>>>(totals.p, nt);
@@ -793,29 +840,26 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaStreamSynchronize(st));
     }
+    tr.mark("fri combine");
     // commit phase
-    struct Layer {
-        dbuf<u64> values;  // [2][cur] leaf order
-        PolyBatch tree;
-        size_t cur;
-        int logcur, ab;
-    };
-    std::vector<Layer> layers(nl);
+    typedef p2g_circuit::FriLayer Layer;
+    std::vector<Layer>& layers = C->ws.layers;
+    if ((int)layers.size() != nl) layers.resize(nl);
     std::vector<e2> fri_betas(nl);
     C->fri_caps.clear();
-    dbuf<u64> coeffs_a(2 * n), coeffs_b;
+    struct { u64* p; } coeffs_a = {ensure(C->ws.coeffs_a, 2 * n)}, coeffs_b = {nullptr};
     CUDA_CHECK(cudaMemcpyAsync(coeffs_a.p, fin.p, 16 * n, cudaMemcpyDeviceToDevice, st));
     u64* cur_coeffs = coeffs_a.p;
     size_t m = n;  // number of (possibly) non-zero coefficients
     int logm = logn;
     u64 shift = GL_GEN;
-    if (nl) coeffs_b.alloc(2 * (n >> d.reduction_arity_bits[0]) + 2);
+    if (nl) coeffs_b.p = ensure(C->ws.coeffs_b, 2 * (n >> d.reduction_arity_bits[0]) + 2);
     for (int l = 0; l < nl; l++) {
         Layer& L = layers[l];
         L.ab = d.reduction_arity_bits[l];
         L.logcur = logm + d.rate_bits;
         L.cur = (size_t)1 << L.logcur;
-        L.values.alloc(2 * L.cur);
+        ensure(L.values, 2 * L.cur);
         // values = coset_fft(coeffs.lde(rate_bits), shift), both components, leaf order
         ntt_lde(c, cur_coeffs, m, L.values.p, L.cur, logm, d.rate_bits, 2, shift);
         const int arity = 1 << L.ab;
@@ -849,13 +893,14 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         }
     }
     for (size_t i = 0; i < m; i++) ch.observe_e2(e2_make(C->final_poly[2 * i], C->final_poly[2 * i + 1]));
+    tr.mark("fri commit phase");
 
     // proof of work
     u64 pow_witness = 0;
     if (forced_pow) {
         pow_witness = *forced_pow;
     } else {
-        dbuf<unsigned long long> best(1);
+        struct { unsigned long long* p; } best = {ensure(C->ws.best, 1)};
         const u64 batch = (u64)1 << 20;
         for (u64 start = 0;; start += batch) {
             CUDA_CHECK(cudaMemsetAsync(best.p, 0xff, 8, st));
@@ -880,6 +925,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     std::vector<u32> indices(NQ);
     for (int q = 0; q < NQ; q++) indices[q] = (u32)(ch.get() % (u64)lde);
     CUDA_CHECK(cudaEventRecord(ev[5], st));
+    tr.mark("pow + indices");
 
     // challenges dump (P2G_BUF_CHALLENGES)
     C->challenges.clear();
@@ -898,7 +944,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     for (int q = 0; q < NQ; q++) C->challenges.push_back(indices[q]);
 
     // query rounds: gather opened rows and Merkle paths on the device, one D2H
-    dbuf<u32> d_idx(NQ);
+    struct { u32* p; } d_idx = {ensure(C->ws.idx, NQ)};
     CUDA_CHECK(cudaMemcpyAsync(d_idx.p, indices.data(), 4 * NQ, cudaMemcpyHostToDevice, st));
     size_t row_words = 0, path_digests = 0;
     size_t row_off[4 + P2G_MAX_FRI_LAYERS], path_off[4 + P2G_MAX_FRI_LAYERS];
@@ -917,8 +963,8 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         path_len[4 + l] = (int)layers[l].tree.tree.levels.size() - 1;
         path_digests += (size_t)NQ * path_len[4 + l];
     }
-    dbuf<u64> d_rows(row_words);
-    dbuf<digest_t> d_paths(path_digests + 1);
+    struct { u64* p; } d_rows = {ensure(C->ws.rows, row_words)};
+    struct { digest_t* p; } d_paths = {ensure(C->ws.paths, path_digests + 1)};
     for (int o = 0; o < 4; o++) {
         int cnt = NQ * widths[o];
         k_gather_rows<<<(cnt + 127) / 128, 128, 0, st>>>(oracles[o]->lde.p, lde, widths[o], d_idx.p, NQ, d_rows.p + row_off[o]);
@@ -983,6 +1029,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     for (size_t i = 0; i < n_pi; i++) wb.u64v(public_inputs[i]);
     CUDA_CHECK(cudaEventRecord(ev[6], st));
     CUDA_CHECK(cudaEventSynchronize(ev[6]));
+    tr.mark("queries + serialise");
     C->proved = true;
 
     if (tm) {

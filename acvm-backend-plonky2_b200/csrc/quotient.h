@@ -19,9 +19,10 @@ struct QuotientParams {
     GateDev gates[P2G_MAX_GATES];
 };
 
+
 struct DevCtx;
 void quotient_upload_params(DevCtx* c, const QuotientParams& p);
 void quotient_points(DevCtx* c, u64* d_xs, u64* d_l0s, int logn, int rate_bits, const u64* h_zh);
-void quotient_eval(DevCtx* c, const u64* d_cs, const u64* d_wires, const u64* d_zpp, const u64* d_xs, const u64* d_l0s,
-                   u64* d_out, size_t j0, size_t count);
+void quotient_eval(DevCtx* c, const QuotientParams& qp, const u64* d_cs, const u64* d_wires, const u64* d_zpp, const u64* d_xs,
+                   const u64* d_l0s, u64* d_out, size_t lde);
 void gates_eval_standalone(DevCtx* c, const u64* d_consts, const u64* d_wires, u64* d_out, size_t npoints);
