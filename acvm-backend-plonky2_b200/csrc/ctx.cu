@@ -244,3 +244,51 @@ extern "C" void p2g_host_two_to_one(uint32_t hasher, const uint8_t* l, const uin
     memcpy(out, &o, hs);
 }
 extern "C" uint64_t p2g_host_gl_mul(uint64_t a, uint64_t b) { return gl_mul(a, b); }
+
+// ---- field-arithmetic self-test: the PTX carry-chain forms of gl.cuh against big-integer arithmetic on the host ----
+// op: 0 sub(a N, b<=p)  1 add(a N, b C)  2 mul  3 glz_mul  4 mul_small(a, (u32)b)  5 canon(a)  6 glz_reduce128(hi=a, lo=b)
+//     7 gl_acc dot product over groups of 8: out[i] = sum_k a[8i+k] b[8i+k]   (out has n/8 entries)
+// Results of N-class ops are canonicalised before they are returned.
+GL_HD u64 field_op(int op, const u64* a, const u64* b, size_t i) {
+    switch (op) {
+    case 0: return gl_canon(gl_sub(a[i], b[i]));
+    case 1: return gl_canon(gl_add(a[i], b[i]));
+    case 2: return gl_mul(a[i], b[i]);
+    case 3: return gl_canon(glz_mul(a[i], b[i]));
+    case 4: return gl_mul_small(a[i], (u32)b[i]);
+    case 5: return gl_canon(a[i]);
+    case 6: return gl_canon(glz_reduce128(a[i], b[i]));
+    case 7: {
+        gl_acc acc;
+        acc.clear();
+        for (int k = 0; k < 8; k++) acc.mac(a[8 * i + k], b[8 * i + k]);
+        return acc.reduce();
+    }
+    default: return 0;
+    }
+}
+namespace {
+__global__ void k_field_ops(int op, const u64* a, const u64* b, u64* out, size_t nout) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nout) out[i] = field_op(op, a, b, i);
+}
+}  // namespace
+extern "C" int p2g_test_field_ops(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, int device) {
+    return guard([&] {
+        if (!a || !b || !out || op < 0 || op > 7) throw p2g_error(P2G_EBADARG, "p2g_test_field_ops: bad argument");
+        size_t nout = op == 7 ? n / 8 : n;
+        if (!nout) return;
+        if (device < 0) {  // host twin
+            for (size_t i = 0; i < nout; i++) out[i] = field_op(op, a, b, i);
+            return;
+        }
+        DevCtx* c = get_ctx(device);
+        dbuf<u64> da(n), db(n), dout(nout);
+        CUDA_CHECK(cudaMemcpyAsync(da.p, a, n * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(db.p, b, n * 8, cudaMemcpyHostToDevice, c->stream));
+        k_field_ops<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(op, da.p, db.p, dout.p, nout);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(out, dout.p, nout * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}

@@ -22,13 +22,13 @@ struct GateDev {
 
 // l (l-1)(l-2)(l-3): the base-4 limb range check shared by the u32 gates
 __device__ __forceinline__ u64 limb4_check(u64 l) {
-    u64 t = gl_mul(l, gl_sub(l, 3));   // l(l-3) = l^2 - 3l ;  (l-1)(l-2) = l^2 - 3l + 2
-    return gl_mul(t, gl_add(t, 2));
+    u64 t = glz_mul(l, gl_sub(l, 3));   // l(l-3) = l^2 - 3l ;  (l-1)(l-2) = l^2 - 3l + 2        (l: C; result N)
+    return glz_mul(t, gl_add(t, 2));
 }
 // prod_{v < base} (l - v)
 __device__ __forceinline__ u64 limb_range_product(u64 l, u32 base) {
     u64 r = l;
-    for (u32 v = 1; v < base; v++) r = gl_mul(r, gl_sub(l, v));
+    for (u32 v = 1; v < base; v++) r = glz_mul(r, gl_sub(l, v));   // l: C; result N
     return r;
 }
 
@@ -47,6 +47,8 @@ __host__ __device__ inline u32 gate_num_ops(u32 kind, const u32* p) {
 }
 
 // W: callable u64(int wire); K: callable u64(int gate_local_constant); S: sink with seek(int constraint_index), emit(u64).
+// Wires and constants are canonical (class C of gl.cuh); emitted constraint values may be unreduced (class N): the sinks
+// only ever multiply them.  Second operands of gl_sub / gl_add are always C.
 // Evaluates ops [op_lo, op_hi) of the gate (all of it for indivisible gates); constraints keep the reference's numbering.
 // KIND is a compile-time constant, so each instantiation contains the code of exactly one gate.
 template <int KIND, class W, class K, class S>
@@ -66,7 +68,7 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
         const u64 c0 = c(0), c1 = c(1);
         sink.seek(op_lo);
         for (u32 i = op_lo; i < op_hi; i++) {
-            u64 prod = gl_mul(gl_mul(w(4 * i), w(4 * i + 1)), c0);
+            u64 prod = gl_mul(glz_mul(w(4 * i), w(4 * i + 1)), c0);
             sink.emit(gl_sub(w(4 * i + 3), gl_add(prod, gl_mul(w(4 * i + 2), c1))));
         }
         break;
@@ -75,7 +77,7 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
         const u32 base = p[0], nl = p[1];
         if (op_lo == 0) {
             u64 acc = 0;
-            for (int k = (int)nl - 1; k >= 0; k--) acc = gl_add(gl_mul_small(acc, base), w(1 + k));
+            for (int k = (int)nl - 1; k >= 0; k--) acc = gl_add(glz_mul_small(acc, base), w(1 + k));   // N + C -> N
             sink.seek(0);
             sink.emit(gl_sub(acc, w(0)));
         }
@@ -87,7 +89,7 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
         // wires: in 0..12, out 12..24, swap 24, delta 25..29, full-round-0 sbox inputs 29..65 (rounds 1-3),
         // partial sbox inputs 65..87, full-round-1 sbox inputs 87..135
         const u64 swap = w(24);
-        sink.emit(gl_mul(swap, gl_sub(swap, 1)));
+        sink.emit(glz_mul(swap, gl_sub(swap, 1)));
         u64 st[12];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -153,7 +155,7 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
             u64 rec = 0;
             for (u32 i = 0; i < bits; i++) {
                 u64 b = w(bw + i);
-                sink.emit(gl_mul(b, gl_sub(b, 1)));
+                sink.emit(glz_mul(b, gl_sub(b, 1)));
             }
             for (int i = (int)bits - 1; i >= 0; i--) rec = gl_add(gl_dbl(rec), w(bw + i));
             sink.emit(gl_sub(rec, w(base)));
@@ -181,15 +183,15 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
             u64 computed = gl_add(gl_mul(w(q), w(q + 1)), w(q + 2));
             u64 lo = w(q + 3), hi = w(q + 4), inv = w(q + 5);
             u64 hi_not_max = gl_sub(gl_mul(inv, gl_sub(0xFFFFFFFFULL, hi)), 1);
-            sink.emit(gl_mul(hi_not_max, lo));
+            sink.emit(glz_mul(hi_not_max, lo));
             sink.emit(gl_sub(gl_add(gl_mul(hi, 1ULL << 32), lo), computed));
             u64 comb_lo = 0, comb_hi = 0;
             const u32 lw = 6 * ops + 32 * i;
             for (int j = 31; j >= 0; j--) {
                 u64 limb = w(lw + j);
                 sink.emit(limb4_check(limb));
-                if (j < 16) comb_lo = gl_add(gl_mul_small(comb_lo, 4), limb);
-                else comb_hi = gl_add(gl_mul_small(comb_hi, 4), limb);
+                if (j < 16) comb_lo = gl_add(glz_mul_small(comb_lo, 4), limb);   // N + C -> N
+                else comb_hi = gl_add(glz_mul_small(comb_hi, 4), limb);
             }
             sink.emit(gl_sub(comb_lo, lo));
             sink.emit(gl_sub(comb_hi, hi));
@@ -210,8 +212,8 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
             for (int j = 17; j >= 0; j--) {
                 u64 limb = w(lw + j);
                 sink.emit(limb4_check(limb));
-                if (j < 16) comb_res = gl_add(gl_mul_small(comb_res, 4), limb);
-                else comb_carry = gl_add(gl_mul_small(comb_carry, 4), limb);
+                if (j < 16) comb_res = gl_add(glz_mul_small(comb_res, 4), limb);
+                else comb_carry = gl_add(glz_mul_small(comb_carry, 4), limb);
             }
             sink.emit(gl_sub(comb_res, res));
             sink.emit(gl_sub(comb_carry, carry));
@@ -231,10 +233,10 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
             for (int j = 15; j >= 0; j--) {
                 u64 limb = w(lw + j);
                 sink.emit(limb4_check(limb));
-                comb = gl_add(gl_mul_small(comb, 4), limb);
+                comb = gl_add(glz_mul_small(comb, 4), limb);
             }
             sink.emit(gl_sub(comb, res));
-            sink.emit(gl_mul(bout, gl_sub(1, bout)));
+            sink.emit(glz_mul(bout, gl_sub(1, bout)));
         }
         break;
     }
@@ -244,7 +246,7 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
         for (u32 i = op_lo; i < op_hi; i++) {
             const u32 aw = nl + 16 * i;
             u64 acc = 0;
-            for (int j = 15; j >= 0; j--) acc = gl_add(gl_mul_small(acc, 4), w(aw + j));
+            for (int j = 15; j >= 0; j--) acc = gl_add(glz_mul_small(acc, 4), w(aw + j));
             sink.emit(gl_sub(acc, w(i)));
             for (int j = 0; j < 16; j++) sink.emit(limb4_check(w(aw + j)));
         }
@@ -256,8 +258,8 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
         const u32 W_FC = 4, W_SC = 4 + nc, W_EQD = 4 + 2 * nc, W_CHEQ = 4 + 3 * nc, W_INT = 4 + 4 * nc, W_BITS = 4 + 5 * nc;
         u64 fcomb = 0, scomb = 0;
         for (int i = (int)nc - 1; i >= 0; i--) {
-            fcomb = gl_add(gl_mul_small(fcomb, cs), w(W_FC + i));
-            scomb = gl_add(gl_mul_small(scomb, cs), w(W_SC + i));
+            fcomb = gl_add(glz_mul_small(fcomb, cs), w(W_FC + i));
+            scomb = gl_add(glz_mul_small(scomb, cs), w(W_SC + i));
         }
         sink.emit(gl_sub(fcomb, w(0)));
         sink.emit(gl_sub(scomb, w(1)));
@@ -269,7 +271,7 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
             u64 diff = gl_sub(s, f);
             u64 eqd = w(W_EQD + i), cheq = w(W_CHEQ + i), inter = w(W_INT + i);
             sink.emit(gl_sub(gl_mul(diff, eqd), gl_sub(1, cheq)));
-            sink.emit(gl_mul(cheq, diff));
+            sink.emit(glz_mul(cheq, diff));
             sink.emit(gl_sub(inter, gl_mul(cheq, msd)));
             msd = gl_add(inter, gl_mul(gl_sub(1, cheq), diff));
         }
@@ -277,7 +279,7 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
         u64 bcomb = 0;
         for (u32 i = 0; i <= cb; i++) {
             u64 b = w(W_BITS + i);
-            sink.emit(gl_mul(b, gl_sub(1, b)));
+            sink.emit(glz_mul(b, gl_sub(1, b)));
         }
         for (int i = (int)cb; i >= 0; i--) bcomb = gl_add(gl_dbl(bcomb), w(W_BITS + i));
         sink.emit(gl_sub(gl_add(w(3), cs), bcomb));
@@ -307,7 +309,7 @@ __device__ void eval_gate_unfiltered(const GateDev& g, u32 op_lo, u32 op_hi, con
 __device__ __forceinline__ u64 gate_filter(const GateDev& g, u32 row, u64 s, bool many_selectors) {
     u64 r = 1;
     for (u32 i = g.group_lo; i < g.group_hi; i++)
-        if (i != row) r = gl_mul(r, gl_sub((u64)i, s));
-    if (many_selectors) r = gl_mul(r, gl_sub(0xFFFFFFFFULL, s));
+        if (i != row) r = glz_mul(r, gl_sub((u64)i, s));
+    if (many_selectors) r = glz_mul(r, gl_sub(0xFFFFFFFFULL, s));   // result N
     return r;
 }

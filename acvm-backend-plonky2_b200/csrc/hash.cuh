@@ -168,9 +168,10 @@ GL_HD digest_t keccak25_two_to_one(const digest_t& l, const digest_t& r) {
 #define POSEIDON_RC(i) P2G_POSEIDON_RC[i]
 #endif
 
+// x: N -> x^7: N (the MDS layer that always follows splits its inputs into 32-bit halves and accepts any u64)
 GL_HD u64 poseidon_sbox(u64 x) {
-    u64 x2 = gl_sqr(x), x4 = gl_sqr(x2), x3 = gl_mul(x2, x);
-    return gl_mul(x3, x4);
+    u64 x2 = glz_sqr(x), x4 = glz_sqr(x2), x3 = glz_mul(x2, x);
+    return glz_mul(x3, x4);
 }
 
 // MDS row sums over split 32-bit halves: every partial sum stays below 2^42, so no carries until the final recombination

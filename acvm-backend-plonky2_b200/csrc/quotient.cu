@@ -15,13 +15,13 @@ __constant__ QuotientParams d_qp;
 
 namespace {
 
-struct WeightedSink {  // folds constraint k into sum_c += v * alpha_c^(off + k)
-    u64 s0, s1;
+struct WeightedSink {  // folds constraint k into sum_c += v * alpha_c^(off + k); products accumulated unreduced (gl_acc)
+    gl_acc a0, a1;
     int k, base;
     __device__ __forceinline__ void seek(int idx) { k = base + idx; }
-    __device__ __forceinline__ void emit(u64 v) {
-        s0 = gl_add(s0, gl_mul(v, d_qp.apow[0][k]));
-        s1 = gl_add(s1, gl_mul(v, d_qp.apow[1][k]));
+    __device__ __forceinline__ void emit(u64 v) {   // v: class N
+        a0.mac(v, d_qp.apow[0][k]);
+        a1.mac(v, d_qp.apow[1][k]);
         k++;
     }
 };
@@ -46,13 +46,15 @@ __global__ void __launch_bounds__(256) k_quotient_perm(const u64* __restrict__ c
     const size_t jn = (j & ~(size_t)nmask) | bitrev32((k + 1) & nmask, P.logn);
     const u64 x = xs[j], l0 = l0s[j];
     const int chunk = P.qdf;
+    gl_acc acc0, acc1;   // the two alpha-weighted sums, one reduction each at the end
+    acc0.clear();
+    acc1.clear();
     for (int c = 0; c < NC; c++) {
-        u64 acc0 = 0, acc1 = 0;
         u64 prev = zpp[(size_t)c * L + j];
         {   // L_0(x) (Z_c(x) - 1)
-            u64 tz = gl_mul(l0, gl_sub(prev, 1));
-            acc0 = gl_mul(tz, P.apow[0][c]);
-            acc1 = gl_mul(tz, P.apow[1][c]);
+            u64 tz = glz_mul(l0, gl_sub(prev, 1));
+            acc0.mac(tz, P.apow[0][c]);
+            acc1.mac(tz, P.apow[1][c]);
         }
         const u64 gamma = P.gammas[c], beta = P.betas[c];
         const int term = NC + c * (NPP + 1);
@@ -61,23 +63,18 @@ __global__ void __launch_bounds__(256) k_quotient_perm(const u64* __restrict__ c
             int hi = min((m + 1) * chunk, R);
             for (int r = m * chunk; r < hi; r++) {
                 u64 base = gl_add(wires[(size_t)r * L + j], gamma);
-                pn = gl_mul(pn, gl_add(base, gl_mul(P.beta_k[c][r], x)));
-                pd = gl_mul(pd, gl_add(base, gl_mul(beta, cs[(size_t)(C + r) * L + j])));
+                pn = glz_mul(pn, gl_add(base, gl_mul(P.beta_k[c][r], x)));
+                pd = glz_mul(pd, gl_add(base, gl_mul(beta, cs[(size_t)(C + r) * L + j])));
             }
             u64 next = (m < NPP) ? zpp[(size_t)(NC + c * NPP + m) * L + j] : zpp[(size_t)c * L + jn];
-            u64 tv = gl_sub(gl_mul(prev, pn), gl_mul(next, pd));
-            acc0 = gl_add(acc0, gl_mul(tv, P.apow[0][term + m]));
-            acc1 = gl_add(acc1, gl_mul(tv, P.apow[1][term + m]));
+            u64 tv = gl_sub(glz_mul(prev, pn), gl_mul(next, pd));
+            acc0.mac(tv, P.apow[0][term + m]);
+            acc1.mac(tv, P.apow[1][term + m]);
             prev = next;
         }
-        if (c == 0) {
-            out[j] = acc0;
-            if (NC > 1) out[L + j] = acc1;
-        } else {
-            out[j] = gl_add(out[j], acc0);
-            out[L + j] = gl_add(out[L + j], acc1);
-        }
     }
+    out[j] = acc0.reduce();
+    if (NC > 1) out[L + j] = acc1.reduce();
     if (scale_now) {
         const u64 zhi = P.zh_inv[bitrev32((u32)(j >> P.logn), P.rate_bits)];
         out[j] = gl_mul(out[j], zhi);
@@ -97,10 +94,13 @@ __global__ void __launch_bounds__(256) k_quotient_gate(const u64* __restrict__ c
     auto konst = [&](int i) -> u64 { return __ldg(cs + (size_t)(P.num_selectors + i) * L + j); };
     const int off = P.num_challenges * (2 + P.num_partial_products);
     u64 f = gate_filter(gd, g, cs[(size_t)gd.selector_index * L + j], P.num_selectors > 1);
-    WeightedSink sink = {0, 0, off, off};
+    WeightedSink sink;
+    sink.a0.clear();
+    sink.a1.clear();
+    sink.k = sink.base = off;
     eval_gate_kind<KIND>(gd, op_lo, op_hi, wire, konst, P.pi_hash, sink);
-    u64 a0 = gl_add(out[j], gl_mul(f, sink.s0));
-    u64 a1 = P.num_challenges > 1 ? gl_add(out[L + j], gl_mul(f, sink.s1)) : 0;
+    u64 a0 = gl_add(out[j], gl_mul(f, sink.a0.reduce()));
+    u64 a1 = P.num_challenges > 1 ? gl_add(out[L + j], gl_mul(f, sink.a1.reduce())) : 0;
     if (scale_now) {
         const u64 zhi = P.zh_inv[bitrev32((u32)(j >> P.logn), P.rate_bits)];
         a0 = gl_mul(a0, zhi);

@@ -61,7 +61,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 EXPORTS = ["p2g_version", "p2g_device_count", "p2g_last_error", "p2g_circuit_create", "p2g_circuit_destroy",
            "p2g_circuit_cap", "p2g_prove", "p2g_prove_device", "p2g_proof_size_bound", "p2g_circuit_set_sharding",
            "p2g_circuit_read", "p2g_ifft", "p2g_lde", "p2g_coset_ifft_leaforder", "p2g_merkle_cap",
-           "p2g_poseidon_permute", "p2g_keccak256", "p2g_eval_gate_constraints"]
+           "p2g_poseidon_permute", "p2g_keccak256", "p2g_eval_gate_constraints", "p2g_test_field_ops"]
 
 
 def build(force=False, verbose=False):
@@ -109,6 +109,7 @@ def lib():
         L.p2g_keccak256.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int]
         L.p2g_eval_gate_constraints.argtypes = [C.POINTER(DescS), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                                 C.c_void_p, C.c_int]
+        L.p2g_test_field_ops.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         _LIB = L
     return _LIB
 
@@ -177,4 +178,15 @@ def keccak256(msgs, device=0):
     n, ln = m.shape
     out = np.empty((n, 32), dtype=np.uint8)
     check(lib().p2g_keccak256(_p(m), ln, n, _p(out), device))
+    return out
+
+
+FIELD_OPS = {"sub": 0, "add": 1, "mul": 2, "mulz": 3, "mul_small": 4, "canon": 5, "reduce128": 6, "dot8": 7}
+
+
+def field_ops(op, a, b, device=0):
+    """Self-test of csrc/gl.cuh: device >= 0 runs the sm_100a PTX forms, device < 0 their host twins."""
+    a, b = _u64(a), _u64(b)
+    out = np.empty(a.size // 8 if op == "dot8" else a.size, dtype=np.uint64)
+    check(lib().p2g_test_field_ops(FIELD_OPS[op], _p(a), _p(b), _p(out), a.size, device))
     return out

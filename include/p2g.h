@@ -202,6 +202,9 @@ int p2g_keccak256(const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* out, i
 int p2g_eval_gate_constraints(const p2g_circuit_desc* desc, const uint64_t* constants, const uint64_t* wires,
                               const uint64_t* pi_hash, size_t npoints, uint64_t* out, int device);
 
+/* field-arithmetic self-test of the device (device >= 0) or host (device < 0) forms of csrc/gl.cuh; see ctx.cu for `op` */
+int p2g_test_field_ops(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, int device);
+
 #ifdef __cplusplus
 }
 #endif
