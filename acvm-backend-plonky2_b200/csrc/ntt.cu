@@ -16,6 +16,8 @@
 //    (leaves [r*N,(r+1)*N) = coset shift*omega_{8N}^{bitrev3(r)}), never a zero-padded size-8N transform;
 //  * inverse transforms are decimation-in-time (bit-reversed in -> natural out); for natural-order input (the witness) the
 //    first pass gathers bit-reversed 64-byte runs, so no separate permutation pass exists either.
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace {
@@ -37,6 +39,7 @@ struct PassArgs {
     size_t stab_zs;            // per-coset table stride
     u64 scale;                 // constant multiplier on store (1 = none)
     int gather;                // contiguous inverse pass: input is in natural order, gather bit-reversed runs
+    u32 nz;                    // cosets per tile (grid.x = tiles * nz)
 };
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -86,75 +89,114 @@ __device__ __forceinline__ u64 tab_pow(const u64* tab, int split, u32 i) {
     return gl_mul(lo, hi);
 }
 
-// log2(A) butterfly stages over `rows` independent rows; element (m, r) lives at s[m * sm_m + r * sm_r]
-template <bool INV>
-__device__ __forceinline__ void smem_butterflies(u64* s, const u64* s_tw, int loga, int logr, int sm_m, int sm_r, bool r_fast) {
-    const int A = 1 << loga;
-    const int total = (A >> 1) << logr;
-    for (int st = 0; st < loga; st++) {
-        const int u = INV ? (loga - 1 - st) : st;
-        const int lh = loga - 1 - u;  // log2(half)
-        const int half = 1 << lh;
-        const u64* twu = s_tw + (A - (A >> u));
-        for (int e = threadIdx.x; e < total; e += blockDim.x) {
-            int p, r;
-            if (r_fast) {
-                r = e & ((1 << logr) - 1);
-                p = e >> logr;
-            } else {
-                p = e & ((A >> 1) - 1);
-                r = e >> (loga - 1);
-            }
-            int j = p & (half - 1);
-            int lo = ((p >> lh) << (lh + 1)) | j;
-            u64* x0 = s + lo * sm_m + r * sm_r;
-            u64* x1 = x0 + half * sm_m;
-            u64 a = *x0, b = *x1, w = twu[j];
-            if (INV) {
-                b = gl_mul(b, w);
-                *x0 = gl_add(a, b);
-                *x1 = gl_sub(a, b);
-            } else {
-                *x0 = gl_add(a, b);
-                *x1 = gl_mul(gl_sub(a, b), w);
+// Shared-memory tile: logical index e = (((bb << a) + m) << logq) | qq  (bb: block of a contiguous pass, m: position along
+// the sub-transform, qq: position inside a 2^logq-element run of a strided pass), stored at e + (e >> 4): one pad word per 16
+// keeps every access pattern of the rounds below free of bank conflicts.
+__device__ __forceinline__ int phys(int e) { return e + (e >> 4); }
+__host__ __device__ inline size_t tile_words(size_t elems) { return (elems + (elems >> 4) + 3) & ~(size_t)1; }   // even: TMA dst 16 B aligned
+
+// One register round: R butterfly stages [s0, s0 + R) of the 2^a-point sub-transforms of the tile.  A thread owns the 2^R
+// elements that differ in bits [a-s0-R, a-s0) of m, runs the R stages on them in registers (radix-2^R, 2^(R-1) R butterflies,
+// 2^R - 1 twiddle loads) and writes them back: the tile makes one shared-memory round trip per R stages instead of one per
+// stage.  Forward = decimation in frequency (stage order s0 .. s0+R-1), inverse = decimation in time (reverse order).
+template <int R, bool INV>
+__device__ __forceinline__ void reg_round(u64* __restrict__ sm, const u64* __restrict__ s_tw, int a, int s0, int logq, int log_tasks) {
+    const int lo_bits = a - s0 - R;
+    const int A = 1 << a;
+    const int lo_mask = (1 << lo_bits) - 1, q_mask = (1 << logq) - 1;
+    for (int task = threadIdx.x; task < (1 << log_tasks); task += blockDim.x) {
+        const int qq = task & q_mask, t = task >> logq;
+        const int lo = t & lo_mask;
+        const int base_m = ((t >> lo_bits) << (lo_bits + R)) | lo;
+        u64 x[1 << R];
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) x[k] = sm[phys(((base_m + (k << lo_bits)) << logq) | qq)];
+#pragma unroll
+        for (int ii = 0; ii < R; ii++) {
+            const int i = INV ? R - 1 - ii : ii;
+            const int h = 1 << (R - 1 - i);
+            const u64* tw = s_tw + (A - (A >> (s0 + i)));
+            const bool unit = (h == 1) && (lo_bits == 0);   // last stage of the sub-transform: every twiddle is 1
+#pragma unroll
+            for (int kk = 0; kk < h; kk++) {
+                const u64 w = unit ? 1 : tw[(kk << lo_bits) | lo];
+#pragma unroll
+                for (int g = 0; g < (1 << R); g += 2 * h) {
+                    u64 u = x[g + kk], v = x[g + kk + h];
+                    if (INV) {
+                        if (!unit) v = gl_mul(v, w);
+                        x[g + kk] = gl_add(u, v);
+                        x[g + kk + h] = gl_sub(u, v);
+                    } else {
+                        x[g + kk] = gl_add(u, v);
+                        v = gl_sub(u, v);
+                        x[g + kk + h] = unit ? v : gl_mul(v, w);
+                    }
+                }
             }
         }
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) sm[phys(((base_m + (k << lo_bits)) << logq) | qq)] = x[k];
+    }
+    __syncthreads();
+}
+
+// all `a` stages of the tile: rounds of RMAX stages, then one round with the remainder
+template <bool INV, int RMAX>
+__device__ __forceinline__ void tile_butterflies(u64* sm, const u64* s_tw, int a, int logq, int log_elems) {
+    const int rem = a % RMAX, full = a / RMAX;
+    if (!INV) {
+        int s0 = 0;
+        for (int r = 0; r < full; r++, s0 += RMAX) reg_round<RMAX, false>(sm, s_tw, a, s0, logq, log_elems - RMAX);
+        if (rem == 3) reg_round<3, false>(sm, s_tw, a, s0, logq, log_elems - 3);
+        else if (rem == 2) reg_round<2, false>(sm, s_tw, a, s0, logq, log_elems - 2);
+        else if (rem == 1) reg_round<1, false>(sm, s_tw, a, s0, logq, log_elems - 1);
+    } else {
+        int s0 = a - rem;
+        if (rem == 3) reg_round<3, true>(sm, s_tw, a, s0, logq, log_elems - 3);
+        else if (rem == 2) reg_round<2, true>(sm, s_tw, a, s0, logq, log_elems - 2);
+        else if (rem == 1) reg_round<1, true>(sm, s_tw, a, s0, logq, log_elems - 1);
+        for (int r = 0; r < full; r++) {
+            s0 -= RMAX;
+            reg_round<RMAX, true>(sm, s_tw, a, s0, logq, log_elems - RMAX);
+        }
     }
 }
 
-// Strided pass: tile [A][Q], element (m, qq) at column index blk*B + m*S + q0 + qq.
-template <bool INV>
-__global__ void __launch_bounds__(512) k_pass_strided(PassArgs a) {
+// Strided pass: tile [A][Q], element (m, qq) at column index blk*B + m*S + q0 + qq.  grid.x = tile * nz + coset: the cosets
+// of one coefficient tile are adjacent in launch order, so the tile is read from HBM once and from L2 seven times.
+template <bool INV, int RMAX>
+__global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_strided(PassArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const int A = 1 << a.loga, Q = 1 << a.logq;
     const int logS = a.logB - a.loga;
-    u64* s_tw = sm + (A << a.logq);
+    const int total = A << a.logq;
+    u64* s_tw = sm + tile_words(total);
     u64* mbar = s_tw + A;
+    const u32 z = blockIdx.x % a.nz, tile = blockIdx.x / a.nz;
     const u32 tiles_per_blk = 1u << (logS - a.logq);
-    const u32 blk = blockIdx.x / tiles_per_blk;
-    const u32 q0 = (blockIdx.x % tiles_per_blk) << a.logq;
-    const u64* in = a.in + (size_t)blockIdx.y * a.in_cs + (size_t)blockIdx.z * a.in_zs;
-    u64* out = a.out + (size_t)blockIdx.y * a.out_cs + (size_t)blockIdx.z * a.out_zs;
-    const u64* stab = a.stab ? a.stab + (size_t)blockIdx.z * a.stab_zs : nullptr;
+    const u32 blk = tile / tiles_per_blk;
+    const u32 q0 = (tile % tiles_per_blk) << a.logq;
+    const u64* in = a.in + (size_t)blockIdx.y * a.in_cs + (size_t)z * a.in_zs;
+    u64* out = a.out + (size_t)blockIdx.y * a.out_cs + (size_t)z * a.out_zs;
+    const u64* stab = a.stab ? a.stab + (size_t)z * a.stab_zs : nullptr;
     const size_t base = ((size_t)blk << a.logB) + q0;
 
     stage_tw_begin(s_tw, a.tw, A, mbar);
-    const int total = A << a.logq;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
         int qq = e & (Q - 1), m = e >> a.logq;
         size_t idx = base + ((size_t)m << logS) + qq;
         u64 v = in[idx];
         if (!INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
         if (INV && a.twist) v = gl_mul(v, tab_pow(a.twist, a.twist_split, (q0 + qq) * bitrev32(m, a.loga)));
-        sm[e] = v;
+        sm[phys(e)] = v;
     }
     stage_tw_end(A, mbar);
-    smem_butterflies<INV>(sm, s_tw, a.loga, a.logq, Q, 1, true);
+    tile_butterflies<INV, RMAX>(sm, s_tw, a.loga, a.logq, a.loga + a.logq);
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
         int qq = e & (Q - 1), m = e >> a.logq;
         size_t idx = base + ((size_t)m << logS) + qq;
-        u64 v = sm[e];
+        u64 v = sm[phys(e)];
         if (!INV && a.twist) v = gl_mul(v, tab_pow(a.twist, a.twist_split, (q0 + qq) * bitrev32(m, a.loga)));
         if (INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
         if (a.scale != 1) v = gl_mul(v, a.scale);
@@ -162,45 +204,44 @@ __global__ void __launch_bounds__(512) k_pass_strided(PassArgs a) {
     }
 }
 
-// Contiguous pass: tile = 2^logq consecutive blocks of A elements (rows padded by one word when there are several).
-template <bool INV>
-__global__ void __launch_bounds__(512) k_pass_contig(PassArgs a) {
+// Contiguous pass: tile = 2^logq consecutive blocks of A elements.
+template <bool INV, int RMAX>
+__global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_contig(PassArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const int A = 1 << a.loga, NB = 1 << a.logq;
-    const int AP = A + (NB > 1 ? 1 : 0);
-    u64* s_tw = sm + ((NB * AP + 1) & ~1);
+    const int total = A << a.logq;
+    u64* s_tw = sm + tile_words(total);
     u64* mbar = s_tw + A;
-    const u64* in = a.in + (size_t)blockIdx.y * a.in_cs + (size_t)blockIdx.z * a.in_zs;
-    u64* out = a.out + (size_t)blockIdx.y * a.out_cs + (size_t)blockIdx.z * a.out_zs;
-    const u64* stab = a.stab ? a.stab + (size_t)blockIdx.z * a.stab_zs : nullptr;
+    const u32 z = blockIdx.x % a.nz, tile = blockIdx.x / a.nz;
+    const u64* in = a.in + (size_t)blockIdx.y * a.in_cs + (size_t)z * a.in_zs;
+    u64* out = a.out + (size_t)blockIdx.y * a.out_cs + (size_t)z * a.out_zs;
+    const u64* stab = a.stab ? a.stab + (size_t)z * a.stab_zs : nullptr;
     const int lognb = a.logn - a.loga;  // log2(#blocks in the column)
-    const u32 c0 = blockIdx.x << a.logq;
+    const u32 c0 = tile << a.logq;
 
     stage_tw_begin(s_tw, a.tw, A, mbar);
-    const int total = A << a.logq;
     if (INV && a.gather) {
         // virtual bit-reversed array: block b = bitrev(c), element m' <- natural index bitrev_a(m') * (N/A) + c
         for (int e = threadIdx.x; e < total; e += blockDim.x) {
             int c = e & (NB - 1), m = e >> a.logq;
             size_t idx = ((size_t)bitrev32(m, a.loga) << lognb) + c0 + c;
-            sm[c * AP + m] = in[idx];
+            sm[phys((c << a.loga) + m)] = in[idx];
         }
     } else {
         for (int e = threadIdx.x; e < total; e += blockDim.x) {
-            int bb = e >> a.loga, m = e & (A - 1);
-            size_t idx = ((size_t)(c0 + bb) << a.loga) + m;
+            size_t idx = ((size_t)c0 << a.loga) + e;
             u64 v = in[idx];
             if (!INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
-            sm[bb * AP + m] = v;
+            sm[phys(e)] = v;
         }
     }
     stage_tw_end(A, mbar);
-    smem_butterflies<INV>(sm, s_tw, a.loga, a.logq, 1, AP, false);
+    tile_butterflies<INV, RMAX>(sm, s_tw, a.loga, 0, a.loga + a.logq);
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
         int bb = e >> a.loga, m = e & (A - 1);
         u32 blk = (INV && a.gather) ? bitrev32(c0 + bb, lognb) : (c0 + bb);
         size_t idx = ((size_t)blk << a.loga) + m;
-        u64 v = sm[bb * AP + m];
+        u64 v = sm[phys(e)];
         if (INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
         if (a.scale != 1) v = gl_mul(v, a.scale);
         out[idx] = v;
@@ -228,6 +269,23 @@ __global__ void k_fill_tw(u64* out, int loga, u64 root) {
     out[i] = gl_pow(root, (u64)j << u);
 }
 
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+// tuning knobs (defaults chosen on B200, see profiles/): log2 of the tile size in elements, log2 of the last (contiguous)
+// pass, threads per block (0 = by tile size)
+int ntt_tile_log() { static int v = env_int("P2G_NTT_TILE", 12); return v; }
+int ntt_last_log() { static int v = env_int("P2G_NTT_LAST", 11); return v; }
+int ntt_threads() { static int v = env_int("P2G_NTT_TH", 0); return v; }
+int ntt_rmax() {
+    static int r = 0;
+    if (!r) {
+        const char* e = getenv("P2G_NTT_R");
+        r = (e && atoi(e) == 4) ? 4 : 3;   // 8 elements per thread: 64 registers, two 512-thread blocks per SM
+    }
+    return r;
+}
 const int MAX_CONTIG_LOG = 11;
 const int MAX_STRIDED_LOG = 10;
 
@@ -238,7 +296,7 @@ std::vector<int> make_plan(int logn) {
         plan.push_back(logn);
         return plan;
     }
-    int last = 10;
+    int last = std::min(ntt_last_log(), MAX_CONTIG_LOG);
     int rem = logn - last;
     int cnt = (rem + MAX_STRIDED_LOG - 1) / MAX_STRIDED_LOG;
     for (int i = 0; i < cnt; i++) {
@@ -250,24 +308,28 @@ std::vector<int> make_plan(int logn) {
     return plan;
 }
 
-size_t strided_smem(int loga, int logq) { return ((size_t)(1 << loga) << logq) * 8 + (size_t)(1 << loga) * 8 + 16; }
-size_t contig_smem(int loga, int logq) {
-    int A = 1 << loga, NB = 1 << logq, AP = A + (NB > 1 ? 1 : 0);
-    return (size_t)((NB * AP + 1) & ~1) * 8 + (size_t)A * 8 + 16;
-}
+size_t strided_smem(int loga, int logq) { return tile_words((size_t)1 << (loga + logq)) * 8 + (size_t)(1 << loga) * 8 + 16; }
+size_t contig_smem(int loga, int logq) { return strided_smem(loga, logq); }
 
 void set_smem_attrs() {
     static bool done = false;
     if (done) return;
     const int lim = 160 * 1024;
-    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     done = true;
 }
 
-int pick_threads(size_t tile_elems) { return tile_elems >= 8192 ? 512 : (tile_elems >= 512 ? 256 : 64); }
+int pick_threads(size_t tile_elems) {
+    if (ntt_threads() && tile_elems >= 4096) return ntt_threads();
+    return tile_elems >= 8192 ? 512 : (tile_elems >= 4096 ? 256 : (tile_elems >= 1024 ? 64 : 32));
+}
 
 // run the passes of one direction.  fwd: in -> out (first pass), then in place on out.
 struct XformDesc {
@@ -308,19 +370,23 @@ void run_forward(DevCtx* c, const XformDesc& d) {
         if (!last) {
             a.logB = d.logn - done;
             int logS = a.logB - a.loga;
-            a.logq = std::min(logS, std::max(3, 12 - a.loga));
+            a.logq = std::min(logS, std::max(3, ntt_tile_log() - a.loga));
             a.twist = c->get_twist(a.logB, false, &a.twist_split);
             size_t tiles = (size_t)1 << (d.logn - a.loga - a.logq);
-            dim3 grid((unsigned)tiles, d.ncols, d.nz);
+            a.nz = d.nz;
+            dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
-            k_pass_strided<false><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
+            if (ntt_rmax() == 4) k_pass_strided<false, 4><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
+            else k_pass_strided<false, 3><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
         } else {
             int lognb = d.logn - a.loga;
-            a.logq = std::min(lognb, std::max(0, 12 - a.loga));
+            a.logq = std::min(lognb, std::max(0, ntt_tile_log() - a.loga));
             size_t tiles = (size_t)1 << (lognb - a.logq);
-            dim3 grid((unsigned)tiles, d.ncols, d.nz);
+            a.nz = d.nz;
+            dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
-            k_pass_contig<false><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
+            if (ntt_rmax() == 4) k_pass_contig<false, 4><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
+            else k_pass_contig<false, 3><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
         }
         count_launch(c);
         done += plan[pi];
@@ -356,20 +422,24 @@ void run_inverse(DevCtx* c, const XformDesc& d) {
             int lognb = d.logn - a.loga;
             a.gather = d.natural_input ? 1 : 0;
             int want = a.gather ? 3 : 0;
-            a.logq = std::min(lognb, std::max(want, 12 - a.loga));
+            a.logq = std::min(lognb, std::max(want, ntt_tile_log() - a.loga));
             size_t tiles = (size_t)1 << (lognb - a.logq);
-            dim3 grid((unsigned)tiles, d.ncols, d.nz);
+            a.nz = d.nz;
+            dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
-            k_pass_contig<true><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
+            if (ntt_rmax() == 4) k_pass_contig<true, 4><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
+            else k_pass_contig<true, 3><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
         } else {
             a.logB = done + a.loga;
             int logS = a.logB - a.loga;
-            a.logq = std::min(logS, std::max(3, 12 - a.loga));
+            a.logq = std::min(logS, std::max(3, ntt_tile_log() - a.loga));
             a.twist = c->get_twist(a.logB, true, &a.twist_split);
             size_t tiles = (size_t)1 << (d.logn - a.loga - a.logq);
-            dim3 grid((unsigned)tiles, d.ncols, d.nz);
+            a.nz = d.nz;
+            dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
-            k_pass_strided<true><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
+            if (ntt_rmax() == 4) k_pass_strided<true, 4><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
+            else k_pass_strided<true, 3><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
         }
         count_launch(c);
         done += plan[pi];
