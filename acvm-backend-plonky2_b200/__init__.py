@@ -7,3 +7,4 @@ from .lib import P2GError, build  # noqa: F401
 from . import circuit  # noqa: F401,E402
 from . import synth  # noqa: F401,E402
 from .circuit import CircuitConfig, CircuitData, CommonCircuitData, Gate, ProofWithPublicInputs  # noqa: F401,E402
+from . import sharding  # noqa: F401,E402

@@ -279,12 +279,19 @@ class ProofWithPublicInputs:
 class CircuitData:
     """plonky2 `CircuitData`: `prover_only` (preprocessed polynomials, resident on the GPU) + `common`."""
 
-    def __init__(self, common, constants_sigmas, circuit_digest=None, device=0):
+    def __init__(self, common, constants_sigmas, circuit_digest=None, device=0, shard=None):
+        """`shard`: a sharding.TorchDistGroup / ThreadGroup member -> this handle is one rank of a coset-sharded prover
+        (every rank is created with the same arguments and must call prove() with the same witness)."""
         self.common = common
         self.device = device
+        self.shard = shard
         self._h = C.c_void_p()
         desc, keep = common.fill_desc(constants_sigmas, circuit_digest)
-        _lib.check(_lib.lib().p2g_circuit_create(C.byref(desc), device, C.byref(self._h)))
+        if shard is None or shard.world == 1:
+            _lib.check(_lib.lib().p2g_circuit_create(C.byref(desc), device, C.byref(self._h)))
+        else:
+            _lib.check(_lib.lib().p2g_circuit_create_sharded(C.byref(desc), device, shard.rank, shard.world,
+                                                             shard.callback(), None, C.byref(self._h)))
         del keep
         hs, ncap = common.hash_size, 1 << min(common.config.cap_height, common.degree_bits_ + common.config.rate_bits)
         cap = C.create_string_buffer(ncap * hs)

@@ -91,8 +91,10 @@ struct StageTimer {  // RAII: accumulates elapsed ms of a stream segment into *a
 void ntt_ifft(DevCtx* c, const u64* d_values, size_t in_cs, u64* d_coeffs, size_t out_cs, int logn, int ncols);
 // coefficients (natural, N) -> values on shift*<omega_{N<<rate_bits}> in LEAF order (index j <-> point shift*omega^bitrev(j))
 // (PolynomialBatch::lde_values followed by reverse_index_bits_in_place)
+// z0 / nzl: only the cosets [z0, z0 + nzl) are produced (coset-sharded proofs), at d_lde[col * out_cs + (z - z0) * N + i];
+// nzl = 0 means all 2^rate_bits cosets.
 void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t out_cs, int logn, int rate_bits, int ncols,
-             u64 shift);
+             u64 shift, int z0 = 0, int nzl = 0);
 // leaf-order values on shift*<omega_N> -> natural coefficients, in place (coset_ifft)
 void ntt_coset_ifft_leaforder(DevCtx* c, u64* d_data, size_t cs, int logn, int ncols, u64 shift);
 

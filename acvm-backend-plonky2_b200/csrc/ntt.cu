@@ -312,8 +312,13 @@ size_t strided_smem(int loga, int logq) { return tile_words((size_t)1 << (loga +
 size_t contig_smem(int loga, int logq) { return strided_smem(loga, logq); }
 
 void set_smem_attrs() {
-    static bool done = false;
-    if (done) return;
+    static std::mutex m;
+    static std::vector<int> devs;   // the attribute is per device
+    std::lock_guard<std::mutex> lk(m);
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    if (std::find(devs.begin(), devs.end(), dev) != devs.end()) return;
+    devs.push_back(dev);
     const int lim = 160 * 1024;
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -323,7 +328,6 @@ void set_smem_attrs() {
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    done = true;
 }
 
 int pick_threads(size_t tile_elems) {
@@ -453,6 +457,7 @@ void run_inverse(DevCtx* c, const XformDesc& d) {
 // table caches
 // ---------------------------------------------------------------------------------------------------------------------
 const u64* DevCtx::get_tw(int log, bool inverse) {
+    std::lock_guard<std::mutex> lk(mu);
     auto key = std::make_pair(log, (int)inverse);
     auto it = tw.find(key);
     if (it != tw.end()) return it->second.p;
@@ -468,6 +473,7 @@ const u64* DevCtx::get_tw(int log, bool inverse) {
 }
 
 const u64* DevCtx::get_twist(int logB, bool inverse, int* split) {
+    std::lock_guard<std::mutex> lk(mu);
     int sp = (logB + 1) / 2;
     *split = sp;
     auto key = std::make_pair(logB, (int)inverse);
@@ -486,6 +492,7 @@ const u64* DevCtx::get_twist(int logB, bool inverse, int* split) {
 }
 
 const u64* DevCtx::get_powtab(int logn, u64 base, u64 premul, int* split) {
+    std::lock_guard<std::mutex> lk(mu);
     int sp = (logn + 1) / 2;
     *split = sp;
     auto key = std::make_tuple(logn, base, premul);
@@ -526,10 +533,14 @@ void ntt_ifft(DevCtx* c, const u64* d_values, size_t in_cs, u64* d_coeffs, size_
 }
 
 void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t out_cs, int logn, int rate_bits, int ncols,
-             u64 shift) {
+             u64 shift, int z0, int nzl) {
     if (ncols <= 0) return;
     StageTimer tm(c, &c->ntt_ms);
     const int nz = 1 << rate_bits;
+    if (nzl <= 0) {   // all cosets
+        z0 = 0;
+        nzl = nz;
+    }
     const size_t n = (size_t)1 << logn;
     // per-coset index-power tables: coset z covers leaves [z*N, (z+1)*N) = shift * omega_{N*nz}^{bitrev(z)} * <omega_N>
     int split = (logn + 1) / 2;
@@ -539,6 +550,7 @@ void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t ou
     auto key = std::make_tuple(logn + 64 * (rate_bits + 1), shift, (u64)0);
     const u64* tabs;
     {
+        std::lock_guard<std::mutex> lk(c->mu);
         auto it = c->powtab.find(key);
         if (it == c->powtab.end()) {
             dbuf<u64> t(tab_len * nz);
@@ -562,14 +574,14 @@ void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t ou
     d.out_zs = n;
     d.logn = logn;
     d.ncols = ncols;
-    d.nz = nz;
-    d.stab = tabs;
+    d.nz = nzl;                                   // this rank's cosets [z0, z0 + nzl): leaves [z0 N, (z0 + nzl) N)
+    d.stab = tabs + (size_t)z0 * tab_len;
     d.stab_split = split;
     d.stab_zs = tab_len;
     d.scale = 1;
     if (logn == 0) {
         // constant polynomials: every coset value equals the coefficient
-        for (int z = 0; z < nz; z++)
+        for (int z = 0; z < nzl; z++)
             CUDA_CHECK(cudaMemcpy2DAsync(d_lde + z, out_cs * 8, d_coeffs, in_cs * 8, 8, ncols, cudaMemcpyDeviceToDevice, c->stream));
         return;
     }
@@ -579,8 +591,8 @@ void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t ou
         run_forward(c, d);
         c->lde_launches += c->launches - before;
     }
-    c->lde_bytes += (8.0 + 8.0 * nz) * (double)n * ncols;
-    c->ntt_bytes += (8.0 + 8.0 * nz) * (double)n * ncols;
+    c->lde_bytes += (8.0 + 8.0 * nzl) * (double)n * ncols;
+    c->ntt_bytes += (8.0 + 8.0 * nzl) * (double)n * ncols;
 }
 
 void ntt_coset_ifft_leaforder(DevCtx* c, u64* d_data, size_t cs, int logn, int ncols, u64 shift) {

@@ -362,7 +362,7 @@ struct p2g_circuit {
     dbuf<u64> zpp_values;
     std::vector<u64> challenges;
     std::vector<u64> final_poly;  // c0,c1 interleaved
-    std::vector<digest_t> fri_caps;
+    std::vector<digest_t> fri_caps, last_caps[3];   // wires, Z/PP, quotient caps of the last proof
     bool proved = false;
     // scratch that survives between proofs
     struct FriLayer {
@@ -379,8 +379,13 @@ struct p2g_circuit {
         dbuf<digest_t> paths;
         std::vector<FriLayer> layers;
     } ws;
-    // sharding (one process per GPU); world == 1: single device
-    int rank = 0, world = 1;
+    // coset sharding (one process per GPU).  world == 1: single device.  A rank owns the `nzl` cosets
+    // [z0, z0 + nzl) = leaves [j0, j0 + lde_l) of every oracle: their LDE columns, their Merkle subtrees down to the
+    // cap entries [cap0, cap0 + ncap_l), their share of the quotient evaluation and of the query openings.
+    int rank = 0, world = 1, logworld = 0;
+    int z0 = 0, nzl = 0, ncap_l = 0, cap0 = 0;
+    size_t lde_l = 0, j0 = 0;
+    int loglde_l = 0;
     p2g_allgather_fn allgather = nullptr;
     void* allgather_user = nullptr;
 };
@@ -397,25 +402,48 @@ void upload_level_ptrs(DevCtx* c, PolyBatch& b) {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
-// coefficients already in b.coeffs: LDE + Merkle
+void shard_allgather(p2g_circuit* C, const void* send, void* recv, size_t bytes, bool is_device) {
+    if (is_device) CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));   // the host binding runs on its own stream
+    int rc = C->allgather(C->allgather_user, send, recv, bytes, is_device ? 1 : 0);
+    if (rc != 0) throw p2g_error(P2G_ENCCL, "allgather callback failed (" + std::to_string(rc) + ")");
+}
+
+// coefficients already in b.coeffs: LDE of this rank's cosets + their Merkle subtrees
 void commit_from_coeffs(p2g_circuit* C, PolyBatch& b) {
     DevCtx* c = C->ctx;
-    size_t want = (size_t)b.ncols * C->lde;
+    size_t want = (size_t)b.ncols * C->lde_l;
     if (b.lde.n != want) b.lde.alloc(want);
-    ntt_lde(c, b.coeffs.p, C->n, b.lde.p, C->lde, C->logn, C->d.rate_bits, b.ncols, GL_GEN);
-    merkle_build(c, &b.tree, b.lde.p, C->lde, C->loglde, b.ncols, C->d.cap_height, C->h);
+    ntt_lde(c, b.coeffs.p, C->n, b.lde.p, C->lde_l, C->logn, C->d.rate_bits, b.ncols, GL_GEN, C->z0, C->nzl);
+    merkle_build(c, &b.tree, b.lde.p, C->lde_l, C->loglde_l, b.ncols, (int)C->d.cap_height - C->logworld, C->h);
     upload_level_ptrs(c, b);
 }
-void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs) {
-    size_t want = (size_t)b.ncols * C->n;
+// values -> coefficients.  Sharded: each rank transforms a contiguous block of columns and the blocks are all-gathered
+// (the coefficient buffer is padded to world * ceil(ncols / world) columns so the blocks are equal).
+void ifft_columns(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs) {
+    const int per = (b.ncols + C->world - 1) / C->world;
+    size_t want = (size_t)per * C->world * C->n;
     if (b.coeffs.n != want) b.coeffs.alloc(want);
-    ntt_ifft(C->ctx, d_values, values_cs, b.coeffs.p, C->n, C->logn, b.ncols);
+    if (C->world == 1 || b.ncols < 4 * C->world) {
+        ntt_ifft(C->ctx, d_values, values_cs, b.coeffs.p, C->n, C->logn, b.ncols);
+        return;
+    }
+    const int c0 = std::min(b.ncols, C->rank * per), c1 = std::min(b.ncols, c0 + per);
+    ntt_ifft(C->ctx, d_values + (size_t)c0 * values_cs, values_cs, b.coeffs.p + (size_t)c0 * C->n, C->n, C->logn, c1 - c0);
+    shard_allgather(C, b.coeffs.p + (size_t)C->rank * per * C->n, b.coeffs.p, (size_t)per * C->n * 8, true);
+}
+void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs) {
+    ifft_columns(C, b, d_values, values_cs);
     commit_from_coeffs(C, b);
 }
-std::vector<digest_t> read_cap(p2g_circuit* C, const MerkleTree& t) {
-    std::vector<digest_t> cap(t.ncap());
-    CUDA_CHECK(cudaMemcpyAsync(cap.data(), t.cap(), sizeof(digest_t) * cap.size(), cudaMemcpyDeviceToHost, C->ctx->stream));
+// the 2^cap_height cap of an oracle: this rank's subtree roots, all-gathered when sharded (the one collective of the
+// commitment)
+std::vector<digest_t> read_cap(p2g_circuit* C, const MerkleTree& t, bool sharded = true) {
+    std::vector<digest_t> mine(t.ncap());
+    CUDA_CHECK(cudaMemcpyAsync(mine.data(), t.cap(), sizeof(digest_t) * mine.size(), cudaMemcpyDeviceToHost, C->ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));
+    if (C->world == 1 || !sharded) return mine;
+    std::vector<digest_t> cap(mine.size() * C->world);
+    shard_allgather(C, mine.data(), cap.data(), sizeof(digest_t) * mine.size(), false);
     return cap;
 }
 
@@ -487,16 +515,28 @@ void fill_gates(QuotientParams& qp, const p2g_circuit* C) {
 // =====================================================================================================================
 // circuit handle
 // =====================================================================================================================
-extern "C" int p2g_circuit_create(const p2g_circuit_desc* desc, int device, p2g_circuit** out) {
+static int circuit_create_impl(const p2g_circuit_desc* desc, int device, int rank, int world, p2g_allgather_fn allgather,
+                               void* user, p2g_circuit** out) {
     if (out) *out = nullptr;
     p2g_circuit* C = nullptr;
     int rc = guard([&] {
         if (!out) throw p2g_error(P2G_EBADARG, "p2g_circuit_create: null out");
         validate_desc(desc);
+        int logworld = 0;
+        while ((1 << logworld) < world) logworld++;
+        if (world < 1 || (1 << logworld) != world || rank < 0 || rank >= world || (world > 1 && !allgather) ||
+            logworld > (int)desc->rate_bits || logworld > (int)desc->cap_height)
+            throw p2g_error(P2G_EBADARG, "p2g_circuit_create_sharded: world must be a power of two <= 2^min(rate_bits, cap_height), "
+                                         "0 <= rank < world, and an allgather callback is required");
         DevCtx* c = get_ctx(device);
         C = new p2g_circuit();
         C->d = *desc;
         C->ctx = c;
+        C->rank = rank;
+        C->world = world;
+        C->logworld = logworld;
+        C->allgather = allgather;
+        C->allgather_user = user;
         C->gates.assign(desc->gates, desc->gates + desc->num_gates);
         C->k_is.assign(desc->k_is, desc->k_is + desc->num_routed_wires);
         C->d.gates = C->gates.data();
@@ -507,6 +547,11 @@ extern "C" int p2g_circuit_create(const p2g_circuit_desc* desc, int device, p2g_
         C->loglde = desc->degree_bits + desc->rate_bits;
         C->n = (size_t)1 << C->logn;
         C->lde = (size_t)1 << C->loglde;
+        C->loglde_l = C->loglde - logworld;
+        C->lde_l = C->lde >> logworld;
+        C->j0 = (size_t)rank * C->lde_l;
+        C->nzl = (1 << desc->rate_bits) >> logworld;
+        C->z0 = rank * C->nzl;
         C->h = desc->hasher;
         C->hs = hasher_bytes(C->h);
         const int Cc = desc->num_constants, R = desc->num_routed_wires, P = Cc + R;
@@ -550,20 +595,29 @@ extern "C" int p2g_circuit_create(const p2g_circuit_desc* desc, int device, p2g_
         // persistent buffers of the per-proof commitments
         const int W = desc->num_wires, NC = desc->num_challenges, nzp = NC * (1 + desc->num_partial_products),
                   nq = NC * desc->quotient_degree_factor;
+        auto padded = [&](int cols) { return (size_t)((cols + world - 1) / world) * world; };
         C->wires.ncols = W;
-        C->wires.coeffs.alloc((size_t)W * n);
-        C->wires.lde.alloc((size_t)W * C->lde);
+        C->wires.coeffs.alloc(padded(W) * n);
+        C->wires.lde.alloc((size_t)W * C->lde_l);
         C->zpp.ncols = nzp;
-        C->zpp.coeffs.alloc((size_t)nzp * n);
-        C->zpp.lde.alloc((size_t)nzp * C->lde);
+        C->zpp.coeffs.alloc(padded(nzp) * n);
+        C->zpp.lde.alloc((size_t)nzp * C->lde_l);
         C->zpp_values.alloc((size_t)nzp * n);
         C->quot.ncols = nq;
-        C->quot.coeffs.alloc((size_t)nq * n);
-        C->quot.lde.alloc((size_t)nq * C->lde);
+        C->quot.coeffs.alloc(padded(nq) * n);
+        C->quot.lde.alloc((size_t)nq * C->lde_l);
         *out = C;
     });
     if (rc != P2G_OK && C) delete C;
     return rc;
+}
+
+extern "C" int p2g_circuit_create(const p2g_circuit_desc* desc, int device, p2g_circuit** out) {
+    return circuit_create_impl(desc, device, 0, 1, nullptr, nullptr, out);
+}
+extern "C" int p2g_circuit_create_sharded(const p2g_circuit_desc* desc, int device, int rank, int world, p2g_allgather_fn allgather,
+                                          void* user, p2g_circuit** out) {
+    return circuit_create_impl(desc, device, rank, world, allgather, user, out);
 }
 
 extern "C" void p2g_circuit_destroy(p2g_circuit* c) {
@@ -600,17 +654,6 @@ extern "C" size_t p2g_proof_size_bound(const p2g_circuit* c) {
     sz += d.num_query_rounds * per_q;
     sz += 16 * c->n + 8 + 8 * d.num_public_inputs;
     return sz;
-}
-
-extern "C" int p2g_circuit_set_sharding(p2g_circuit* c, int rank, int world, p2g_allgather_fn allgather, void* user) {
-    return guard([&] {
-        if (!c || world < 1 || rank < 0 || rank >= world) throw p2g_error(P2G_EBADARG, "p2g_circuit_set_sharding: bad argument");
-        if (world > 1) throw p2g_error(P2G_EBADARG, "p2g_circuit_set_sharding: intra-proof sharding is not built yet; run one proof per GPU");
-        c->rank = rank;
-        c->world = world;
-        c->allgather = allgather;
-        c->allgather_user = user;
-    });
 }
 
 // =====================================================================================================================
@@ -734,8 +777,11 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         CUDA_CHECK(cudaEventCreate(&qa));
         CUDA_CHECK(cudaEventCreate(&qb));
         CUDA_CHECK(cudaEventRecord(qa, st));
-        quotient_eval(c, qp, C->cs.lde.p, C->wires.lde.p, C->zpp.lde.p, C->xs.p, C->l0s.p, qv, lde);
+        quotient_eval(c, qp, C->cs.lde.p, C->wires.lde.p, C->zpp.lde.p, C->xs.p, C->l0s.p, qv, C->lde_l, C->j0, lde);
         CUDA_CHECK(cudaEventRecord(qb, st));
+        if (C->world > 1)   // every rank needs all 8N quotient values for the size-8N inverse transform
+            for (int cc = 0; cc < NC; cc++)
+                shard_allgather(C, qv + (size_t)cc * lde + C->j0, qv + (size_t)cc * lde, C->lde_l * 8, true);
         ntt_coset_ifft_leaforder(c, qv, lde, C->loglde, NC, GL_GEN);
         CUDA_CHECK(cudaEventSynchronize(qb));
         cudaEventElapsedTime(&quotient_kernel_ms, qa, qb);
@@ -865,7 +911,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         const int arity = 1 << L.ab;
         merkle_build(c, &L.tree.tree, L.values.p, L.cur, L.logcur - L.ab, 2 * arity, d.cap_height, h, true);
         upload_level_ptrs(c, L.tree);
-        std::vector<digest_t> cap = read_cap(C, L.tree.tree);
+        std::vector<digest_t> cap = read_cap(C, L.tree.tree, false);   // FRI layers are replicated on every rank
         for (auto& dg : cap) ch.observe_digest(dg);
         C->fri_caps.insert(C->fri_caps.end(), cap.begin(), cap.end());
         e2 beta = ch.get_e2();
@@ -944,8 +990,15 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     for (int q = 0; q < NQ; q++) C->challenges.push_back(indices[q]);
 
     // query rounds: gather opened rows and Merkle paths on the device, one D2H
-    struct { u32* p; } d_idx = {ensure(C->ws.idx, NQ)};
-    CUDA_CHECK(cudaMemcpyAsync(d_idx.p, indices.data(), 4 * NQ, cudaMemcpyHostToDevice, st));
+    // d_idx: global leaf indices (FRI layers, replicated); d_lidx: indices into this rank's leaves (0 for queries it does not own)
+    struct { u32* p; } d_idx = {ensure(C->ws.idx, 2 * NQ)}, d_lidx = {d_idx.p + NQ};
+    std::vector<u32> idx2(2 * NQ);
+    for (int q = 0; q < NQ; q++) {
+        idx2[q] = indices[q];
+        bool mine = indices[q] >= C->j0 && indices[q] < C->j0 + C->lde_l;
+        idx2[NQ + q] = mine ? (u32)(indices[q] - C->j0) : 0;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(d_idx.p, idx2.data(), 8 * NQ, cudaMemcpyHostToDevice, st));
     size_t row_words = 0, path_digests = 0;
     size_t row_off[4 + P2G_MAX_FRI_LAYERS], path_off[4 + P2G_MAX_FRI_LAYERS];
     int path_len[4 + P2G_MAX_FRI_LAYERS];
@@ -967,10 +1020,10 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     struct { digest_t* p; } d_paths = {ensure(C->ws.paths, path_digests + 1)};
     for (int o = 0; o < 4; o++) {
         int cnt = NQ * widths[o];
-        k_gather_rows<<<(cnt + 127) / 128, 128, 0, st>>>(oracles[o]->lde.p, lde, widths[o], d_idx.p, NQ, d_rows.p + row_off[o]);
+        k_gather_rows<<<(cnt + 127) / 128, 128, 0, st>>>(oracles[o]->lde.p, C->lde_l, widths[o], d_lidx.p, NQ, d_rows.p + row_off[o]);
         if (path_len[o] > 0) {
             int pc = NQ * path_len[o];
-            k_gather_paths<<<(pc + 127) / 128, 128, 0, st>>>(oracles[o]->d_levels.p, path_len[o], d_idx.p, NQ, 0, d_paths.p + path_off[o]);
+            k_gather_paths<<<(pc + 127) / 128, 128, 0, st>>>(oracles[o]->d_levels.p, path_len[o], d_lidx.p, NQ, 0, d_paths.p + path_off[o]);
         }
         count_launch(c, 2);
     }
@@ -996,6 +1049,24 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     CUDA_CHECK(cudaMemcpyAsync(h_rows.data(), d_rows.p, 8 * row_words, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(h_paths.data(), d_paths.p, sizeof(digest_t) * path_digests, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    if (C->world > 1) {
+        // opened rows and paths of the four committed oracles come from the rank that owns the leaf
+        const size_t rw = (size_t)NQ * total, pd = path_off[3] + (size_t)NQ * path_len[3];
+        const size_t bytes = 8 * rw + sizeof(digest_t) * pd;
+        std::vector<uint8_t> mine(bytes), all(bytes * C->world);
+        memcpy(mine.data(), h_rows.data(), 8 * rw);
+        memcpy(mine.data() + 8 * rw, h_paths.data(), sizeof(digest_t) * pd);
+        shard_allgather(C, mine.data(), all.data(), bytes, false);
+        for (int q = 0; q < NQ; q++) {
+            const int owner = (int)(indices[q] / C->lde_l);
+            const uint8_t* src = all.data() + (size_t)owner * bytes;
+            for (int o = 0; o < 4; o++) {
+                memcpy(h_rows.data() + row_off[o] + (size_t)q * widths[o], src + 8 * (row_off[o] + (size_t)q * widths[o]), 8 * (size_t)widths[o]);
+                memcpy(h_paths.data() + path_off[o] + (size_t)q * path_len[o],
+                       src + 8 * rw + sizeof(digest_t) * (path_off[o] + (size_t)q * path_len[o]), sizeof(digest_t) * (size_t)path_len[o]);
+            }
+        }
+    }
 
     // serialise: Proof || public_inputs   (App. A.12, uncompressed)
     Writer wb(out, out ? *out_len : 0);
@@ -1030,6 +1101,9 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     CUDA_CHECK(cudaEventRecord(ev[6], st));
     CUDA_CHECK(cudaEventSynchronize(ev[6]));
     tr.mark("queries + serialise");
+    C->last_caps[0] = wires_cap;
+    C->last_caps[1] = zpp_cap;
+    C->last_caps[2] = quot_cap;
     C->proved = true;
 
     if (tm) {
@@ -1120,8 +1194,7 @@ extern "C" int p2g_circuit_read(p2g_circuit* C, int what, void* out, size_t* len
         const void* hsrc = nullptr;   // host source
         std::vector<uint8_t> packed;
         size_t sz = 0;
-        auto cap_of = [&](const MerkleTree& t) {
-            std::vector<digest_t> cap = read_cap(C, t);
+        auto cap_of = [&](const std::vector<digest_t>& cap) {
             packed.resize(cap.size() * C->hs);
             pack_digests(C->h, cap.data(), cap.size(), packed.data());
             hsrc = packed.data();
@@ -1129,10 +1202,10 @@ extern "C" int p2g_circuit_read(p2g_circuit* C, int what, void* out, size_t* len
         };
         if (what != P2G_BUF_CS_CAP && !C->proved) throw p2g_error(P2G_EBADARG, "p2g_circuit_read: no proof has been produced yet");
         switch (what) {
-        case P2G_BUF_WIRES_CAP: cap_of(C->wires.tree); break;
-        case P2G_BUF_ZS_PP_CAP: cap_of(C->zpp.tree); break;
-        case P2G_BUF_QUOTIENT_CAP: cap_of(C->quot.tree); break;
-        case P2G_BUF_CS_CAP: cap_of(C->cs.tree); break;
+        case P2G_BUF_WIRES_CAP: cap_of(C->last_caps[0]); break;
+        case P2G_BUF_ZS_PP_CAP: cap_of(C->last_caps[1]); break;
+        case P2G_BUF_QUOTIENT_CAP: cap_of(C->last_caps[2]); break;
+        case P2G_BUF_CS_CAP: cap_of(C->cs_cap); break;
         case P2G_BUF_ZS_PP_VALUES: dsrc = C->zpp_values.p; sz = (size_t)nzp * C->n * 8; break;
         case P2G_BUF_QUOTIENT_CHUNKS: dsrc = C->quot.coeffs.p; sz = (size_t)nq * C->n * 8; break;
         case P2G_BUF_WIRES_COEFFS: dsrc = C->wires.coeffs.p; sz = (size_t)d.num_wires * C->n * 8; break;
@@ -1144,7 +1217,7 @@ extern "C" int p2g_circuit_read(p2g_circuit* C, int what, void* out, size_t* len
             hsrc = packed.data();
             sz = packed.size();
             break;
-        case P2G_BUF_WIRES_LDE: dsrc = C->wires.lde.p; sz = (size_t)d.num_wires * C->lde * 8; break;
+        case P2G_BUF_WIRES_LDE: dsrc = C->wires.lde.p; sz = (size_t)d.num_wires * C->lde_l * 8; break;   // this rank's leaves
         default: throw p2g_error(P2G_EBADARG, "p2g_circuit_read: unknown buffer");
         }
         if (!out || *len < sz) {

@@ -32,13 +32,18 @@ struct WeightedSink {  // folds constraint k into sum_c += v * alpha_c^(off + k)
 // two running sums.  A first kernel seeds the sums with the Z and permutation (partial-product) terms; the last gate
 // kernel divides by Z_H.  (A single fused kernel holding all 12 gates was measured first: 307 ms at 2^20 rows, 30% of the
 // warp time stalled on instruction fetch and 38% on a load-imbalance barrier; see profiles/.)
+// Sharding: a rank evaluates the `npts` leaves [j0, j0 + npts) (whole cosets).  Input columns are local (stride L = npts,
+// index j); xs / l0s are the full per-circuit tables (index j0 + j); `out` is the full-size [NC][OL] quotient-value buffer.
 __global__ void __launch_bounds__(256) k_quotient_perm(const u64* __restrict__ cs, const u64* __restrict__ wires,
                                                        const u64* __restrict__ zpp, const u64* __restrict__ xs,
-                                                       const u64* __restrict__ l0s, u64* __restrict__ out, int scale_now) {
+                                                       const u64* __restrict__ l0s, u64* __restrict__ out_, int scale_now,
+                                                       size_t L, size_t j0, size_t OL) {
     const QuotientParams& P = d_qp;
-    const size_t L = (size_t)1 << (P.logn + P.rate_bits);
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= L) return;
+    u64* __restrict__ out = out_ + j0;
+    xs += j0;
+    l0s += j0;
     const int NC = P.num_challenges, NPP = P.num_partial_products, R = P.num_routed, C = P.num_constants;
     // next row of Z: natural index + 2^rate_bits  <=>  same coset, k -> k + 1 (k = bitrev_n(j mod N))
     const u32 nmask = (1u << P.logn) - 1;
@@ -74,21 +79,22 @@ __global__ void __launch_bounds__(256) k_quotient_perm(const u64* __restrict__ c
         }
     }
     out[j] = acc0.reduce();
-    if (NC > 1) out[L + j] = acc1.reduce();
+    if (NC > 1) out[OL + j] = acc1.reduce();
     if (scale_now) {
-        const u64 zhi = P.zh_inv[bitrev32((u32)(j >> P.logn), P.rate_bits)];
+        const u64 zhi = P.zh_inv[bitrev32((u32)((j0 + j) >> P.logn), P.rate_bits)];
         out[j] = gl_mul(out[j], zhi);
-        if (NC > 1) out[L + j] = gl_mul(out[L + j], zhi);
+        if (NC > 1) out[OL + j] = gl_mul(out[OL + j], zhi);
     }
 }
 
 template <int KIND>
 __global__ void __launch_bounds__(256) k_quotient_gate(const u64* __restrict__ cs, const u64* __restrict__ wires,
-                                                       u64* __restrict__ out, int g, u32 op_lo, u32 op_hi, int scale_now) {
+                                                       u64* __restrict__ out_, int g, u32 op_lo, u32 op_hi, int scale_now,
+                                                       size_t L, size_t j0, size_t OL) {
     const QuotientParams& P = d_qp;
-    const size_t L = (size_t)1 << (P.logn + P.rate_bits);
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= L) return;
+    u64* __restrict__ out = out_ + j0;
     const GateDev& gd = P.gates[g];
     auto wire = [&](int i) -> u64 { return __ldg(wires + (size_t)i * L + j); };
     auto konst = [&](int i) -> u64 { return __ldg(cs + (size_t)(P.num_selectors + i) * L + j); };
@@ -100,14 +106,14 @@ __global__ void __launch_bounds__(256) k_quotient_gate(const u64* __restrict__ c
     sink.k = sink.base = off;
     eval_gate_kind<KIND>(gd, op_lo, op_hi, wire, konst, P.pi_hash, sink);
     u64 a0 = gl_add(out[j], gl_mul(f, sink.a0.reduce()));
-    u64 a1 = P.num_challenges > 1 ? gl_add(out[L + j], gl_mul(f, sink.a1.reduce())) : 0;
+    u64 a1 = P.num_challenges > 1 ? gl_add(out[OL + j], gl_mul(f, sink.a1.reduce())) : 0;
     if (scale_now) {
-        const u64 zhi = P.zh_inv[bitrev32((u32)(j >> P.logn), P.rate_bits)];
+        const u64 zhi = P.zh_inv[bitrev32((u32)((j0 + j) >> P.logn), P.rate_bits)];
         a0 = gl_mul(a0, zhi);
         a1 = gl_mul(a1, zhi);
     }
     out[j] = a0;
-    if (P.num_challenges > 1) out[L + j] = a1;
+    if (P.num_challenges > 1) out[OL + j] = a1;
 }
 
 struct StoreSink {  // stand-alone entry point: out[k][pt] += filter * constraint_k
@@ -168,13 +174,13 @@ void quotient_points(DevCtx* c, u64* d_xs, u64* d_l0s, int logn, int rate_bits, 
 }
 
 void quotient_eval(DevCtx* c, const QuotientParams& qp, const u64* d_cs, const u64* d_wires, const u64* d_zpp, const u64* d_xs,
-                   const u64* d_l0s, u64* d_out, size_t lde) {
+                   const u64* d_l0s, u64* d_out, size_t npts, size_t j0, size_t out_stride) {
     const int TH = 256;
-    const unsigned grid = (unsigned)((lde + TH - 1) / TH);
+    const unsigned grid = (unsigned)((npts + TH - 1) / TH);
     int last = -1;
     for (int g = 0; g < qp.num_gates; g++)
         if (qp.gates[g].num_constraints) last = g;
-    k_quotient_perm<<<grid, TH, 0, c->stream>>>(d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, last < 0);
+    k_quotient_perm<<<grid, TH, 0, c->stream>>>(d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, last < 0, npts, j0, out_stride);
     count_launch(c);
     for (int g = 0; g <= last; g++) {
         const GateDev& gd = qp.gates[g];
@@ -182,7 +188,7 @@ void quotient_eval(DevCtx* c, const QuotientParams& qp, const u64* d_cs, const u
         const u32 nops = gate_num_ops(gd.kind, gd.params);
         const int fin = g == last;
         switch (gd.kind) {
-#define P2G_LAUNCH(KIND) case KIND: k_quotient_gate<KIND><<<grid, TH, 0, c->stream>>>(d_cs, d_wires, d_out, g, 0, nops, fin); break;
+#define P2G_LAUNCH(KIND) case KIND: k_quotient_gate<KIND><<<grid, TH, 0, c->stream>>>(d_cs, d_wires, d_out, g, 0, nops, fin, npts, j0, out_stride); break;
             P2G_LAUNCH(P2G_GATE_CONSTANT) P2G_LAUNCH(P2G_GATE_PUBLIC_INPUT) P2G_LAUNCH(P2G_GATE_ARITHMETIC)
             P2G_LAUNCH(P2G_GATE_BASE_SUM) P2G_LAUNCH(P2G_GATE_POSEIDON) P2G_LAUNCH(P2G_GATE_RANDOM_ACCESS)
             P2G_LAUNCH(P2G_GATE_U32_ARITHMETIC) P2G_LAUNCH(P2G_GATE_U32_ADD_MANY) P2G_LAUNCH(P2G_GATE_U32_SUBTRACTION)

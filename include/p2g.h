@@ -159,11 +159,17 @@ int p2g_prove_device(p2g_circuit* c, const uint64_t* d_wires, const uint64_t* pu
 size_t p2g_proof_size_bound(const p2g_circuit* c);
 
 /* ---- multi-GPU (one process per GPU): coset sharding, SURVEY 8(e) ----------------------------------------------
- * Each rank owns lde/world contiguous leaves of every oracle = whole cosets.  `allgather` is called by the library
- * whenever ranks must exchange data (Merkle subtree caps, opened rows); the host binds it to NCCL / torch.distributed.
- * It must gather `bytes` from every rank into recv (world * bytes), rank order.  is_device: buffers are device memory. */
+ * One proof across `world` GPUs (a power of two <= 2^min(rate_bits, cap_height)).  Rank r owns the leaves
+ * [r * 8N/world, (r+1) * 8N/world) of every oracle = whole LDE cosets = whole Merkle-cap subtrees: their LDE, leaf and
+ * subtree hashing, their share of the quotient evaluation and of the query openings.  `allgather` is called by the
+ * library (same sequence on every rank) whenever ranks exchange data -- inverse-NTT column blocks, Merkle subtree caps,
+ * quotient values, opened rows; the host binds it to NCCL (torch.distributed / ncclAllGather).  It must gather `bytes`
+ * from every rank into recv (world * bytes, rank order); send may alias recv + rank * bytes (in-place).  is_device:
+ * both buffers are device memory on the handle's device, and all prior work on them has completed.  Return 0 on success.
+ * Every rank passes the same desc, the same wires and public inputs to p2g_prove; all ranks return the same bytes. */
 typedef int (*p2g_allgather_fn)(void* user, const void* send, void* recv, size_t bytes, int is_device);
-int p2g_circuit_set_sharding(p2g_circuit* c, int rank, int world, p2g_allgather_fn allgather, void* user);
+int p2g_circuit_create_sharded(const p2g_circuit_desc* desc, int device, int rank, int world, p2g_allgather_fn allgather,
+                               void* user, p2g_circuit** out);
 
 /* ---- intermediates of the last prove, for parity tests ---------------------------------------------------------- */
 enum p2g_buffer {
@@ -177,7 +183,7 @@ enum p2g_buffer {
     P2G_BUF_CHALLENGES = 7,     /* u64: betas[nc], gammas[nc], alphas[nc], zeta[2], fri_alpha[2], fri_betas[2*L], pow_witness, indices[q] */
     P2G_BUF_FINAL_POLY = 8,     /* ext coefficients (2 u64 each)                                                       */
     P2G_BUF_FRI_CAPS = 9,       /* num_fri_layers x 2^cap_height digests                                               */
-    P2G_BUF_WIRES_LDE = 10      /* num_wires x 8N u64, col-major, leaf (bit-reversed) order                            */
+    P2G_BUF_WIRES_LDE = 10      /* num_wires x 8N/world u64, col-major, leaf (bit-reversed) order: this rank's leaves    */
 };
 int p2g_circuit_read(p2g_circuit* c, int what, void* out, size_t* len /* in: capacity, out: bytes */);
 
