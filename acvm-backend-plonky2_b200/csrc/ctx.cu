@@ -17,6 +17,20 @@ extern "C" int p2g_device_count(void) {
     return n;
 }
 
+// Pinned host memory for the witness matrix: p2g_prove's upload then runs at full PCIe rate and overlaps the inverse NTT.
+extern "C" void* p2g_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("p2g_host_alloc: cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void p2g_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 static std::mutex g_ctx_mu;
 static std::map<int, DevCtx*> g_ctx;
 

@@ -388,6 +388,20 @@ struct p2g_circuit {
     int loglde_l = 0;
     p2g_allgather_fn allgather = nullptr;
     void* allgather_user = nullptr;
+    // host-trace upload, pipelined with the inverse NTT: column chunks go up on `copy` while earlier chunks are transformed
+    struct Upload {
+        cudaStream_t copy = nullptr;
+        std::vector<cudaEvent_t> pool;                    // reusable events
+        std::vector<std::tuple<int, int, cudaEvent_t>> chunks;   // [col0, col1) ready when the event fires
+        cudaEvent_t start = nullptr, routed = nullptr;    // routed: columns [0, R) needed by the Z computation (sharded only)
+        cudaEvent_t last = nullptr;
+        bool active = false;
+        double bytes = 0;
+    } up;
+    ~p2g_circuit() {
+        for (cudaEvent_t e : up.pool) cudaEventDestroy(e);
+        if (up.copy) cudaStreamDestroy(up.copy);
+    }
 };
 
 namespace {
@@ -419,20 +433,54 @@ void commit_from_coeffs(p2g_circuit* C, PolyBatch& b) {
 }
 // values -> coefficients.  Sharded: each rank transforms a contiguous block of columns and the blocks are all-gathered
 // (the coefficient buffer is padded to world * ceil(ncols / world) columns so the blocks are equal).
-void ifft_columns(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs) {
+// the block of columns whose inverse NTT this rank computes; false = every rank transforms all columns (no exchange)
+bool column_block(const p2g_circuit* C, int ncols, int* c0, int* c1) {
+    if (C->world == 1 || ncols < 4 * C->world) {
+        *c0 = 0;
+        *c1 = ncols;
+        return false;
+    }
+    const int per = (ncols + C->world - 1) / C->world;
+    *c0 = std::min(ncols, C->rank * per);
+    *c1 = std::min(ncols, *c0 + per);
+    return true;
+}
+void ifft_columns(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs, const p2g_circuit::Upload* up = nullptr) {
     const int per = (b.ncols + C->world - 1) / C->world;
     size_t want = (size_t)per * C->world * C->n;
     if (b.coeffs.n != want) b.coeffs.alloc(want);
-    if (C->world == 1 || b.ncols < 4 * C->world) {
-        ntt_ifft(C->ctx, d_values, values_cs, b.coeffs.p, C->n, C->logn, b.ncols);
+    int c0, c1;
+    const bool sharded = column_block(C, b.ncols, &c0, &c1);
+    if (up) {   // chunks of [c0, c1) arrive on the copy stream; transform each as soon as it is there
+        for (auto& ch : up->chunks) {
+            int a = std::get<0>(ch), e = std::get<1>(ch);
+            CUDA_CHECK(cudaStreamWaitEvent(C->ctx->stream, std::get<2>(ch), 0));
+            ntt_ifft(C->ctx, d_values + (size_t)a * values_cs, values_cs, b.coeffs.p + (size_t)a * C->n, C->n, C->logn, e - a);
+        }
+    } else {
+        ntt_ifft(C->ctx, d_values + (size_t)c0 * values_cs, values_cs, b.coeffs.p + (size_t)c0 * C->n, C->n, C->logn, c1 - c0);
+    }
+    if (sharded) shard_allgather(C, b.coeffs.p + (size_t)C->rank * per * C->n, b.coeffs.p, (size_t)per * C->n * 8, true);
+}
+void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs, const p2g_circuit::Upload* up = nullptr) {
+    if (up && C->world == 1) {
+        // single GPU, trace arriving from the host: inverse NTT + LDE per column chunk, so both hide behind the upload
+        DevCtx* c = C->ctx;
+        size_t want = (size_t)b.ncols * C->n;
+        if (b.coeffs.n < want) b.coeffs.alloc(want);
+        if (b.lde.n != (size_t)b.ncols * C->lde_l) b.lde.alloc((size_t)b.ncols * C->lde_l);
+        for (auto& ch : up->chunks) {
+            int a = std::get<0>(ch), e = std::get<1>(ch);
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, std::get<2>(ch), 0));
+            ntt_ifft(c, d_values + (size_t)a * values_cs, values_cs, b.coeffs.p + (size_t)a * C->n, C->n, C->logn, e - a);
+            ntt_lde(c, b.coeffs.p + (size_t)a * C->n, C->n, b.lde.p + (size_t)a * C->lde_l, C->lde_l, C->logn, C->d.rate_bits, e - a,
+                    GL_GEN, C->z0, C->nzl);
+        }
+        merkle_build(c, &b.tree, b.lde.p, C->lde_l, C->loglde_l, b.ncols, (int)C->d.cap_height - C->logworld, C->h);
+        upload_level_ptrs(c, b);
         return;
     }
-    const int c0 = std::min(b.ncols, C->rank * per), c1 = std::min(b.ncols, c0 + per);
-    ntt_ifft(C->ctx, d_values + (size_t)c0 * values_cs, values_cs, b.coeffs.p + (size_t)c0 * C->n, C->n, C->logn, c1 - c0);
-    shard_allgather(C, b.coeffs.p + (size_t)C->rank * per * C->n, b.coeffs.p, (size_t)per * C->n * 8, true);
-}
-void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs) {
-    ifft_columns(C, b, d_values, values_cs);
+    ifft_columns(C, b, d_values, values_cs, up);
     commit_from_coeffs(C, b);
 }
 // the 2^cap_height cap of an oracle: this rank's subtree roots, all-gathered when sharded (the one collective of the
@@ -686,7 +734,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     }
 
     // 2. wires commitment
-    commit_from_values(C, C->wires, d_wires, n);
+    commit_from_values(C, C->wires, d_wires, n, C->up.active ? &C->up : nullptr);
     std::vector<digest_t> wires_cap = read_cap(C, C->wires.tree);
     CUDA_CHECK(cudaEventRecord(ev[1], st));
     tr.mark("wires commit");
@@ -720,6 +768,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
         struct { u64* p; } q = {ensure(C->ws.q, (size_t)NC * nchunk * n)}, totals = {ensure(C->ws.totals, 4 * nt)};
         dim3 g1((unsigned)((n + 127) / 128), NC);
+        if (C->up.active && C->up.routed) CUDA_CHECK(cudaStreamWaitEvent(st, C->up.routed, 0));
         k_zpp_chunks<<<g1, 128, 0, st>>>(d_wires, n, C->sigma_values.p, xtab, xsplit, q.p);
         dim3 g2((unsigned)((nt + 127) / 128), NC);
         k_zscan_totals<<<g2, 128, 0, st>>>(q.p, totals.p, nt);
@@ -1115,7 +1164,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         cudaEventElapsedTime(&t, ev[4], ev[5]); tm->fri_ms = t;
         cudaEventElapsedTime(&t, ev[5], ev[6]); tm->d2h_ms = t;
         cudaEventElapsedTime(&t, ev_start ? ev_start : ev[0], ev[6]); tm->total_ms = t;
-        if (ev_start) { cudaEventElapsedTime(&t, ev_start, ev[0]); tm->h2d_ms = t; } else tm->h2d_ms = 0;
+        if (ev_start && C->up.last) { cudaEventElapsedTime(&t, ev_start, C->up.last); tm->h2d_ms = t; } else tm->h2d_ms = 0;
         tm->quotient_kernel_ms = quotient_kernel_ms;
         tm->ntt_ms = c->ntt_ms;
         tm->merkle_ms = c->merkle_ms;
@@ -1128,6 +1177,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         tm->leaf_hash_bytes = c->leaf_bytes;
         tm->lde_bytes = c->lde_bytes;
         tm->lde_launches = c->lde_launches;
+        tm->h2d_bytes = C->up.active ? C->up.bytes : 0;
     }
     size_t need = wb.len;
     bool small = !out || need > wb.cap;
@@ -1157,19 +1207,64 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
         } toff{c};
         const u64* d_wires = wires;
         cudaEvent_t ev_start = nullptr;
+        p2g_circuit::Upload& up = C->up;
+        up.active = false;
         if (!on_device) {
-            size_t cnt = (size_t)C->d.num_wires * C->n;
+            // Upload in column chunks on a copy stream; the inverse NTT of chunk k overlaps the transfer of chunk k+1.
+            // A sharded rank uploads only what it reads: its inverse-NTT column block and the routed columns (Z computation).
+            const int W = C->d.num_wires, R = C->d.num_routed_wires;
+            const size_t n = C->n;
+            size_t cnt = (size_t)W * n;
             if (C->wires_values.n != cnt) C->wires_values.alloc(cnt);
-            CUDA_CHECK(cudaEventCreate(&ev_start));
-            CUDA_CHECK(cudaEventRecord(ev_start, c->stream));
-            CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p, wires, cnt * 8, cudaMemcpyHostToDevice, c->stream));
+            if (!up.copy) CUDA_CHECK(cudaStreamCreateWithFlags(&up.copy, cudaStreamNonBlocking));
+            size_t used = 0;
+            auto next_event = [&]() {
+                if (used == up.pool.size()) {
+                    cudaEvent_t e;
+                    CUDA_CHECK(cudaEventCreate(&e));
+                    up.pool.push_back(e);
+                }
+                return up.pool[used++];
+            };
+            auto copy_cols = [&](int a, int e) {
+                CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)a * n, wires + (size_t)a * n, (size_t)(e - a) * n * 8,
+                                           cudaMemcpyHostToDevice, up.copy));
+                up.bytes += (double)(e - a) * n * 8;
+            };
+            up.chunks.clear();
+            up.bytes = 0;
+            up.routed = nullptr;
+            // the copy stream must not overwrite the staging buffer while the previous proof's kernels still read it
+            cudaEvent_t idle = next_event();
+            CUDA_CHECK(cudaEventRecord(idle, c->stream));
+            CUDA_CHECK(cudaStreamWaitEvent(up.copy, idle, 0));
+            up.start = next_event();
+            CUDA_CHECK(cudaEventRecord(up.start, up.copy));
+            ev_start = up.start;
+            int c0, c1;
+            column_block(C, W, &c0, &c1);
+            int step = std::max(1, std::min(32, (int)(((size_t)64 << 20) / (n * 8)) + 1));   // >= 64 MB per chunk ...
+            step = std::max(step, (c1 - c0 + 7) / 8);                                         // ... and at most 8 chunks for small traces
+            for (int a = c0; a < c1; a += step) {
+                int e = std::min(c1, a + step);
+                copy_cols(a, e);
+                cudaEvent_t ev = next_event();
+                CUDA_CHECK(cudaEventRecord(ev, up.copy));
+                up.chunks.emplace_back(a, e, ev);
+                up.last = ev;
+            }
+            if (c0 > 0 || c1 < R) {   // sharded: routed columns outside the block
+                if (c0 > 0) copy_cols(0, std::min(c0, R));
+                if (c1 < R) copy_cols(c1, R);
+                up.routed = next_event();
+                CUDA_CHECK(cudaEventRecord(up.routed, up.copy));
+                up.last = up.routed;
+            }
+            up.active = true;
             d_wires = C->wires_values.p;
         }
-        struct EvDel {
-            cudaEvent_t e;
-            ~EvDel() { if (e) cudaEventDestroy(e); }
-        } evd{ev_start};
         prove_impl(C, d_wires, public_inputs, n_pi, forced_pow, out, out_len, tm, ev_start);
+        up.active = false;
     });
 }
 

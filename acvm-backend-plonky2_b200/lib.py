@@ -49,7 +49,8 @@ class TimingsS(C.Structure):
                 ("quotient_kernel_ms", C.c_float), ("ntt_bytes", C.c_double), ("merkle_bytes", C.c_double),
                 ("kernel_launches", C.c_uint32), ("leaf_hash_launches", C.c_uint32),
                 ("leaf_hash_ms", C.c_float), ("lde_ms", C.c_float), ("leaf_hash_bytes", C.c_double),
-                ("lde_bytes", C.c_double), ("d2h_ms", C.c_float), ("lde_launches", C.c_uint32)]
+                ("lde_bytes", C.c_double), ("d2h_ms", C.c_float), ("lde_launches", C.c_uint32),
+                ("h2d_bytes", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -58,7 +59,7 @@ class TimingsS(C.Structure):
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
 
 # every symbol include/p2g.h declares (tests/test_abi.py checks the header against this list and the built library)
-EXPORTS = ["p2g_version", "p2g_device_count", "p2g_last_error", "p2g_circuit_create", "p2g_circuit_destroy",
+EXPORTS = ["p2g_version", "p2g_device_count", "p2g_last_error", "p2g_host_alloc", "p2g_host_free", "p2g_circuit_create", "p2g_circuit_destroy",
            "p2g_circuit_cap", "p2g_prove", "p2g_prove_device", "p2g_proof_size_bound", "p2g_circuit_create_sharded",
            "p2g_circuit_read", "p2g_ifft", "p2g_lde", "p2g_coset_ifft_leaforder", "p2g_merkle_cap",
            "p2g_poseidon_permute", "p2g_keccak256", "p2g_eval_gate_constraints", "p2g_test_field_ops"]
@@ -110,6 +111,10 @@ def lib():
         L.p2g_keccak256.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int]
         L.p2g_eval_gate_constraints.argtypes = [C.POINTER(DescS), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                                 C.c_void_p, C.c_int]
+        L.p2g_host_alloc.restype = C.c_void_p
+        L.p2g_host_alloc.argtypes = [C.c_size_t]
+        L.p2g_host_free.argtypes = [C.c_void_p]
+        L.p2g_host_free.restype = None
         L.p2g_test_field_ops.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         _LIB = L
     return _LIB

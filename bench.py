@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--workload", default="ecdsa")
     ap.add_argument("--hasher", default="keccak25")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-proof-across-N-GPUs measurement")
     ap.add_argument("--cpu-sample-bits", type=int, default=0, help="rows (log2) of the CPU-baseline sample; 0 = auto")
     return ap.parse_args()
 
@@ -219,6 +220,35 @@ def main():
     ms_e2e, outs_e2e = timed(lambda: data.prove(wires_host, sc.public_inputs), args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # one proof across all N GPUs (coset sharding + NCCL all-gathers): latency of a single proof
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        data.close()
+        grp = p2g.sharding.TorchDistGroup(device=local_rank)
+        sc0 = sc if rank == 0 else None
+        if rank != 0:   # every rank proves the SAME circuit and witness
+            sc0 = p2g.synth.SyntheticCircuit(args.degree_bits, args.workload, config=cfg, num_public_inputs=4,
+                                             seed=0xAC1D + 3, pinned=True)
+        sdata = p2g.CircuitData(sc0.common, sc0.constants_sigmas, device=local_rank, shard=grp)
+        wh = sc0._wires_t
+        wd = wh.cuda()
+        for _ in range(args.warmup):
+            sdata.prove(wd, sc0.public_inputs)
+        ms_sd, souts = timed(lambda: sdata.prove(wd, sc0.public_inputs), args.steps)
+        sdata.prove(wh, sc0.public_inputs)
+        ms_se, souts_e = timed(lambda: sdata.prove(wh, sc0.public_inputs), args.steps)
+        digest = torch.tensor(list(__import__("hashlib").sha256(souts[0].to_bytes()).digest()), device="cuda", dtype=torch.int32)
+        gathered = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(gathered, digest)
+        same = all(bool((g == gathered[0]).all()) for g in gathered)
+        sharded = {"proofs_per_s": args.steps / (ms_sd / 1e3), "ms_per_proof": ms_sd / args.steps,
+                   "e2e_ms_per_proof": ms_se / args.steps, "h2d_bytes_per_rank": int(souts_e[0].timings.get("h2d_bytes", 0)),
+                   "collectives_per_proof": grp.calls // max(1, 2 * (args.warmup + args.steps) + 1),
+                   "identical_bytes_on_all_ranks": same,
+                   "stages_ms": {k: round(sum(o.timings[k] for o in souts) / args.steps, 3)
+                                 for k in ["wires_commit_ms", "zs_pp_ms", "quotient_ms", "openings_ms", "fri_ms", "total_ms"]}}
+        sdata.close()
+
     if rank == 0:
         K = args.steps
         tms = [o.timings for o in outs]
@@ -255,6 +285,9 @@ def main():
             "stages_ms": stages,
             "clocks": clocks,
         }
+        if sharded is not None:
+            line["sharded_proof"] = dict(sharded, note=f"ONE proof of the same circuit coset-sharded across the {world} GPUs "
+                                                      "(NCCL all-gathers of coefficient blocks, subtree caps, quotient values, opened rows)")
         if not args.no_cpu_baseline and world == 1:
             bits = pick_cpu_sample_bits(p2g, args)
             dt, cores = cpu_sample_proof(p2g, args, bits, 300)
@@ -264,7 +297,8 @@ def main():
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
-    data.close()
+    if sharded is None:
+        data.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -124,6 +124,7 @@ typedef struct p2g_timings {
     double lde_bytes;          /* algorithmic bytes of the LDE passes (8N read + 64N written per column)               */
     float d2h_ms;              /* query-opening gather + proof assembly                                                */
     uint32_t lde_launches;
+    double h2d_bytes;          /* bytes of the trace this call uploaded (a sharded rank uploads only the columns it reads)  */
 } p2g_timings;
 
 typedef struct p2g_circuit p2g_circuit;
@@ -132,6 +133,10 @@ typedef struct p2g_circuit p2g_circuit;
 int p2g_version(void);
 int p2g_device_count(void);
 const char* p2g_last_error(void); /* thread-local, never NULL */
+
+/* Pinned (page-locked) host memory for the witness matrix handed to p2g_prove; pageable memory works too, slower. */
+void* p2g_host_alloc(size_t bytes);
+void p2g_host_free(void* p);
 
 /* Per circuit, once: uploads the preprocessed polynomials, builds their LDE + Merkle tree on the device (what
  * CircuitBuilder::build() does at circuit_translation/mod.rs:81) and keeps them resident across proofs.
