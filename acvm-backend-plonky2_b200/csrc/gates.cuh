@@ -74,15 +74,32 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
         break;
     }
     case P2G_GATE_BASE_SUM: {
+        // limbs are loaded once, in batches of 8 independent loads; sum_k limb_k base^k accumulates unreduced
         const u32 base = p[0], nl = p[1];
-        if (op_lo == 0) {
-            u64 acc = 0;
-            for (int k = (int)nl - 1; k >= 0; k--) acc = gl_add(glz_mul_small(acc, base), w(1 + k));   // N + C -> N
-            sink.seek(0);
-            sink.emit(gl_sub(acc, w(0)));
-        }
+        gl_acc sum;
+        sum.clear();
+        u64 pw = 1;   // base^k, canonical
         sink.seek(1 + op_lo);
-        for (u32 k = op_lo; k < op_hi; k++) sink.emit(limb_range_product(w(1 + k), base));
+        for (u32 k0 = 0; k0 < nl; k0 += 8) {
+            u64 L[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) L[i] = (k0 + i < nl) ? w(1 + k0 + i) : 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const u32 k = k0 + i;
+                if (k < nl) {
+                    if (op_lo == 0) {
+                        sum.mac(L[i], pw);
+                        pw = gl_mul_small(pw, base);
+                    }
+                    if (k >= op_lo && k < op_hi) sink.emit(limb_range_product(L[i], base));
+                }
+            }
+        }
+        if (op_lo == 0) {
+            sink.seek(0);
+            sink.emit(gl_sub(sum.reduce(), w(0)));
+        }
         break;
     }
     case P2G_GATE_POSEIDON: {
@@ -185,16 +202,25 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
             u64 hi_not_max = gl_sub(gl_mul(inv, gl_sub(0xFFFFFFFFULL, hi)), 1);
             sink.emit(glz_mul(hi_not_max, lo));
             sink.emit(gl_sub(gl_add(gl_mul(hi, 1ULL << 32), lo), computed));
-            u64 comb_lo = 0, comb_hi = 0;
+            gl_acc32 comb_lo, comb_hi;   // sum_j limb_j 4^j, unreduced
+            comb_lo.clear();
+            comb_hi.clear();
             const u32 lw = 6 * ops + 32 * i;
-            for (int j = 31; j >= 0; j--) {
-                u64 limb = w(lw + j);
-                sink.emit(limb4_check(limb));
-                if (j < 16) comb_lo = gl_add(glz_mul_small(comb_lo, 4), limb);   // N + C -> N
-                else comb_hi = gl_add(glz_mul_small(comb_hi, 4), limb);
+#pragma unroll 1
+            for (int b = 3; b >= 0; b--) {   // four batches of 8 independent loads
+                u64 L[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) L[j] = w(lw + 8 * b + j);
+                const u32 sh = (b & 1) ? 16 : 0;
+#pragma unroll
+                for (int j = 7; j >= 0; j--) {
+                    sink.emit(limb4_check(L[j]));
+                    if (b >= 2) comb_hi.mac(L[j], 1u << (sh + 2 * j));
+                    else comb_lo.mac(L[j], 1u << (sh + 2 * j));
+                }
             }
-            sink.emit(gl_sub(comb_lo, lo));
-            sink.emit(gl_sub(comb_hi, hi));
+            sink.emit(gl_sub(comb_lo.reduce(), lo));
+            sink.emit(gl_sub(comb_hi.reduce(), hi));
         }
         break;
     }
@@ -207,16 +233,25 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
             for (u32 j = 0; j <= na; j++) computed = gl_add(computed, w(q + j));  // addends then carry-in
             u64 res = w(q + na + 1), carry = w(q + na + 2);
             sink.emit(gl_sub(gl_add(gl_mul(carry, 1ULL << 32), res), computed));
-            u64 comb_res = 0, comb_carry = 0;
+            gl_acc32 comb_res, comb_carry;
+            comb_res.clear();
+            comb_carry.clear();
             const u32 lw = (na + 3) * ops + 18 * i;
-            for (int j = 17; j >= 0; j--) {
-                u64 limb = w(lw + j);
-                sink.emit(limb4_check(limb));
-                if (j < 16) comb_res = gl_add(glz_mul_small(comb_res, 4), limb);
-                else comb_carry = gl_add(glz_mul_small(comb_carry, 4), limb);
+#pragma unroll 1
+            for (int b = 2; b >= 0; b--) {   // three batches of 6 independent loads
+                u64 L[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++) L[j] = w(lw + 6 * b + j);
+#pragma unroll
+                for (int jj = 5; jj >= 0; jj--) {
+                    const int j = 6 * b + jj;
+                    sink.emit(limb4_check(L[jj]));
+                    if (j < 16) comb_res.mac(L[jj], 1u << (2 * j));
+                    else comb_carry.mac(L[jj], 1u << (2 * (j - 16)));
+                }
             }
-            sink.emit(gl_sub(comb_res, res));
-            sink.emit(gl_sub(comb_carry, carry));
+            sink.emit(gl_sub(comb_res.reduce(), res));
+            sink.emit(gl_sub(comb_carry.reduce(), carry));
         }
         break;
     }
@@ -228,14 +263,21 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
             u64 initial = gl_sub(gl_sub(w(q), w(q + 1)), w(q + 2));
             u64 res = w(q + 3), bout = w(q + 4);
             sink.emit(gl_sub(res, gl_add(initial, gl_mul(bout, 1ULL << 32))));
-            u64 comb = 0;
+            gl_acc32 comb;
+            comb.clear();
             const u32 lw = 5 * ops + 16 * i;
-            for (int j = 15; j >= 0; j--) {
-                u64 limb = w(lw + j);
-                sink.emit(limb4_check(limb));
-                comb = gl_add(glz_mul_small(comb, 4), limb);
+#pragma unroll 1
+            for (int b = 1; b >= 0; b--) {   // two batches of 8 independent loads
+                u64 L[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) L[j] = w(lw + 8 * b + j);
+#pragma unroll
+                for (int j = 7; j >= 0; j--) {
+                    sink.emit(limb4_check(L[j]));
+                    comb.mac(L[j], 1u << (16 * b + 2 * j));
+                }
             }
-            sink.emit(gl_sub(comb, res));
+            sink.emit(gl_sub(comb.reduce(), res));
             sink.emit(glz_mul(bout, gl_sub(1, bout)));
         }
         break;
@@ -245,10 +287,23 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
         sink.seek(op_lo * 17);
         for (u32 i = op_lo; i < op_hi; i++) {
             const u32 aw = nl + 16 * i;
-            u64 acc = 0;
-            for (int j = 15; j >= 0; j--) acc = gl_add(glz_mul_small(acc, 4), w(aw + j));
-            sink.emit(gl_sub(acc, w(i)));
-            for (int j = 0; j < 16; j++) sink.emit(limb4_check(w(aw + j)));
+            gl_acc32 acc;
+            acc.clear();
+            sink.seek(i * 17 + 1);
+#pragma unroll 1
+            for (int b = 0; b < 2; b++) {   // two batches of 8 independent loads
+                u64 L[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) L[j] = w(aw + 8 * b + j);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    acc.mac(L[j], 1u << (16 * b + 2 * j));
+                    sink.emit(limb4_check(L[j]));
+                }
+            }
+            sink.seek(i * 17);
+            sink.emit(gl_sub(acc.reduce(), w(i)));
+            sink.seek(i * 17 + 17);
         }
         break;
     }

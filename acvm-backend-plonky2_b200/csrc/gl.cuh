@@ -172,6 +172,41 @@ struct gl_acc {
     }
 };
 
+// Same idea for a 32-bit multiplier: acc += a * c, a: N, c < 2^32 (limb recombination sum_j limb_j B^j): 2 IMAD.WIDE.U32 and 2
+// carry adds per term.  Low halves a0 * c accumulate in `e`, high halves a1 * c in `o`; total = e + o 2^32.  Up to 2^31 terms.
+struct gl_acc32 {
+    u32 e0, e1, e2, o0, o1, o2;
+    GL_HD void clear() { e0 = e1 = e2 = o0 = o1 = o2 = 0; }
+    GL_HD void mac(u64 a, u32 c) {
+#if defined(__CUDA_ARCH__)
+        u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+        asm("{\n\t"
+            "mad.lo.cc.u32 %0, %6, %8, %0;\n\t"
+            "madc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+            "addc.u32 %2, %2, 0;\n\t"
+            "mad.lo.cc.u32 %3, %7, %8, %3;\n\t"
+            "madc.hi.cc.u32 %4, %7, %8, %4;\n\t"
+            "addc.u32 %5, %5, 0;\n\t"
+            "}"
+            : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(o0), "+r"(o1), "+r"(o2)
+            : "r"(a0), "r"(a1), "r"(c));
+#else
+        unsigned __int128 E = ((unsigned __int128)e2 << 64) | (((u64)e1 << 32) | e0);
+        E += (u64)(u32)a * c;
+        e0 = (u32)E; e1 = (u32)(E >> 32); e2 = (u32)(E >> 64);
+        unsigned __int128 O = ((unsigned __int128)o2 << 64) | (((u64)o1 << 32) | o0);
+        O += (a >> 32) * (u64)c;
+        o0 = (u32)O; o1 = (u32)(O >> 32); o2 = (u32)(O >> 64);
+#endif
+    }
+    // e0 + e1 2^32 + e2 2^64  +  (o0 + o1 2^32 + o2 2^64) 2^32   ->  C
+    GL_HD u64 reduce() const {
+        u64 r = gl_reduce128((u64)e2, ((u64)e1 << 32) | e0);
+        u64 x = gl_reduce128(((u64)o2 << 32) | o1, (u64)o0 << 32);
+        return gl_add(r, x);
+    }
+};
+
 GL_HD u64 gl_pow(u64 b, u64 e) {
     u64 r = 1;
     while (e) {

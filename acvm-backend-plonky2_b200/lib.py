@@ -187,12 +187,12 @@ def keccak256(msgs, device=0):
     return out
 
 
-FIELD_OPS = {"sub": 0, "add": 1, "mul": 2, "mulz": 3, "mul_small": 4, "canon": 5, "reduce128": 6, "dot8": 7}
+FIELD_OPS = {"sub": 0, "add": 1, "mul": 2, "mulz": 3, "mul_small": 4, "canon": 5, "reduce128": 6, "dot8": 7, "dot8_small": 8}
 
 
 def field_ops(op, a, b, device=0):
     """Self-test of csrc/gl.cuh: device >= 0 runs the sm_100a PTX forms, device < 0 their host twins."""
     a, b = _u64(a), _u64(b)
-    out = np.empty(a.size // 8 if op == "dot8" else a.size, dtype=np.uint64)
+    out = np.empty(a.size // 8 if op.startswith("dot8") else a.size, dtype=np.uint64)
     check(lib().p2g_test_field_ops(FIELD_OPS[op], _p(a), _p(b), _p(out), a.size, device))
     return out

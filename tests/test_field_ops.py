@@ -60,6 +60,12 @@ def run(p2g, device):
     al, bl = a.tolist(), b.tolist()
     want = np.array([sum(al[8 * i + k] * bl[8 * i + k] for k in range(8)) % P for i in range(len(al) // 8)], dtype=np.uint64)
     assert np.array_equal(got, want)
+    b32 = b & np.uint64(EPS)
+    b32[:64] = np.uint64(EPS)
+    got = p2g.lib.field_ops("dot8_small", a, b32, device=device)
+    bl = b32.tolist()
+    want = np.array([sum(al[8 * i + k] * bl[8 * i + k] for k in range(8)) % P for i in range(len(al) // 8)], dtype=np.uint64)
+    assert np.array_equal(got, want)
 
 
 def test_field_ops_host_twins(p2g):
