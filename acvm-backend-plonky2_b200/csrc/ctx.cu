@@ -52,6 +52,25 @@ DevCtx* get_ctx(int device) {
     return c;
 }
 
+DevCtx* new_child_ctx(int device) {
+    DevCtx* root = get_ctx(device);
+    DevCtx* c = new DevCtx();
+    c->device = device;
+    c->parent = root;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        throw p2g_error(P2G_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    return c;
+}
+void free_child_ctx(DevCtx* c) {
+    if (!c || !c->parent) return;
+    cudaStreamSynchronize(c->stream);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
 StageTimer::StageTimer(DevCtx* ctx, float* accum) : c(ctx), acc(accum) {
     if (!c->timing) return;
     cudaEventCreate(&a);

@@ -53,10 +53,13 @@ struct dbuf {
     }
 };
 
-// Per-device context: one stream, cached twiddle / twist / coset-power tables, launch counters and stage timers.
+// Execution context: one stream, launch counters and stage timers, and the cached twiddle / twist / coset-power tables.
+// There is one root context per device (stand-alone entry points) and one child per circuit handle: a child has its own
+// stream and accounting -- proofs on different handles run concurrently -- and shares the root's tables.
 struct DevCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    DevCtx* parent = nullptr;   // table owner (null for the root)
     std::mutex mu;
     // key: (log size, inverse) -> omega_{2^log}^{+-j}, j < 2^(log-1)        (smem-staged butterfly table)
     std::map<std::pair<int, int>, dbuf<u64>> tw;
@@ -75,8 +78,12 @@ struct DevCtx {
     const u64* get_tw(int log, bool inverse);
     const u64* get_twist(int logB, bool inverse, int* split);
     const u64* get_powtab(int logn, u64 base, u64 premul, int* split);
+    // the 2^rate_bits per-coset index-power tables of an LDE: table z = [lo | hi] powers of shift * omega_{N 2^rate}^{bitrev(z)}
+    const u64* get_coset_tabs(int logn, int rate_bits, u64 shift, int* split, size_t* tab_len);
 };
-DevCtx* get_ctx(int device);
+DevCtx* get_ctx(int device);          // the device's root context
+DevCtx* new_child_ctx(int device);    // own stream, shares the root's tables
+void free_child_ctx(DevCtx* c);
 
 struct StageTimer {  // RAII: accumulates elapsed ms of a stream segment into *acc when ctx->timing is on
     DevCtx* c;

@@ -456,7 +456,9 @@ void run_inverse(DevCtx* c, const XformDesc& d) {
 // ---------------------------------------------------------------------------------------------------------------------
 // table caches
 // ---------------------------------------------------------------------------------------------------------------------
+// Tables are filled on the root's stream and the stream is drained before a new table is published, so any stream may use it.
 const u64* DevCtx::get_tw(int log, bool inverse) {
+    if (parent) return parent->get_tw(log, inverse);
     std::lock_guard<std::mutex> lk(mu);
     auto key = std::make_pair(log, (int)inverse);
     auto it = tw.find(key);
@@ -467,12 +469,14 @@ const u64* DevCtx::get_tw(int log, bool inverse) {
     if (inverse) root = gl_inv(root);
     k_fill_tw<<<(A + 255) / 256, 256, 0, stream>>>(t.p, log, root);
     CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(stream));
     const u64* p = t.p;
     tw.emplace(key, std::move(t));
     return p;
 }
 
 const u64* DevCtx::get_twist(int logB, bool inverse, int* split) {
+    if (parent) return parent->get_twist(logB, inverse, split);
     std::lock_guard<std::mutex> lk(mu);
     int sp = (logB + 1) / 2;
     *split = sp;
@@ -486,12 +490,14 @@ const u64* DevCtx::get_twist(int logB, bool inverse, int* split) {
     k_fill_pow<<<(nlo + 255) / 256, 256, 0, stream>>>(t.p, nlo, root, 1, 1);
     k_fill_pow<<<(nhi + 255) / 256, 256, 0, stream>>>(t.p + nlo, nhi, root, (u64)nlo, 1);
     CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(stream));
     const u64* p = t.p;
     twist.emplace(key, std::move(t));
     return p;
 }
 
 const u64* DevCtx::get_powtab(int logn, u64 base, u64 premul, int* split) {
+    if (parent) return parent->get_powtab(logn, base, premul, split);
     std::lock_guard<std::mutex> lk(mu);
     int sp = (logn + 1) / 2;
     *split = sp;
@@ -503,9 +509,37 @@ const u64* DevCtx::get_powtab(int logn, u64 base, u64 premul, int* split) {
     k_fill_pow<<<(nlo + 255) / 256, 256, 0, stream>>>(t.p, nlo, base, 1, 1);
     k_fill_pow<<<(nhi + 255) / 256, 256, 0, stream>>>(t.p + nlo, nhi, base, (u64)nlo, premul);
     CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(stream));
     const u64* p = t.p;
     powtab.emplace(key, std::move(t));
     return p;
+}
+
+const u64* DevCtx::get_coset_tabs(int logn, int rate_bits, u64 shift, int* split_out, size_t* tab_len_out) {
+    if (parent) return parent->get_coset_tabs(logn, rate_bits, shift, split_out, tab_len_out);
+    // coset z covers leaves [z*N, (z+1)*N) = shift * omega_{N*nz}^{bitrev(z)} * <omega_N>
+    const int nz = 1 << rate_bits;
+    const int split = (logn + 1) / 2;
+    const size_t tab_len = ((size_t)1 << split) + ((size_t)1 << (logn - split));
+    *split_out = split;
+    *tab_len_out = tab_len;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple(logn + 64 * (rate_bits + 1), shift, (u64)0);
+    auto it = powtab.find(key);
+    if (it == powtab.end()) {
+        const u64 wl = gl_root_of_unity(logn + rate_bits);
+        dbuf<u64> t(tab_len * nz);
+        for (int z = 0; z < nz; z++) {
+            u64 s = gl_mul(shift, gl_pow(wl, bitrev32((u32)z, rate_bits)));
+            u32 nlo = 1u << split, nhi = 1u << (logn - split);
+            k_fill_pow<<<(nlo + 255) / 256, 256, 0, stream>>>(t.p + z * tab_len, nlo, s, 1, 1);
+            k_fill_pow<<<(nhi + 255) / 256, 256, 0, stream>>>(t.p + z * tab_len + nlo, nhi, s, (u64)nlo, 1);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        it = powtab.emplace(key, std::move(t)).first;
+    }
+    return it->second.p;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -542,29 +576,9 @@ void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t ou
         nzl = nz;
     }
     const size_t n = (size_t)1 << logn;
-    // per-coset index-power tables: coset z covers leaves [z*N, (z+1)*N) = shift * omega_{N*nz}^{bitrev(z)} * <omega_N>
-    int split = (logn + 1) / 2;
-    size_t tab_len = ((size_t)1 << split) + ((size_t)1 << (logn - split));
-    u64 wl = gl_root_of_unity(logn + rate_bits);
-    // one contiguous buffer holding the nz tables, cached under (logn, shift, rate_bits marker)
-    auto key = std::make_tuple(logn + 64 * (rate_bits + 1), shift, (u64)0);
-    const u64* tabs;
-    {
-        std::lock_guard<std::mutex> lk(c->mu);
-        auto it = c->powtab.find(key);
-        if (it == c->powtab.end()) {
-            dbuf<u64> t(tab_len * nz);
-            for (int z = 0; z < nz; z++) {
-                u64 s = gl_mul(shift, gl_pow(wl, bitrev32((u32)z, rate_bits)));
-                u32 nlo = 1u << split, nhi = 1u << (logn - split);
-                k_fill_pow<<<(nlo + 255) / 256, 256, 0, c->stream>>>(t.p + z * tab_len, nlo, s, 1, 1);
-                k_fill_pow<<<(nhi + 255) / 256, 256, 0, c->stream>>>(t.p + z * tab_len + nlo, nhi, s, (u64)nlo, 1);
-            }
-            CUDA_CHECK(cudaGetLastError());
-            it = c->powtab.emplace(key, std::move(t)).first;
-        }
-        tabs = it->second.p;
-    }
+    int split;
+    size_t tab_len;
+    const u64* tabs = c->get_coset_tabs(logn, rate_bits, shift, &split, &tab_len);
     XformDesc d = {};
     d.in = d_coeffs;
     d.in_cs = in_cs;

@@ -42,14 +42,13 @@ struct ZppParams {
     u64 betas[2], gammas[2];
     u64 beta_k[2][P2G_MAX_ROUTED];
 };
-__constant__ ZppParams d_zp;
 
 #define ZPP_MAX_CHUNKS 16
 
 // q[c][m][i] = prod_{r in chunk m} (w_r + beta k_r x + gamma) / (w_r + beta sigma_r + gamma) at row i
-__global__ void __launch_bounds__(128) k_zpp_chunks(const u64* __restrict__ wires, size_t wires_cs, const u64* __restrict__ sigmas,
-                                                    const u64* __restrict__ xtab, int xsplit, u64* __restrict__ q) {
-    const ZppParams& P = d_zp;
+__global__ void __launch_bounds__(128) k_zpp_chunks(const __grid_constant__ ZppParams P, const u64* __restrict__ wires, size_t wires_cs,
+                                                    const u64* __restrict__ sigmas, const u64* __restrict__ xtab, int xsplit,
+                                                    u64* __restrict__ q) {
     const size_t n = (size_t)1 << P.logn;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -86,8 +85,7 @@ __global__ void __launch_bounds__(128) k_zpp_chunks(const u64* __restrict__ wire
 #define SCAN_CH 16  // rows per thread in the scans
 
 // phase 1: totals[c][t] = prod over rows of chunk t of prod_m q[c][m][row]
-__global__ void k_zscan_totals(const u64* __restrict__ q, u64* __restrict__ totals, size_t nt) {
-    const ZppParams& P = d_zp;
+__global__ void k_zscan_totals(const __grid_constant__ ZppParams P, const u64* __restrict__ q, u64* __restrict__ totals, size_t nt) {
     const size_t n = (size_t)1 << P.logn;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
@@ -123,8 +121,8 @@ __global__ void __launch_bounds__(1024) k_scan_mul_excl(u64* totals, size_t nt) 
     }
 }
 // phase 3: write Z (column c) and the partial products (column NC + c*NPP + m)
-__global__ void k_zscan_apply(const u64* __restrict__ q, const u64* __restrict__ totals, size_t nt, u64* __restrict__ out) {
-    const ZppParams& P = d_zp;
+__global__ void k_zscan_apply(const __grid_constant__ ZppParams P, const u64* __restrict__ q, const u64* __restrict__ totals, size_t nt,
+                              u64* __restrict__ out) {
     const size_t n = (size_t)1 << P.logn;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
@@ -401,6 +399,7 @@ struct p2g_circuit {
     ~p2g_circuit() {
         for (cudaEvent_t e : up.pool) cudaEventDestroy(e);
         if (up.copy) cudaStreamDestroy(up.copy);
+        free_child_ctx(ctx);
     }
 };
 
@@ -576,8 +575,8 @@ static int circuit_create_impl(const p2g_circuit_desc* desc, int device, int ran
             logworld > (int)desc->rate_bits || logworld > (int)desc->cap_height)
             throw p2g_error(P2G_EBADARG, "p2g_circuit_create_sharded: world must be a power of two <= 2^min(rate_bits, cap_height), "
                                          "0 <= rank < world, and an allgather callback is required");
-        DevCtx* c = get_ctx(device);
         C = new p2g_circuit();
+        DevCtx* c = new_child_ctx(device);   // own stream: proofs on different handles overlap on the device
         C->d = *desc;
         C->ctx = c;
         C->rank = rank;
@@ -671,6 +670,7 @@ extern "C" int p2g_circuit_create_sharded(const p2g_circuit_desc* desc, int devi
 extern "C" void p2g_circuit_destroy(p2g_circuit* c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
     delete c;
 }
 
@@ -762,18 +762,17 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             zp.gammas[cc] = gammas[cc];
             for (int r = 0; r < R; r++) zp.beta_k[cc][r] = gl_mul(betas[cc], C->k_is[r]);
         }
-        CUDA_CHECK(cudaMemcpyToSymbolAsync(d_zp, &zp, sizeof(zp), 0, cudaMemcpyHostToDevice, st));
         int xsplit;
         const u64* xtab = c->get_powtab(logn, gl_root_of_unity(logn), 1, &xsplit);
         size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
         struct { u64* p; } q = {ensure(C->ws.q, (size_t)NC * nchunk * n)}, totals = {ensure(C->ws.totals, 4 * nt)};
         dim3 g1((unsigned)((n + 127) / 128), NC);
         if (C->up.active && C->up.routed) CUDA_CHECK(cudaStreamWaitEvent(st, C->up.routed, 0));
-        k_zpp_chunks<<<g1, 128, 0, st>>>(d_wires, n, C->sigma_values.p, xtab, xsplit, q.p);
+        k_zpp_chunks<<<g1, 128, 0, st>>>(zp, d_wires, n, C->sigma_values.p, xtab, xsplit, q.p);
         dim3 g2((unsigned)((nt + 127) / 128), NC);
-        k_zscan_totals<<<g2, 128, 0, st>>>(q.p, totals.p, nt);
+        k_zscan_totals<<<g2, 128, 0, st>>>(zp, q.p, totals.p, nt);
         k_scan_mul_excl<<<NC, 1024, 0, st>>>(totals.p, nt);
-        k_zscan_apply<<<g2, 128, 0, st>>>(q.p, totals.p, nt, C->zpp_values.p);
+        k_zscan_apply<<<g2, 128, 0, st>>>(zp, q.p, totals.p, nt, C->zpp_values.p);
         count_launch(c, 4);
         CUDA_CHECK(cudaGetLastError());
         tr.mark("zpp launches");
@@ -818,7 +817,6 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         for (u32 r = 0; r < (1u << d.rate_bits); r++) qp.zh_inv[r] = C->zh_inv[r];
         memcpy(qp.pi_hash, pi_hash, 32);
         fill_gates(qp, C);
-        quotient_upload_params(c, qp);
         // quotient values land in quot.lde's first NC columns region?  No: they are transformed in place into the
         // chunk coefficients, so evaluate straight into quot.coeffs viewed as [NC][8N]
         u64* qv = C->quot.coeffs.p;
@@ -1355,14 +1353,13 @@ extern "C" int p2g_eval_gate_constraints(const p2g_circuit_desc* desc, const uin
             o.num_constraints = s.num_constraints;
         }
         if (pi_hash) memcpy(qp.pi_hash, pi_hash, 32);
-        quotient_upload_params(c, qp);
         size_t nc = (size_t)desc->num_constants * npoints, nw = (size_t)desc->num_wires * npoints,
                no = (size_t)desc->num_gate_constraints * npoints;
         dbuf<u64> dc(nc), dw(nw), dout(std::max<size_t>(no, 1));
         CUDA_CHECK(cudaMemcpyAsync(dc.p, constants, nc * 8, cudaMemcpyHostToDevice, c->stream));
         CUDA_CHECK(cudaMemcpyAsync(dw.p, wires, nw * 8, cudaMemcpyHostToDevice, c->stream));
         CUDA_CHECK(cudaMemsetAsync(dout.p, 0, no * 8, c->stream));
-        gates_eval_standalone(c, dc.p, dw.p, dout.p, npoints);
+        gates_eval_standalone(c, qp, dc.p, dw.p, dout.p, npoints);
         CUDA_CHECK(cudaMemcpyAsync(out, dout.p, no * 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
     });

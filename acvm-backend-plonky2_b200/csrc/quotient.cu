@@ -11,17 +11,18 @@
 #include "internal.h"
 #include "quotient.h"
 
-__constant__ QuotientParams d_qp;
-
+// The per-proof parameters (alpha powers, beta k_i, gate table: ~13 KB) travel as a __grid_constant__ kernel parameter: they
+// sit in the constant bank (uniform, broadcast reads) and nothing is shared between proofs in flight on other streams.
 namespace {
 
 struct WeightedSink {  // folds constraint k into sum_c += v * alpha_c^(off + k); products accumulated unreduced (gl_acc)
     gl_acc a0, a1;
     int k, base;
+    const u64 *ap0, *ap1;   // alpha_0^k, alpha_1^k tables inside the kernel's parameter block
     __device__ __forceinline__ void seek(int idx) { k = base + idx; }
     __device__ __forceinline__ void emit(u64 v) {   // v: class N
-        a0.mac(v, d_qp.apow[0][k]);
-        a1.mac(v, d_qp.apow[1][k]);
+        a0.mac(v, ap0[k]);
+        a1.mac(v, ap1[k]);
         k++;
     }
 };
@@ -34,11 +35,11 @@ struct WeightedSink {  // folds constraint k into sum_c += v * alpha_c^(off + k)
 // warp time stalled on instruction fetch and 38% on a load-imbalance barrier; see profiles/.)
 // Sharding: a rank evaluates the `npts` leaves [j0, j0 + npts) (whole cosets).  Input columns are local (stride L = npts,
 // index j); xs / l0s are the full per-circuit tables (index j0 + j); `out` is the full-size [NC][OL] quotient-value buffer.
-__global__ void __launch_bounds__(256) k_quotient_perm(const u64* __restrict__ cs, const u64* __restrict__ wires,
+__global__ void __launch_bounds__(256) k_quotient_perm(const __grid_constant__ QuotientParams P, const u64* __restrict__ cs,
+                                                       const u64* __restrict__ wires,
                                                        const u64* __restrict__ zpp, const u64* __restrict__ xs,
                                                        const u64* __restrict__ l0s, u64* __restrict__ out_, int scale_now,
                                                        size_t L, size_t j0, size_t OL) {
-    const QuotientParams& P = d_qp;
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= L) return;
     u64* __restrict__ out = out_ + j0;
@@ -88,10 +89,9 @@ __global__ void __launch_bounds__(256) k_quotient_perm(const u64* __restrict__ c
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256) k_quotient_gate(const u64* __restrict__ cs, const u64* __restrict__ wires,
-                                                       u64* __restrict__ out_, int g, u32 op_lo, u32 op_hi, int scale_now,
-                                                       size_t L, size_t j0, size_t OL) {
-    const QuotientParams& P = d_qp;
+__global__ void __launch_bounds__(256) k_quotient_gate(const __grid_constant__ QuotientParams P, const u64* __restrict__ cs,
+                                                       const u64* __restrict__ wires, u64* __restrict__ out_, int g, u32 op_lo,
+                                                       u32 op_hi, int scale_now, size_t L, size_t j0, size_t OL) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= L) return;
     u64* __restrict__ out = out_ + j0;
@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(256) k_quotient_gate(const u64* __restrict__ c
     sink.a0.clear();
     sink.a1.clear();
     sink.k = sink.base = off;
+    sink.ap0 = P.apow[0];
+    sink.ap1 = P.apow[1];
     eval_gate_kind<KIND>(gd, op_lo, op_hi, wire, konst, P.pi_hash, sink);
     u64 a0 = gl_add(out[j], gl_mul(f, sink.a0.reduce()));
     u64 a1 = P.num_challenges > 1 ? gl_add(out[OL + j], gl_mul(f, sink.a1.reduce())) : 0;
@@ -129,11 +131,10 @@ struct StoreSink {  // stand-alone entry point: out[k][pt] += filter * constrain
     }
 };
 
-__global__ void __launch_bounds__(128) k_eval_gates(const u64* __restrict__ consts, const u64* __restrict__ wires, u64* out,
-                                                    size_t np) {
+__global__ void __launch_bounds__(128) k_eval_gates(const __grid_constant__ QuotientParams P, const u64* __restrict__ consts,
+                                                    const u64* __restrict__ wires, u64* out, size_t np) {
     size_t pt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pt >= np) return;
-    const QuotientParams& P = d_qp;
     auto wire = [&](int i) -> u64 { return wires[(size_t)i * np + pt]; };
     auto konst = [&](int i) -> u64 { return consts[(size_t)(P.num_selectors + i) * np + pt]; };
     const bool many = P.num_selectors > 1;
@@ -157,9 +158,6 @@ __global__ void k_points(u64* xs, u64* l0s, int logn, int rate_bits, u64 shift, 
 
 }  // namespace
 
-void quotient_upload_params(DevCtx* c, const QuotientParams& p) {
-    CUDA_CHECK(cudaMemcpyToSymbolAsync(d_qp, &p, sizeof(QuotientParams), 0, cudaMemcpyHostToDevice, c->stream));
-}
 
 void quotient_points(DevCtx* c, u64* d_xs, u64* d_l0s, int logn, int rate_bits, const u64* h_zh) {
     size_t L = (size_t)1 << (logn + rate_bits);
@@ -180,7 +178,7 @@ void quotient_eval(DevCtx* c, const QuotientParams& qp, const u64* d_cs, const u
     int last = -1;
     for (int g = 0; g < qp.num_gates; g++)
         if (qp.gates[g].num_constraints) last = g;
-    k_quotient_perm<<<grid, TH, 0, c->stream>>>(d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, last < 0, npts, j0, out_stride);
+    k_quotient_perm<<<grid, TH, 0, c->stream>>>(qp, d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, last < 0, npts, j0, out_stride);
     count_launch(c);
     for (int g = 0; g <= last; g++) {
         const GateDev& gd = qp.gates[g];
@@ -188,7 +186,7 @@ void quotient_eval(DevCtx* c, const QuotientParams& qp, const u64* d_cs, const u
         const u32 nops = gate_num_ops(gd.kind, gd.params);
         const int fin = g == last;
         switch (gd.kind) {
-#define P2G_LAUNCH(KIND) case KIND: k_quotient_gate<KIND><<<grid, TH, 0, c->stream>>>(d_cs, d_wires, d_out, g, 0, nops, fin, npts, j0, out_stride); break;
+#define P2G_LAUNCH(KIND) case KIND: k_quotient_gate<KIND><<<grid, TH, 0, c->stream>>>(qp, d_cs, d_wires, d_out, g, 0, nops, fin, npts, j0, out_stride); break;
             P2G_LAUNCH(P2G_GATE_CONSTANT) P2G_LAUNCH(P2G_GATE_PUBLIC_INPUT) P2G_LAUNCH(P2G_GATE_ARITHMETIC)
             P2G_LAUNCH(P2G_GATE_BASE_SUM) P2G_LAUNCH(P2G_GATE_POSEIDON) P2G_LAUNCH(P2G_GATE_RANDOM_ACCESS)
             P2G_LAUNCH(P2G_GATE_U32_ARITHMETIC) P2G_LAUNCH(P2G_GATE_U32_ADD_MANY) P2G_LAUNCH(P2G_GATE_U32_SUBTRACTION)
@@ -201,9 +199,9 @@ void quotient_eval(DevCtx* c, const QuotientParams& qp, const u64* d_cs, const u
     CUDA_CHECK(cudaGetLastError());
 }
 
-void gates_eval_standalone(DevCtx* c, const u64* d_consts, const u64* d_wires, u64* d_out, size_t npoints) {
+void gates_eval_standalone(DevCtx* c, const QuotientParams& qp, const u64* d_consts, const u64* d_wires, u64* d_out, size_t npoints) {
     const int TH = 128;
-    k_eval_gates<<<(unsigned)((npoints + TH - 1) / TH), TH, 0, c->stream>>>(d_consts, d_wires, d_out, npoints);
+    k_eval_gates<<<(unsigned)((npoints + TH - 1) / TH), TH, 0, c->stream>>>(qp, d_consts, d_wires, d_out, npoints);
     CUDA_CHECK(cudaGetLastError());
     count_launch(c);
 }

@@ -1,5 +1,5 @@
-// Parameters of the quotient / gate-evaluation kernels, uploaded to __constant__ memory once per proof (uniform,
-// broadcast reads: alpha powers, beta*k_i, gate table).
+// Parameters of the quotient / gate-evaluation kernels, passed to every launch as a __grid_constant__ kernel parameter
+// (constant bank: uniform, broadcast reads of alpha powers, beta*k_i, gate table).
 #pragma once
 #include "gates.cuh"
 
@@ -21,10 +21,9 @@ struct QuotientParams {
 
 
 struct DevCtx;
-void quotient_upload_params(DevCtx* c, const QuotientParams& p);
 void quotient_points(DevCtx* c, u64* d_xs, u64* d_l0s, int logn, int rate_bits, const u64* h_zh);
 // evaluates leaves [j0, j0 + npts) (whole cosets; column stride of the inputs = npts) into d_out[c * out_stride + j0 + j];
 // d_xs / d_l0s are the full tables
 void quotient_eval(DevCtx* c, const QuotientParams& qp, const u64* d_cs, const u64* d_wires, const u64* d_zpp, const u64* d_xs,
                    const u64* d_l0s, u64* d_out, size_t npts, size_t j0, size_t out_stride);
-void gates_eval_standalone(DevCtx* c, const u64* d_consts, const u64* d_wires, u64* d_out, size_t npoints);
+void gates_eval_standalone(DevCtx* c, const QuotientParams& qp, const u64* d_consts, const u64* d_wires, u64* d_out, size_t npoints);

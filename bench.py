@@ -34,6 +34,8 @@ def parse():
     ap.add_argument("--degree-bits", type=int, default=20)
     ap.add_argument("--workload", default="ecdsa")
     ap.add_argument("--hasher", default="keccak25")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="proofs in flight per GPU (one circuit handle + stream + host thread each); a step is still one proof")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-proof-across-N-GPUs measurement")
     ap.add_argument("--cpu-sample-bits", type=int, default=0, help="rows (log2) of the CPU-baseline sample; 0 = auto")
@@ -186,7 +188,10 @@ def main():
     cfg = p2g.CircuitConfig.wide_ecc_config(hasher=args.hasher)
     sc = p2g.synth.SyntheticCircuit(args.degree_bits, args.workload, config=cfg, num_public_inputs=4,
                                     seed=0xAC1D + 3 + 1000 * rank, pinned=True)
-    data = p2g.CircuitData(sc.common, sc.constants_sigmas, device=local_rank)   # circuit build: once, outside the timing
+    # circuit build: once, outside the timing.  `inflight` handles = proofs in flight on this GPU (own stream + host thread each)
+    F = max(1, args.inflight)
+    handles = [p2g.CircuitData(sc.common, sc.constants_sigmas, device=local_rank) for _ in range(F)]
+    data = handles[0]
     wires_host = sc._wires_t                                  # pinned host tensor (int64 bit pattern of canonical u64)
     wires_dev = wires_host.cuda(non_blocking=False)
     h2d_bytes = wires_host.numel() * 8
@@ -197,7 +202,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        outs = [fn() for _ in range(steps)]
+        outs = fn(steps)
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -209,21 +214,47 @@ def main():
             ms = float(t.item())
         return ms, outs
 
-    for _ in range(args.warmup):
-        data.prove(wires_dev, sc.public_inputs)
+    def prove_steps(w):
+        """steps -> list of proofs: `steps` proofs in total, spread over the F handles, each driven by its own host thread."""
+        def run(steps):
+            if F == 1:
+                return [data.prove(w, sc.public_inputs) for _ in range(steps)]
+            outs, errs = [[] for _ in range(F)], []
+
+            def work(i):
+                try:
+                    torch.cuda.set_device(local_rank)
+                    for _ in range(steps // F + (1 if i < steps % F else 0)):
+                        outs[i].append(handles[i].prove(w, sc.public_inputs))
+                except BaseException as e:  # noqa: BLE001
+                    errs.append(e)
+            ts = [threading.Thread(target=work, args=(i,)) for i in range(F)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errs:
+                raise errs[0]
+            return [o for lst in outs for o in lst]
+        return run
+
+    prove_steps(wires_dev)(args.warmup * F)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, outs = timed(lambda: data.prove(wires_dev, sc.public_inputs), args.steps)
-    for _ in range(min(args.warmup, 2)):
-        data.prove(wires_host, sc.public_inputs)
-    ms_e2e, outs_e2e = timed(lambda: data.prove(wires_host, sc.public_inputs), args.steps)
+    ms_dev, outs = timed(prove_steps(wires_dev), args.steps)
+    prove_steps(wires_host)(min(args.warmup, 2) * F)
+    ms_e2e, outs_e2e = timed(prove_steps(wires_host), args.steps)
+    # per-kernel / per-stage device timings (CUDA events on the library's stream): with several proofs in flight the stage
+    # events of one proof span kernels of the others, so they are taken from two proofs run alone right after the timed region
+    solo = [data.prove(wires_dev, sc.public_inputs) for _ in range(2)] if F > 1 else outs
     clocks = sampler.stop() if rank == 0 else None
 
     # one proof across all N GPUs (coset sharding + NCCL all-gathers, DESIGN.md section 6): latency of a single proof
     sharded = None
     if world > 1 and not args.no_sharded:
-        data.close()
+        for hd in handles:
+            hd.close()
         grp = p2g.sharding.TorchDistGroup(device=local_rank)
         sc0 = sc if rank == 0 else None
         if rank != 0:   # every rank proves the SAME circuit and witness
@@ -234,9 +265,9 @@ def main():
         wd = wh.cuda()
         for _ in range(args.warmup):
             sdata.prove(wd, sc0.public_inputs)
-        ms_sd, souts = timed(lambda: sdata.prove(wd, sc0.public_inputs), args.steps)
+        ms_sd, souts = timed(lambda k: [sdata.prove(wd, sc0.public_inputs) for _ in range(k)], args.steps)
         sdata.prove(wh, sc0.public_inputs)
-        ms_se, souts_e = timed(lambda: sdata.prove(wh, sc0.public_inputs), args.steps)
+        ms_se, souts_e = timed(lambda k: [sdata.prove(wh, sc0.public_inputs) for _ in range(k)], args.steps)
         digest = torch.tensor(list(__import__("hashlib").sha256(souts[0].to_bytes()).digest()), device="cuda", dtype=torch.int32)
         gathered = [torch.empty_like(digest) for _ in range(world)]
         dist.all_gather(gathered, digest)
@@ -251,8 +282,8 @@ def main():
 
     if rank == 0:
         K = args.steps
-        tms = [o.timings for o in outs]
-        mean = lambda k: sum(t[k] for t in tms) / K
+        tms = [o.timings for o in solo]
+        mean = lambda k: sum(t[k] for t in tms) / len(tms)
         hbm, src = peaks()
         leaf_gbs = sum(t["leaf_hash_bytes"] for t in tms) / 1e9 / (sum(t["leaf_hash_ms"] for t in tms) / 1e3)
         lde_gbs = sum(t["lde_bytes"] for t in tms) / 1e9 / (sum(t["lde_ms"] for t in tms) / 1e3)
@@ -260,7 +291,7 @@ def main():
         stages = {k: round(mean(k), 3) for k in ["wires_commit_ms", "zs_pp_ms", "quotient_ms", "openings_ms", "fri_ms", "d2h_ms",
                                                  "total_ms", "ntt_ms", "merkle_ms", "leaf_hash_ms", "lde_ms",
                                                  "quotient_kernel_ms"]}
-        launches = sum(t["kernel_launches"] for t in tms) + sum(o.timings["kernel_launches"] for o in outs_e2e)
+        launches = sum(o.timings["kernel_launches"] for o in outs) + sum(o.timings["kernel_launches"] for o in outs_e2e)
         proof_bytes = len(outs[0].to_bytes())
         line = {
             "metric": METRIC, "value": world * K / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": K,
@@ -269,7 +300,8 @@ def main():
             "config": {"workload": f"{args.workload}_2^{args.degree_bits}", "rows": 1 << args.degree_bits, "wires": cfg.num_wires,
                        "routed": cfg.num_routed_wires, "hasher": args.hasher, "rate_bits": cfg.rate_bits,
                        "gates": len(sc.common.gates), "gate_constraints": sc.common.num_gate_constraints,
-                       "fri_arity_bits": sc.common.reduction_arity_bits, "parallelism": f"{world} independent proofs (1 per GPU)",
+                       "fri_arity_bits": sc.common.reduction_arity_bits, "parallelism": f"{world} GPU(s) x {F} proofs in flight per GPU (independent witnesses per GPU)",
+                       "inflight_per_gpu": F,
                        "l2": "inputs larger than L2 (1.96 GB trace, 14.6 GB LDE per proof); no explicit flush",
                        "proof_bytes": proof_bytes},
             "e2e": {"value": world * K / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d_bytes,
@@ -282,7 +314,7 @@ def main():
             "ntt_roofline": {"kernel": "k_pass_strided/k_pass_contig (coset LDE passes)", "bound": "hbm", "achieved": lde_gbs,
                              "peak": hbm, "unit": "GB/s", "frac": lde_gbs / hbm, "all_ntt_gbs": ntt_gbs,
                              "algorithmic_bytes_per_step": tms[0]["ntt_bytes"]},
-            "stages_ms": stages,
+            "stages_ms": dict(stages, measured_on="one proof at a time (no overlap)" if F > 1 else "the timed region"),
             "clocks": clocks,
         }
         if sharded is not None:
@@ -298,7 +330,8 @@ def main():
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
     if sharded is None:
-        data.close()
+        for hd in handles:
+            hd.close()
     if world > 1:
         dist.destroy_process_group()
 
