@@ -314,21 +314,26 @@ class CircuitData:
     def __exit__(self, *exc):
         self.close()
 
-    def _run(self, fn, wires_ptr, public_inputs, forced_pow_witness, timings):
+    def _run(self, fn, wires_ptr, public_inputs, forced_pow_witness, timings, compressed=None):
         pis = np.array([int(x) for x in public_inputs], dtype=np.uint64)
         if self._out is None:
             self._out = C.create_string_buffer(_lib.lib().p2g_proof_size_bound(self._h))
         ln = C.c_size_t(len(self._out))
         fp = C.byref(C.c_uint64(forced_pow_witness)) if forced_pow_witness is not None else None
         tm = _lib.TimingsS() if timings else None
-        rc = fn(self._h, wires_ptr, pis.ctypes.data_as(C.c_void_p), len(pis), fp, self._out, C.byref(ln),
-                C.byref(tm) if timings else None)
+        if compressed is not None:   # compressed = 0 / 1: wires on host / device
+            rc = _lib.lib().p2g_prove_compressed(self._h, wires_ptr, compressed, pis.ctypes.data_as(C.c_void_p), len(pis), fp,
+                                                 self._out, C.byref(ln), C.byref(tm) if timings else None)
+        else:
+            rc = fn(self._h, wires_ptr, pis.ctypes.data_as(C.c_void_p), len(pis), fp, self._out, C.byref(ln),
+                    C.byref(tm) if timings else None)
         _lib.check(rc)
         return ProofWithPublicInputs(self._out.raw[:ln.value], [int(x) for x in pis], tm.as_dict() if timings else {})
 
-    def prove(self, wires, public_inputs=(), forced_pow_witness=None, timings=True):
+    def prove(self, wires, public_inputs=(), forced_pow_witness=None, timings=True, compressed=False):
         """`wires`: the full witness matrix (`MatrixWitness.wire_values`), shape [num_wires, N], canonical u64; a numpy
-        array (host; may be pinned) or a CUDA torch tensor on this circuit's device."""
+        array (host; may be pinned) or a CUDA torch tensor on this circuit's device.  compressed=True returns plonky2's
+        compressed layout -- what `proof.compress(..).to_bytes()` gives at prove_action.rs:77-78, the CLI's proof file."""
         shape = (self.common.config.num_wires, self.common.degree())
         if hasattr(wires, "is_cuda"):
             if tuple(wires.shape) != shape or not wires.is_contiguous() or wires.element_size() != 8:
@@ -336,11 +341,13 @@ class CircuitData:
             fn = _lib.lib().p2g_prove_device if wires.is_cuda else _lib.lib().p2g_prove
             if wires.is_cuda and wires.device.index != self.device:
                 raise ValueError("wires live on another device")
-            return self._run(fn, C.c_void_p(wires.data_ptr()), public_inputs, forced_pow_witness, timings)
+            return self._run(fn, C.c_void_p(wires.data_ptr()), public_inputs, forced_pow_witness, timings,
+                             (1 if wires.is_cuda else 0) if compressed else None)
         w = np.ascontiguousarray(wires, dtype=np.uint64)
         if w.shape != shape:
             raise ValueError(f"wires must have shape {shape}, got {w.shape}")
-        return self._run(_lib.lib().p2g_prove, w.ctypes.data_as(C.c_void_p), public_inputs, forced_pow_witness, timings)
+        return self._run(_lib.lib().p2g_prove, w.ctypes.data_as(C.c_void_p), public_inputs, forced_pow_witness, timings,
+                         0 if compressed else None)
 
     def read(self, what, dtype=np.uint64):
         """Intermediates of the last proof (enum p2g_buffer), for parity tests."""

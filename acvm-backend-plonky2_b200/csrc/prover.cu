@@ -708,7 +708,7 @@ extern "C" size_t p2g_proof_size_bound(const p2g_circuit* c) {
 // prove
 // =====================================================================================================================
 static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inputs, size_t n_pi, const u64* forced_pow,
-                       uint8_t* out, size_t* out_len, p2g_timings* tm, cudaEvent_t ev_start) {
+                       uint8_t* out, size_t* out_len, p2g_timings* tm, cudaEvent_t ev_start, bool compressed) {
     DevCtx* c = C->ctx;
     const p2g_circuit_desc& d = C->d;
     const size_t n = C->n, lde = C->lde;
@@ -1131,12 +1131,83 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         for (int i = 0; i < nq; i++) wb.e2v(op[o_q + i]);
     }
     for (auto& dg : C->fri_caps) wb.digest(dg, hs);
-    for (int q = 0; q < NQ; q++) {
-        for (int o = 0; o < 4 + nl; o++) {
-            size_t wdt = o < 4 ? (size_t)widths[o] : (size_t)2 * (1 << layers[o - 4].ab);
-            wb.put(h_rows.data() + row_off[o] + (size_t)q * wdt, 8 * wdt);
-            wb.u8v((uint8_t)path_len[o]);
-            for (int k = 0; k < path_len[o]; k++) wb.digest(h_paths[path_off[o] + (size_t)q * path_len[o] + k], hs);
+    if (!compressed) {
+        for (int q = 0; q < NQ; q++) {
+            for (int o = 0; o < 4 + nl; o++) {
+                size_t wdt = o < 4 ? (size_t)widths[o] : (size_t)2 * (1 << layers[o - 4].ab);
+                wb.put(h_rows.data() + row_off[o] + (size_t)q * wdt, 8 * wdt);
+                wb.u8v((uint8_t)path_len[o]);
+                for (int k = 0; k < path_len[o]; k++) wb.digest(h_paths[path_off[o] + (size_t)q * path_len[o] + k], hs);
+            }
+        }
+    } else {
+        // CompressedFriProof (plonky2 fri/proof.rs FriProof::compress + hash/path_compression.rs compress_merkle_proofs):
+        // query indices, then per DISTINCT index (ascending) the opened rows with the Merkle siblings no other opened path
+        // already determines, then per FRI layer per distinct coset index the evaluations minus the one the verifier infers.
+        for (int q = 0; q < NQ; q++) {
+            u32 ix = indices[q];
+            wb.put(&ix, 4);
+        }
+        // keep[o][q][k]: sibling k of query q's path in tree o is written
+        std::vector<std::vector<std::vector<char>>> keep(4 + nl);
+        std::vector<std::vector<u64>> tree_idx(4 + nl, std::vector<u64>(NQ));
+        {
+            int sh = 0;
+            for (int o = 0; o < 4 + nl; o++) {
+                if (o >= 4) sh += layers[o - 4].ab;
+                const int plen = path_len[o];
+                // node ids as in plonky2: (leaf + 2^H) >> j over the full tree of height H
+                std::map<u64, bool> kn;
+                const u64 nlv = (u64)1 << (o < 4 ? C->loglde : layers[o - 4].logcur - layers[o - 4].ab);
+                for (int q = 0; q < NQ; q++) {
+                    tree_idx[o][q] = (u64)indices[q] >> sh;
+                    for (int j = 0; j < plen; j++) kn[(tree_idx[o][q] + nlv) >> j] = true;
+                }
+                keep[o].assign(NQ, std::vector<char>(plen, 0));
+                for (int q = 0; q < NQ; q++) {
+                    u64 node = tree_idx[o][q] + nlv;
+                    for (int k = 0; k < plen; k++) {
+                        u64 sib = node ^ 1;
+                        if (!kn.count(sib)) {
+                            keep[o][q][k] = 1;
+                            kn[sib] = true;
+                        }
+                        node >>= 1;
+                    }
+                }
+            }
+        }
+        auto write_path = [&](int o, int q) {
+            int cnt = 0;
+            for (int k = 0; k < path_len[o]; k++) cnt += keep[o][q][k];
+            wb.u8v((uint8_t)cnt);
+            for (int k = 0; k < path_len[o]; k++)
+                if (keep[o][q][k]) wb.digest(h_paths[path_off[o] + (size_t)q * path_len[o] + k], hs);
+        };
+        {   // initial trees: first query of every distinct index, ascending
+            std::map<u64, int> first;
+            for (int q = NQ - 1; q >= 0; q--) first[indices[q]] = q;
+            for (auto& kv : first) {
+                const int q = kv.second;
+                for (int o = 0; o < 4; o++) {
+                    wb.put(h_rows.data() + row_off[o] + (size_t)q * widths[o], 8 * (size_t)widths[o]);
+                    write_path(o, q);
+                }
+            }
+        }
+        for (int l = 0; l < nl; l++) {
+            const int o = 4 + l, arity = 1 << layers[l].ab;
+            std::map<u64, int> first;
+            for (int q = NQ - 1; q >= 0; q--) first[tree_idx[o][q]] = q;
+            for (auto& kv : first) {
+                const int q = kv.second;
+                const u64 prev = l == 0 ? (u64)indices[q] : tree_idx[o - 1][q];
+                const int within = (int)(prev & (u64)(arity - 1));
+                const u64* ev = h_rows.data() + row_off[o] + (size_t)q * 2 * arity;
+                for (int i = 0; i < arity; i++)
+                    if (i != within) wb.put(ev + 2 * i, 16);
+                write_path(o, q);
+            }
         }
     }
     for (size_t i = 0; i < m; i++) {
@@ -1184,7 +1255,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
 }
 
 static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u64* public_inputs, size_t n_pi,
-                       const u64* forced_pow, uint8_t* out, size_t* out_len, p2g_timings* tm) {
+                       const u64* forced_pow, uint8_t* out, size_t* out_len, p2g_timings* tm, bool compressed = false) {
     return guard([&] {
         if (!C || !wires || !out_len || (n_pi && !public_inputs)) throw p2g_error(P2G_EBADARG, "p2g_prove: null argument");
         if (n_pi != C->d.num_public_inputs) throw p2g_error(P2G_EBADARG, "p2g_prove: public input count");
@@ -1261,7 +1332,7 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
             up.active = true;
             d_wires = C->wires_values.p;
         }
-        prove_impl(C, d_wires, public_inputs, n_pi, forced_pow, out, out_len, tm, ev_start);
+        prove_impl(C, d_wires, public_inputs, n_pi, forced_pow, out, out_len, tm, ev_start, compressed);
         up.active = false;
     });
 }
@@ -1269,6 +1340,14 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
 extern "C" int p2g_prove(p2g_circuit* c, const uint64_t* wires, const uint64_t* public_inputs, size_t num_public_inputs,
                          const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len, p2g_timings* timings) {
     return prove_entry(c, wires, false, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings);
+}
+// Same proof in plonky2's CompressedProofWithPublicInputs::to_bytes layout: exactly the bytes the reference CLI writes
+// (prove_action.rs:75-78: proof.compress(..).to_bytes()); `wires_on_device` selects a host or device trace pointer.
+extern "C" int p2g_prove_compressed(p2g_circuit* c, const uint64_t* wires, int wires_on_device, const uint64_t* public_inputs,
+                                    size_t num_public_inputs, const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len,
+                                    p2g_timings* timings) {
+    return prove_entry(c, wires, wires_on_device != 0, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings,
+                       true);
 }
 extern "C" int p2g_prove_device(p2g_circuit* c, const uint64_t* d_wires, const uint64_t* public_inputs, size_t num_public_inputs,
                                 const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len, p2g_timings* timings) {

@@ -161,6 +161,13 @@ int p2g_prove(p2g_circuit* c, const uint64_t* wires, const uint64_t* public_inpu
 int p2g_prove_device(p2g_circuit* c, const uint64_t* d_wires, const uint64_t* public_inputs, size_t num_public_inputs,
                      const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len, p2g_timings* timings);
 
+/* Same proof in plonky2's *compressed* layout, CompressedProofWithPublicInputs::to_bytes -- byte for byte what the reference
+ * CLI writes to the proof file (prove_action.rs:75-78 `proof.compress(..)`, `to_bytes()`; the committed golden proofs under
+ * example_programs/ are in this format).  Covers SURVEY 8(f) row f3.  wires_on_device: 0 = host pointer, 1 = device pointer. */
+int p2g_prove_compressed(p2g_circuit* c, const uint64_t* wires, int wires_on_device, const uint64_t* public_inputs,
+                         size_t num_public_inputs, const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len,
+                         p2g_timings* timings);
+
 size_t p2g_proof_size_bound(const p2g_circuit* c);
 
 /* ---- multi-GPU (one process per GPU): coset sharding, SURVEY 8(e) ----------------------------------------------

@@ -34,6 +34,8 @@ def test_golden_proofs_regenerated_on_gpu(p2g, corc, name):
         pr = proof.parse_uncompressed(pw.to_bytes(), cd)
         ch = verifier.verify(pr, cd, rec["cs_cap"])
         assert proof.serialize_compressed(proof.compress_proof(pr, ch.indices, cd)) == rec["raw"]
+        # the library's own compressed output IS the committed file (what the reference CLI wrote, prove_action.rs:75-78)
+        assert data.prove(w, cp.public_inputs, forced_pow_witness=cp.pow_witness, compressed=True).to_bytes() == rec["raw"]
         # and byte-for-byte against the oracle prover, including the deterministic proof-of-work search
         op = corc.OracleProver(cd, cs)
         assert pw.to_bytes() == op.prove(w, cp.public_inputs, forced_pow=cp.pow_witness)
@@ -72,6 +74,14 @@ def test_synthetic_proof_bytes_match_oracle(p2g, corc, degree_bits, workload, np
             assert np.array_equal(data.read(what), op.read(what)), what
         assert pw.to_bytes() == ref_bytes
         assert pw.timings["kernel_launches"] > 0 and pw.timings["total_ms"] > 0
+        # compressed layout (CompressedProofWithPublicInputs::to_bytes) against the oracle's compressor
+        from oracle.pyref import proof, verifier
+        cd = op.cd if hasattr(op, "cd") else None
+        if cd is not None:
+            pr = proof.parse_uncompressed(ref_bytes, cd)
+            ch = verifier.verify(pr, cd, cap, dg)
+            want = proof.serialize_compressed(proof.compress_proof(pr, ch.indices, cd))
+            assert data.prove(sc.wires, sc.public_inputs, compressed=True).to_bytes() == want
         # a second proof on the same handle (buffers reused) is identical: the prover is a pure function of its inputs
         assert data.prove(sc.wires, sc.public_inputs, timings=False).to_bytes() == ref_bytes
 
