@@ -282,6 +282,7 @@ extern "C" uint64_t p2g_host_gl_mul(uint64_t a, uint64_t b) { return gl_mul(a, b
 // op: 0 sub(a N, b<=p)  1 add(a N, b C)  2 mul  3 glz_mul  4 mul_small(a, (u32)b)  5 canon(a)  6 glz_reduce128(hi=a, lo=b)
 //     7 gl_acc dot product over groups of 8: out[i] = sum_k a[8i+k] b[8i+k]   (out has n/8 entries)
 //     8 gl_acc32: the same with 32-bit multipliers (u32)b
+//     9 glf_add(a C, b C)  10 glf_mul  11 glf_canon      (carry fixes on the FMA pipe)
 // Results of N-class ops are canonicalised before they are returned.
 GL_HD u64 field_op(int op, const u64* a, const u64* b, size_t i) {
     switch (op) {
@@ -304,6 +305,9 @@ GL_HD u64 field_op(int op, const u64* a, const u64* b, size_t i) {
         for (int k = 0; k < 8; k++) acc.mac(a[8 * i + k], (u32)b[8 * i + k]);
         return acc.reduce();
     }
+    case 9: return glf_add(a[i], b[i]);
+    case 10: return glf_mul(a[i], b[i]);
+    case 11: return glf_canon(a[i]);
     default: return 0;
     }
 }
@@ -315,8 +319,8 @@ __global__ void k_field_ops(int op, const u64* a, const u64* b, u64* out, size_t
 }  // namespace
 extern "C" int p2g_test_field_ops(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, int device) {
     return guard([&] {
-        if (!a || !b || !out || op < 0 || op > 8) throw p2g_error(P2G_EBADARG, "p2g_test_field_ops: bad argument");
-        size_t nout = op >= 7 ? n / 8 : n;
+        if (!a || !b || !out || op < 0 || op > 11) throw p2g_error(P2G_EBADARG, "p2g_test_field_ops: bad argument");
+        size_t nout = (op == 7 || op == 8) ? n / 8 : n;
         if (!nout) return;
         if (device < 0) {  // host twin
             for (size_t i = 0; i < nout; i++) out[i] = field_op(op, a, b, i);

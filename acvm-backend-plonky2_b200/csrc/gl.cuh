@@ -126,6 +126,84 @@ GL_HD u64 glz_mul_small(u64 a, u32 s) {
 }
 GL_HD u64 gl_mul_small(u64 a, u32 s) { return gl_canon(glz_mul_small(a, s)); }
 
+// ---- "f" forms: the same functions with the carry corrections issued on the FMA pipe ------------------------------------
+// The integer ALU pipe (IADD3 / LOP3 / SEL, 64 lanes/clk/SM) is what the NTT butterflies saturate (ncu: 76% ALU, 25% FMA);
+// x + m * eps with m in {0, 1} is one IMAD.WIDE.U32 on the other pipe instead of a negate + two carry adds.  eps comes from
+// constant memory so that ptxas keeps the multiply form instead of strength-reducing it back to adds.
+#if defined(__CUDACC__)
+static __constant__ u32 d_gl_eps = 0xFFFFFFFFu;
+#endif
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ u64 glf_fix(u64 x, u32 m) {   // x + m * eps (mod 2^64), m in {0, 1}
+    u64 r;
+    asm("{\n\t.reg .u32 x0, x1;\n\t"
+        "mov.b64 {x0, x1}, %3;\n\t"
+        "mad.lo.cc.u32 x0, %1, %2, x0;\n\t"
+        "madc.hi.u32 x1, %1, %2, x1;\n\t"
+        "mov.b64 %0, {x0, x1};\n\t}"
+        : "=l"(r) : "r"(m), "r"(d_gl_eps), "l"(x));
+    return r;
+}
+#endif
+// x: N -> C        (x >= p  <=>  x + eps carries;  x - p = x + eps mod 2^64)
+GL_HD u64 glf_canon(u64 x) {
+#if defined(__CUDA_ARCH__)
+    u32 m;
+    asm("{\n\t.reg .u64 y;\n\tadd.cc.u64 y, %1, 0xffffffff;\n\taddc.u32 %0, 0, 0;\n\t}" : "=r"(m) : "l"(x));
+    return glf_fix(x, m);
+#else
+    return gl_canon(x);
+#endif
+}
+// a, b: C -> C     (s = a + b carries, or s >= p: never both; either way the result is s + eps mod 2^64)
+GL_HD u64 glf_add(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    u64 s;
+    u32 c;
+    asm("{\n\t.reg .u64 y;\n\t"
+        "add.cc.u64 %0, %2, %3;\n\t"
+        "addc.u32 %1, 0, 0;\n\t"
+        "add.cc.u64 y, %0, 0xffffffff;\n\t"
+        "addc.u32 %1, %1, 0;\n\t}"
+        : "=&l"(s), "=&r"(c) : "l"(a), "l"(b));
+    return glf_fix(s, c);
+#else
+    return gl_add(a, b);
+#endif
+}
+// a, b: N -> C
+GL_HD u64 glf_mul(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), r0, r1, r2, r3;
+    asm("{\n\t"
+        "mul.lo.u32 %0, %4, %6;\n\t"
+        "mul.hi.u32 %1, %4, %6;\n\t"
+        "mul.lo.u32 %2, %5, %7;\n\t"
+        "mul.hi.u32 %3, %5, %7;\n\t"
+        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
+        "madc.hi.cc.u32 %2, %4, %7, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    // t = lo - r3 (borrow => - eps), x = t + r2 * eps (one IMAD.WIDE with carry out), + carry * eps, canonicalise
+    u64 t = gl_sub(((u64)r1 << 32) | r0, (u64)r3), x;
+    u32 m;
+    asm("{\n\t.reg .u32 x0, x1, t0, t1;\n\t"
+        "mov.b64 {t0, t1}, %2;\n\t"
+        "mad.lo.cc.u32 x0, %3, %4, t0;\n\t"
+        "madc.hi.cc.u32 x1, %3, %4, t1;\n\t"
+        "addc.u32 %1, 0, 0;\n\t"
+        "mov.b64 %0, {x0, x1};\n\t}"
+        : "=l"(x), "=r"(m) : "l"(t), "r"(r2), "r"(d_gl_eps));
+    return glf_canon(glf_fix(x, m));
+#else
+    return gl_mul(a, b);
+#endif
+}
+
 // Sum of products with ONE reduction at the end: acc += a * b for a, b: N.  The 128-bit products are accumulated exactly --
 // even limbs (a0 b0 + a1 b1 2^64) in `e`, cross terms (a0 b1 + a1 b0) in `o` -- so on the device each term costs 4
 // IMAD.WIDE.U32 and 3 carry adds and no modular reduction.  Holds up to 2^31 terms.

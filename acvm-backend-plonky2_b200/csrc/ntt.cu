@@ -124,13 +124,13 @@ __device__ __forceinline__ void reg_round(u64* __restrict__ sm, const u64* __res
                 for (int g = 0; g < (1 << R); g += 2 * h) {
                     u64 u = x[g + kk], v = x[g + kk + h];
                     if (INV) {
-                        if (!unit) v = gl_mul(v, w);
-                        x[g + kk] = gl_add(u, v);
+                        if (!unit) v = glf_mul(v, w);
+                        x[g + kk] = glf_add(u, v);
                         x[g + kk + h] = gl_sub(u, v);
                     } else {
-                        x[g + kk] = gl_add(u, v);
+                        x[g + kk] = glf_add(u, v);
                         v = gl_sub(u, v);
-                        x[g + kk + h] = unit ? v : gl_mul(v, w);
+                        x[g + kk + h] = unit ? v : glf_mul(v, w);
                     }
                 }
             }

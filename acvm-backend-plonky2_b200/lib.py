@@ -189,7 +189,7 @@ def keccak256(msgs, device=0):
     return out
 
 
-FIELD_OPS = {"sub": 0, "add": 1, "mul": 2, "mulz": 3, "mul_small": 4, "canon": 5, "reduce128": 6, "dot8": 7, "dot8_small": 8}
+FIELD_OPS = {"sub": 0, "add": 1, "mul": 2, "mulz": 3, "mul_small": 4, "canon": 5, "reduce128": 6, "dot8": 7, "dot8_small": 8, "addf": 9, "mulf": 10, "canonf": 11}
 
 
 def field_ops(op, a, b, device=0):

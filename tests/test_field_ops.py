@@ -43,7 +43,8 @@ def operands(seed, canonical_b, nrand=20000):
 CASES = [("sub", "le_p", lambda a, b: (a - b) % P), ("add", "lt_p", lambda a, b: (a + b) % P),
          ("mul", None, lambda a, b: a * b % P), ("mulz", None, lambda a, b: a * b % P),
          ("mul_small", "u32", lambda a, b: a * b % P), ("canon", None, lambda a, b: a % P),
-         ("reduce128", None, lambda a, b: ((a << 64) + b) % P)]
+         ("reduce128", None, lambda a, b: ((a << 64) + b) % P),
+         ("mulf", None, lambda a, b: a * b % P), ("canonf", None, lambda a, b: a % P)]
 
 
 def run(p2g, device):
@@ -53,6 +54,12 @@ def run(p2g, device):
         want = np.array([ref(int(x), int(y)) for x, y in zip(a.tolist(), b.tolist())], dtype=np.uint64)
         bad = np.nonzero(got != want)[0]
         assert bad.size == 0, (op, hex(int(a[bad[0]])), hex(int(b[bad[0]])), hex(int(got[bad[0]])), hex(int(want[bad[0]])))
+    # glf_add takes two canonical operands
+    a, b = operands(55, "lt_p")
+    a = np.where(a >= np.uint64(P), a - np.uint64(P), a)
+    got = p2g.lib.field_ops("addf", a, b, device=device)
+    want = np.array([(int(x) + int(y)) % P for x, y in zip(a.tolist(), b.tolist())], dtype=np.uint64)
+    assert np.array_equal(got, want)
     # dot products with one final reduction: groups of 8 arbitrary u64 pairs, incl. all-ones (largest carries)
     a, b = operands(7, None)
     a[:64], b[:64] = np.uint64(M64), np.uint64(M64)
