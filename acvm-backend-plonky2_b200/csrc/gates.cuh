@@ -263,8 +263,7 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
             u64 initial = gl_sub(gl_sub(w(q), w(q + 1)), w(q + 2));
             u64 res = w(q + 3), bout = w(q + 4);
             sink.emit(gl_sub(res, gl_add(initial, gl_mul(bout, 1ULL << 32))));
-            gl_acc32 comb;
-            comb.clear();
+            u64 comb = 0;
             const u32 lw = 5 * ops + 16 * i;
 #pragma unroll 1
             for (int b = 1; b >= 0; b--) {   // two batches of 8 independent loads
@@ -274,10 +273,10 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
 #pragma unroll
                 for (int j = 7; j >= 0; j--) {
                     sink.emit(limb4_check(L[j]));
-                    comb.mac(L[j], 1u << (16 * b + 2 * j));
+                    comb = gl_add(glz_mul_small(comb, 4), L[j]);   // N + C -> N  (fewer live registers than gl_acc32 here)
                 }
             }
-            sink.emit(gl_sub(comb.reduce(), res));
+            sink.emit(gl_sub(comb, res));
             sink.emit(glz_mul(bout, gl_sub(1, bout)));
         }
         break;

@@ -55,28 +55,44 @@ __global__ void __launch_bounds__(256) k_quotient_perm(const __grid_constant__ Q
     gl_acc acc0, acc1;   // the two alpha-weighted sums, one reduction each at the end
     acc0.clear();
     acc1.clear();
+    // Both challenges in one sweep: every wire / sigma column value is loaded once and feeds the running products of
+    // challenge 0 and challenge 1 (ncu: the two-sweep version read 23 GB for 11.6 GB of columns).
+    u64 prev[2], pn[2], pd[2];
     for (int c = 0; c < NC; c++) {
-        u64 prev = zpp[(size_t)c * L + j];
-        {   // L_0(x) (Z_c(x) - 1)
-            u64 tz = glz_mul(l0, gl_sub(prev, 1));
-            acc0.mac(tz, P.apow[0][c]);
-            acc1.mac(tz, P.apow[1][c]);
-        }
-        const u64 gamma = P.gammas[c], beta = P.betas[c];
-        const int term = NC + c * (NPP + 1);
-        for (int m = 0; m <= NPP; m++) {
-            u64 pn = 1, pd = 1;
-            int hi = min((m + 1) * chunk, R);
-            for (int r = m * chunk; r < hi; r++) {
-                u64 base = gl_add(wires[(size_t)r * L + j], gamma);
-                pn = glz_mul(pn, gl_add(base, gl_mul(P.beta_k[c][r], x)));
-                pd = glz_mul(pd, gl_add(base, gl_mul(beta, cs[(size_t)(C + r) * L + j])));
+        prev[c] = zpp[(size_t)c * L + j];
+        u64 tz = glz_mul(l0, gl_sub(prev[c], 1));   // L_0(x) (Z_c(x) - 1)
+        acc0.mac(tz, P.apow[0][c]);
+        acc1.mac(tz, P.apow[1][c]);
+    }
+    for (int m = 0; m <= NPP; m++) {
+        pn[0] = pn[1] = pd[0] = pd[1] = 1;
+        const int lo = m * chunk, hi = min((m + 1) * chunk, R);
+        for (int r0 = lo; r0 < hi; r0 += 4) {   // batches of 4 + 4 independent loads
+            u64 wv[4], sv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                wv[i] = (r0 + i < hi) ? wires[(size_t)(r0 + i) * L + j] : 0;
+                sv[i] = (r0 + i < hi) ? cs[(size_t)(C + r0 + i) * L + j] : 0;
             }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int r = r0 + i;
+                if (r < hi) {
+                    for (int c = 0; c < NC; c++) {
+                        u64 base = gl_add(wv[i], P.gammas[c]);
+                        pn[c] = glz_mul(pn[c], gl_add(base, gl_mul(P.beta_k[c][r], x)));
+                        pd[c] = glz_mul(pd[c], gl_add(base, gl_mul(P.betas[c], sv[i])));
+                    }
+                }
+            }
+        }
+        for (int c = 0; c < NC; c++) {
+            const int term = NC + c * (NPP + 1);
             u64 next = (m < NPP) ? zpp[(size_t)(NC + c * NPP + m) * L + j] : zpp[(size_t)c * L + jn];
-            u64 tv = gl_sub(glz_mul(prev, pn), gl_mul(next, pd));
+            u64 tv = gl_sub(glz_mul(prev[c], pn[c]), gl_mul(next, pd[c]));
             acc0.mac(tv, P.apow[0][term + m]);
             acc1.mac(tv, P.apow[1][term + m]);
-            prev = next;
+            prev[c] = next;
         }
     }
     out[j] = acc0.reduce();
