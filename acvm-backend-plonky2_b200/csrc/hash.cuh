@@ -178,6 +178,46 @@ GL_HD u64 poseidon_sbox(u64 x) {
 GL_HD void poseidon_mds(u64 (&s)[12]) {
     const u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
     u64 r[12];
+#if defined(__CUDA_ARCH__)
+    // sm_100a: 32 x 32 -> 64 multiplies (IMAD.WIDE) issue at a quarter of the 32-bit IMAD rate, so the state is cut into
+    // 22 + 21 + 21-bit limbs: every row sum of limb x coefficient stays below 2^22 * 284 < 2^31 and is a chain of plain 32-bit
+    // multiply-adds (3 per term instead of 2 wide ones); the three limb sums are recombined exactly and reduced once.
+    u32 l0[12], l1[12], l2[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        l0[i] = (u32)s[i] & 0x3FFFFFu;
+        l1[i] = (u32)(s[i] >> 22) & 0x1FFFFFu;
+        l2[i] = (u32)(s[i] >> 43);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        u32 s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            const int k = (i + j) % 12;
+            s0 += l0[k] * CIRC[j];
+            s1 += l1[k] * CIRC[j];
+            s2 += l2[k] * CIRC[j];
+        }
+        if (i == 0) {
+            s0 += l0[0] * 8;
+            s1 += l1[0] * 8;
+            s2 += l2[0] * 8;
+        }
+        // value = s0 + s1 2^22 + s2 2^43  (< 2^74)
+        u64 t = (u64)s0 + ((u64)s1 << 22);   // < 2^54
+        u64 u = (u64)s2 << 43;               // low 64 bits of s2 2^43
+        u64 lo = t + u;
+        u32 hi = (s2 >> 21) + (lo < u);      // multiples of 2^64, < 2^11
+        u64 he = ((u64)hi << 32) - hi;       // hi * eps < 2^43
+        u64 v = lo + he;
+        if (v < he) v += GL_EPS;
+        r[i] = gl_canon(v);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = r[i];
+    return;
+#endif
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         u64 lo = 0, hi = 0;
