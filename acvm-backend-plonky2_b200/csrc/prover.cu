@@ -299,6 +299,16 @@ __global__ void k_pow_search(challenger_t base, u64 start, u64 count, int pow_bi
     if (pow_bits == 0 || (r >> (64 - pow_bits)) == 0) atomicMin(best, (unsigned long long)(start + t));
 }
 
+// the ABI requires canonical field elements (the reference hands over F::to_canonical_u64); a value >= p would silently
+// change the committed polynomial, so the trace is checked on the device (one streaming read, ~0.4 ms at 2^20 rows)
+__global__ void k_check_canonical(const u64* __restrict__ v, size_t count, int* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < count; i += stride) bad |= v[i] >= GL_P;
+    if (bad) *flag = 1;
+}
+
 // query phase gathers
 __global__ void k_gather_rows(const u64* __restrict__ lde, size_t cs, int ncols, const u32* __restrict__ idx, int nq,
                               u64* __restrict__ out) {
@@ -374,6 +384,7 @@ struct p2g_circuit {
         dbuf<e2> partial, apow;
         dbuf<unsigned long long> best;
         dbuf<u32> idx;
+        dbuf<int> flag;
         dbuf<digest_t> paths;
         std::vector<FriLayer> layers;
     } ws;
@@ -735,7 +746,26 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
 
     // 2. wires commitment
     commit_from_values(C, C->wires, d_wires, n, C->up.active ? &C->up : nullptr);
-    std::vector<digest_t> wires_cap = read_cap(C, C->wires.tree);
+    int bad_wire = 0;
+    {
+        // every column this rank reads: its inverse-NTT block and the routed columns (all of them on a single GPU)
+        struct { int* p; } flag = {ensure(C->ws.flag, 1)};
+        CUDA_CHECK(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+        if (C->up.active && C->up.routed) CUDA_CHECK(cudaStreamWaitEvent(st, C->up.routed, 0));
+        int c0, c1;
+        column_block(C, W, &c0, &c1);
+        const int ranges[3][2] = {{c0, c1}, {0, std::min(c0, R)}, {std::max(c1, 0), std::max(c1, R)}};
+        for (auto& rg : ranges) {
+            if (rg[1] <= rg[0]) continue;
+            size_t cnt = (size_t)(rg[1] - rg[0]) * n;
+            unsigned blocks = (unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 16);
+            k_check_canonical<<<blocks, 256, 0, st>>>(d_wires + (size_t)rg[0] * n, cnt, flag.p);
+            count_launch(c);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(&bad_wire, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<digest_t> wires_cap = read_cap(C, C->wires.tree);   // synchronises the stream
+    if (bad_wire) throw p2g_error(P2G_EBADARG, "p2g_prove: non-canonical wire value (>= p)");
     CUDA_CHECK(cudaEventRecord(ev[1], st));
     tr.mark("wires commit");
 

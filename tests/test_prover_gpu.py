@@ -135,6 +135,12 @@ def test_error_codes(p2g):
         assert ei.value.code == p2g.lib.P2G_EBADARG
         with pytest.raises(ValueError):
             data.prove(sc.wires[:, :8])
+        w = sc.wires.copy()
+        w[7, 3] = 0xFFFFFFFF00000001 + 5      # non-canonical wire value: refused, not silently reduced
+        with pytest.raises(p2g.P2GError) as ei:
+            data.prove(w, sc.public_inputs)
+        assert ei.value.code == p2g.lib.P2G_EBADARG
+        assert data.prove(sc.wires, sc.public_inputs).to_bytes()       # the handle stays usable after an error
 
 
 @pytest.mark.parametrize("workload,wires", [("all_gates", 234), ("ecdsa", 234), ("all_gates", 136)])
@@ -166,6 +172,22 @@ def test_gate_constraints_vanish_on_valid_rows(p2g):
     pi_hash = PoseidonHash.hash_no_pad_elems(sc.public_inputs)
     out = p2g.circuit.eval_gate_constraints(com, consts, sc.wires, pi_hash)
     assert not out.any()
+
+
+def test_sharded_full_size_2_20_matches_single_gpu(p2g):
+    """BASELINE headline size through the coset-sharded path (2 ranks as threads on this GPU): same bytes as one GPU."""
+    sc = p2g.synth.SyntheticCircuit(20, "ecdsa", num_public_inputs=4, seed=0xAC1D + 3)
+    with p2g.CircuitData(sc.common, sc.constants_sigmas) as data:
+        want = data.prove(sc.wires, sc.public_inputs, timings=False).to_bytes()
+        cap = data.constants_sigmas_cap
+    group = p2g.sharding.ThreadGroup(2)
+
+    def rank_main(rank, member):
+        with p2g.CircuitData(sc.common, sc.constants_sigmas, device=0, shard=member) as d:
+            assert d.constants_sigmas_cap == cap
+            return d.prove(sc.wires, sc.public_inputs, timings=False).to_bytes()
+    for got in group.run(rank_main):
+        assert got == want
 
 
 def test_full_size_2_20_properties(p2g):
