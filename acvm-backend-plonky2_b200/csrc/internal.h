@@ -77,6 +77,7 @@ struct DevCtx {
 
     const u64* get_tw(int log, bool inverse);
     const u64* get_twist(int logB, bool inverse, int* split);
+    const u64* get_twist_full(int logB, int loga, bool inverse);   // omega_B^{+-q bitrev_a(m)} at [(m << logS) + q]
     const u64* get_powtab(int logn, u64 base, u64 premul, int* split);
     // the 2^rate_bits per-coset index-power tables of an LDE: table z = [lo | hi] powers of shift * omega_{N 2^rate}^{bitrev(z)}
     const u64* get_coset_tabs(int logn, int rate_bits, u64 shift, int* split, size_t* tab_len);

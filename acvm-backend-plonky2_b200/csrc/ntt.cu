@@ -32,8 +32,9 @@ struct PassArgs {
     int loga;                  // sub-transform length A
     int logq;                  // strided: tile width Q; contiguous: log2(blocks per tile)
     const u64* tw;             // stage-major twiddles of size A: stage u at offset A - (A >> u), (A >> (u+1)) entries
-    const u64* twist;          // [lo 2^split | hi] of omega_B^{+-k}, or null
-    int twist_split;
+    const u64* twist;          // full inter-pass twist table of the block: twist[(m << logS) + q] = omega_B^{+-q bitrev_a(m)}, or null
+    int twist_split;           // (unused with full tables)
+    int stab_full;             // stab is a full table of 2^logn entries per coset (forward LDE) instead of a [lo | hi] pair
     const u64* stab;           // [lo 2^split | hi] index-power table applied on load (forward) / store (inverse), or null
     int stab_split;
     size_t stab_zs;            // per-coset table stride
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_strided(PassArg
         int qq = e & (Q - 1), m = e >> a.logq;
         size_t idx = base + ((size_t)m << logS) + qq;
         u64 v = in[idx];
-        if (!INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
-        if (INV && a.twist) v = gl_mul(v, tab_pow(a.twist, a.twist_split, (q0 + qq) * bitrev32(m, a.loga)));
+        if (!INV && stab) v = glf_mul(v, a.stab_full ? __ldg(stab + idx) : tab_pow(stab, a.stab_split, (u32)idx));
+        if (INV && a.twist) v = glf_mul(v, __ldg(a.twist + (((size_t)m << logS) + q0 + qq)));
         sm[phys(e)] = v;
     }
     stage_tw_end(A, mbar);
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_strided(PassArg
         int qq = e & (Q - 1), m = e >> a.logq;
         size_t idx = base + ((size_t)m << logS) + qq;
         u64 v = sm[phys(e)];
-        if (!INV && a.twist) v = gl_mul(v, tab_pow(a.twist, a.twist_split, (q0 + qq) * bitrev32(m, a.loga)));
-        if (INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
+        if (!INV && a.twist) v = glf_mul(v, __ldg(a.twist + (((size_t)m << logS) + q0 + qq)));
+        if (INV && stab) v = glf_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
         if (a.scale != 1) v = gl_mul(v, a.scale);
         out[idx] = v;
     }
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_contig(PassArgs
         for (int e = threadIdx.x; e < total; e += blockDim.x) {
             size_t idx = ((size_t)c0 << a.loga) + e;
             u64 v = in[idx];
-            if (!INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
+            if (!INV && stab) v = glf_mul(v, a.stab_full ? __ldg(stab + idx) : tab_pow(stab, a.stab_split, (u32)idx));
             sm[phys(e)] = v;
         }
     }
@@ -252,6 +253,14 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_contig(PassArgs
 __global__ void k_fill_pow(u64* out, u32 n, u64 base, u64 step, u64 premul) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = gl_mul(premul, gl_pow(base, (u64)i * step));
+}
+// full twist table of a strided pass: out[(m << logS) + q] = root^(q * bitrev_a(m)), root = omega_B^{+-1}
+__global__ void k_fill_twist(u64* out, int logB, int loga, u64 root) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << logB)) return;
+    const int logS = logB - loga;
+    u32 m = (u32)(i >> logS), q = (u32)(i & (((size_t)1 << logS) - 1));
+    out[i] = gl_pow(root, (u64)q * bitrev32(m, loga));
 }
 // stage-major twiddle tile of size A = 2^loga: stage u holds root^(j << u), j < A >> (u+1)
 __global__ void k_fill_tw(u64* out, int loga, u64 root) {
@@ -345,6 +354,7 @@ struct XformDesc {
     const u64* stab;
     int stab_split;
     size_t stab_zs;
+    int stab_full;
     u64 scale;
     bool natural_input;  // inverse only
 };
@@ -370,12 +380,13 @@ void run_forward(DevCtx* c, const XformDesc& d) {
             a.stab = d.stab;
             a.stab_split = d.stab_split;
             a.stab_zs = d.stab_zs;
+            a.stab_full = d.stab_full;
         }
         if (!last) {
             a.logB = d.logn - done;
             int logS = a.logB - a.loga;
             a.logq = std::min(logS, std::max(3, ntt_tile_log() - a.loga));
-            a.twist = c->get_twist(a.logB, false, &a.twist_split);
+            a.twist = c->get_twist_full(a.logB, a.loga, false);
             size_t tiles = (size_t)1 << (d.logn - a.loga - a.logq);
             a.nz = d.nz;
             dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
@@ -437,7 +448,7 @@ void run_inverse(DevCtx* c, const XformDesc& d) {
             a.logB = done + a.loga;
             int logS = a.logB - a.loga;
             a.logq = std::min(logS, std::max(3, ntt_tile_log() - a.loga));
-            a.twist = c->get_twist(a.logB, true, &a.twist_split);
+            a.twist = c->get_twist_full(a.logB, a.loga, true);
             size_t tiles = (size_t)1 << (d.logn - a.loga - a.logq);
             a.nz = d.nz;
             dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
@@ -496,6 +507,23 @@ const u64* DevCtx::get_twist(int logB, bool inverse, int* split) {
     return p;
 }
 
+const u64* DevCtx::get_twist_full(int logB, int loga, bool inverse) {
+    if (parent) return parent->get_twist_full(logB, loga, inverse);
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(logB * 64 + loga, (int)inverse + 2);   // shares the `twist` map with the two-level tables
+    auto it = twist.find(key);
+    if (it != twist.end()) return it->second.p;
+    dbuf<u64> t((size_t)1 << logB);
+    u64 root = gl_root_of_unity(logB);
+    if (inverse) root = gl_inv(root);
+    k_fill_twist<<<(unsigned)((((size_t)1 << logB) + 255) / 256), 256, 0, stream>>>(t.p, logB, loga, root);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    const u64* p = t.p;
+    twist.emplace(key, std::move(t));
+    return p;
+}
+
 const u64* DevCtx::get_powtab(int logn, u64 base, u64 premul, int* split) {
     if (parent) return parent->get_powtab(logn, base, premul, split);
     std::lock_guard<std::mutex> lk(mu);
@@ -517,11 +545,11 @@ const u64* DevCtx::get_powtab(int logn, u64 base, u64 premul, int* split) {
 
 const u64* DevCtx::get_coset_tabs(int logn, int rate_bits, u64 shift, int* split_out, size_t* tab_len_out) {
     if (parent) return parent->get_coset_tabs(logn, rate_bits, shift, split_out, tab_len_out);
-    // coset z covers leaves [z*N, (z+1)*N) = shift * omega_{N*nz}^{bitrev(z)} * <omega_N>
+    // coset z covers leaves [z*N, (z+1)*N) = shift * omega_{N*nz}^{bitrev(z)} * <omega_N>; table z holds s_z^i for every i < N
+    // (one load + one multiply per element in the first LDE pass; 8 N words per LDE shape, 64 MB at N = 2^20)
     const int nz = 1 << rate_bits;
-    const int split = (logn + 1) / 2;
-    const size_t tab_len = ((size_t)1 << split) + ((size_t)1 << (logn - split));
-    *split_out = split;
+    const size_t tab_len = (size_t)1 << logn;
+    *split_out = 0;
     *tab_len_out = tab_len;
     std::lock_guard<std::mutex> lk(mu);
     auto key = std::make_tuple(logn + 64 * (rate_bits + 1), shift, (u64)0);
@@ -531,9 +559,7 @@ const u64* DevCtx::get_coset_tabs(int logn, int rate_bits, u64 shift, int* split
         dbuf<u64> t(tab_len * nz);
         for (int z = 0; z < nz; z++) {
             u64 s = gl_mul(shift, gl_pow(wl, bitrev32((u32)z, rate_bits)));
-            u32 nlo = 1u << split, nhi = 1u << (logn - split);
-            k_fill_pow<<<(nlo + 255) / 256, 256, 0, stream>>>(t.p + z * tab_len, nlo, s, 1, 1);
-            k_fill_pow<<<(nhi + 255) / 256, 256, 0, stream>>>(t.p + z * tab_len + nlo, nhi, s, (u64)nlo, 1);
+            k_fill_pow<<<(unsigned)((tab_len + 255) / 256), 256, 0, stream>>>(t.p + z * tab_len, (u32)tab_len, s, 1, 1);
         }
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -592,6 +618,7 @@ void ntt_lde(DevCtx* c, const u64* d_coeffs, size_t in_cs, u64* d_lde, size_t ou
     d.stab = tabs + (size_t)z0 * tab_len;
     d.stab_split = split;
     d.stab_zs = tab_len;
+    d.stab_full = 1;
     d.scale = 1;
     if (logn == 0) {
         // constant polynomials: every coset value equals the coefficient
