@@ -137,6 +137,8 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port, OpenMP, all host threads) on a bounded sample."""
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host thread
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from __graft_entry__ import load_product
     p2g = load_product()
     bits = pick_cpu_sample_bits(p2g, args)
