@@ -40,7 +40,8 @@ struct PassArgs {
     size_t stab_zs;            // per-coset table stride
     u64 scale;                 // constant multiplier on store (1 = none)
     int gather;                // contiguous inverse pass: input is in natural order, gather bit-reversed runs
-    u32 nz;                    // cosets per tile (grid.x = tiles * nz)
+    u32 nz;                    // cosets per tile
+    int col_fast;              // grid = (columns, tiles * nz): the columns of one (tile, coset) are adjacent in launch order
 };
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -174,12 +175,13 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_strided(PassArg
     const int total = A << a.logq;
     u64* s_tw = sm + tile_words(total);
     u64* mbar = s_tw + A;
-    const u32 z = blockIdx.x % a.nz, tile = blockIdx.x / a.nz;
+    const u32 col = a.col_fast ? blockIdx.x : blockIdx.y, tz = a.col_fast ? blockIdx.y : blockIdx.x;
+    const u32 z = tz % a.nz, tile = tz / a.nz;
     const u32 tiles_per_blk = 1u << (logS - a.logq);
     const u32 blk = tile / tiles_per_blk;
     const u32 q0 = (tile % tiles_per_blk) << a.logq;
-    const u64* in = a.in + (size_t)blockIdx.y * a.in_cs + (size_t)z * a.in_zs;
-    u64* out = a.out + (size_t)blockIdx.y * a.out_cs + (size_t)z * a.out_zs;
+    const u64* in = a.in + (size_t)col * a.in_cs + (size_t)z * a.in_zs;
+    u64* out = a.out + (size_t)col * a.out_cs + (size_t)z * a.out_zs;
     const u64* stab = a.stab ? a.stab + (size_t)z * a.stab_zs : nullptr;
     const size_t base = ((size_t)blk << a.logB) + q0;
 
@@ -213,9 +215,10 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_contig(PassArgs
     const int total = A << a.logq;
     u64* s_tw = sm + tile_words(total);
     u64* mbar = s_tw + A;
-    const u32 z = blockIdx.x % a.nz, tile = blockIdx.x / a.nz;
-    const u64* in = a.in + (size_t)blockIdx.y * a.in_cs + (size_t)z * a.in_zs;
-    u64* out = a.out + (size_t)blockIdx.y * a.out_cs + (size_t)z * a.out_zs;
+    const u32 col = a.col_fast ? blockIdx.x : blockIdx.y, tz = a.col_fast ? blockIdx.y : blockIdx.x;
+    const u32 z = tz % a.nz, tile = tz / a.nz;
+    const u64* in = a.in + (size_t)col * a.in_cs + (size_t)z * a.in_zs;
+    u64* out = a.out + (size_t)col * a.out_cs + (size_t)z * a.out_zs;
     const u64* stab = a.stab ? a.stab + (size_t)z * a.stab_zs : nullptr;
     const int lognb = a.logn - a.loga;  // log2(#blocks in the column)
     const u32 c0 = tile << a.logq;
@@ -339,6 +342,13 @@ void set_smem_attrs() {
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
 }
 
+// Launch order (x fastest): all columns of one (tile, coset) first, then the next coset of the same tile.  The per-coset scale
+// slice and the twist slice of the tile stay in L2 across the columns, and a column's coefficient tile is re-read by its 8
+// cosets only `ncols` blocks later (also from L2).  Falls back to (tiles * nz, columns) when grid.y would overflow.
+dim3 make_grid(PassArgs& a, size_t tz, int ncols) {
+    a.col_fast = tz <= 65535;
+    return a.col_fast ? dim3((unsigned)ncols, (unsigned)tz, 1) : dim3((unsigned)tz, (unsigned)ncols, 1);
+}
 int pick_threads(size_t tile_elems) {
     if (ntt_threads() && tile_elems >= 4096) return ntt_threads();
     return tile_elems >= 8192 ? 512 : (tile_elems >= 4096 ? 256 : (tile_elems >= 1024 ? 64 : 32));
@@ -389,7 +399,7 @@ void run_forward(DevCtx* c, const XformDesc& d) {
             a.twist = c->get_twist_full(a.logB, a.loga, false);
             size_t tiles = (size_t)1 << (d.logn - a.loga - a.logq);
             a.nz = d.nz;
-            dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
+            dim3 grid = make_grid(a, tiles * d.nz, d.ncols);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
             if (ntt_rmax() == 4) k_pass_strided<false, 4><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
             else k_pass_strided<false, 3><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
@@ -398,7 +408,7 @@ void run_forward(DevCtx* c, const XformDesc& d) {
             a.logq = std::min(lognb, std::max(0, ntt_tile_log() - a.loga));
             size_t tiles = (size_t)1 << (lognb - a.logq);
             a.nz = d.nz;
-            dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
+            dim3 grid = make_grid(a, tiles * d.nz, d.ncols);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
             if (ntt_rmax() == 4) k_pass_contig<false, 4><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
             else k_pass_contig<false, 3><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
@@ -440,7 +450,7 @@ void run_inverse(DevCtx* c, const XformDesc& d) {
             a.logq = std::min(lognb, std::max(want, ntt_tile_log() - a.loga));
             size_t tiles = (size_t)1 << (lognb - a.logq);
             a.nz = d.nz;
-            dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
+            dim3 grid = make_grid(a, tiles * d.nz, d.ncols);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
             if (ntt_rmax() == 4) k_pass_contig<true, 4><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
             else k_pass_contig<true, 3><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
@@ -451,7 +461,7 @@ void run_inverse(DevCtx* c, const XformDesc& d) {
             a.twist = c->get_twist_full(a.logB, a.loga, true);
             size_t tiles = (size_t)1 << (d.logn - a.loga - a.logq);
             a.nz = d.nz;
-            dim3 grid((unsigned)(tiles * d.nz), d.ncols, 1);
+            dim3 grid = make_grid(a, tiles * d.nz, d.ncols);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
             if (ntt_rmax() == 4) k_pass_strided<true, 4><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
             else k_pass_strided<true, 3><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);

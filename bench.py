@@ -26,7 +26,7 @@ METRIC = "proofs/sec on a 2^20-row ACIR circuit (ECDSA-shaped, 234 wires, Keccak
 NCU = {"lde_traffic_over_algorithmic": 6.18 / 2.265, "keccak_traffic_over_algorithmic": 15.98 / 15.70,
        "lde_limiter": "integer ALU pipe 76% active, FMA pipe 23%, DRAM 905 GB/s: issue-bound 64-bit modular arithmetic, not HBM-bound",
        "keccak_limiter": "integer ALU pipe 99.7% active (LOP3/SHF): at the hardware floor for Keccak-f",
-       "files": ["profiles/r1d_ntt_ncu_raw.csv", "profiles/r1d_keccak_ncu_raw.csv", "profiles/r1d_launches_bench.csv"]}
+       "files": ["profiles/r1d_ntt_ncu_raw.csv", "profiles/r1d_keccak_ncu_raw.csv", "profiles/r1h_launches_bench.csv"]}
 UNIT = "proofs/s"
 
 
