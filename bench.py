@@ -185,6 +185,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
