@@ -749,8 +749,8 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     int bad_wire = 0;
     {
         // every column this rank reads: its inverse-NTT block and the routed columns (all of them on a single GPU)
-        struct { int* p; } flag = {ensure(C->ws.flag, 1)};
-        CUDA_CHECK(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+        int* flag = ensure(C->ws.flag, 1);
+        CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
         if (C->up.active && C->up.routed) CUDA_CHECK(cudaStreamWaitEvent(st, C->up.routed, 0));
         int c0, c1;
         column_block(C, W, &c0, &c1);
@@ -759,10 +759,10 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             if (rg[1] <= rg[0]) continue;
             size_t cnt = (size_t)(rg[1] - rg[0]) * n;
             unsigned blocks = (unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 16);
-            k_check_canonical<<<blocks, 256, 0, st>>>(d_wires + (size_t)rg[0] * n, cnt, flag.p);
+            k_check_canonical<<<blocks, 256, 0, st>>>(d_wires + (size_t)rg[0] * n, cnt, flag);
             count_launch(c);
         }
-        CUDA_CHECK(cudaMemcpyAsync(&bad_wire, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(&bad_wire, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     std::vector<digest_t> wires_cap = read_cap(C, C->wires.tree);   // synchronises the stream
     if (bad_wire) throw p2g_error(P2G_EBADARG, "p2g_prove: non-canonical wire value (>= p)");
@@ -795,23 +795,21 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         int xsplit;
         const u64* xtab = c->get_powtab(logn, gl_root_of_unity(logn), 1, &xsplit);
         size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
-        struct { u64* p; } q = {ensure(C->ws.q, (size_t)NC * nchunk * n)}, totals = {ensure(C->ws.totals, 4 * nt)};
+        u64* q = ensure(C->ws.q, (size_t)NC * nchunk * n);
+        u64* totals = ensure(C->ws.totals, 4 * nt);
         dim3 g1((unsigned)((n + 127) / 128), NC);
         if (C->up.active && C->up.routed) CUDA_CHECK(cudaStreamWaitEvent(st, C->up.routed, 0));
-        k_zpp_chunks<<<g1, 128, 0, st>>>(zp, d_wires, n, C->sigma_values.p, xtab, xsplit, q.p);
+        k_zpp_chunks<<<g1, 128, 0, st>>>(zp, d_wires, n, C->sigma_values.p, xtab, xsplit, q);
         dim3 g2((unsigned)((nt + 127) / 128), NC);
-        k_zscan_totals<<<g2, 128, 0, st>>>(zp, q.p, totals.p, nt);
-        k_scan_mul_excl<<<NC, 1024, 0, st>>>(totals.p, nt);
-        k_zscan_apply<<<g2, 128, 0, st>>>(zp, q.p, totals.p, nt, C->zpp_values.p);
+        k_zscan_totals<<<g2, 128, 0, st>>>(zp, q, totals, nt);
+        k_scan_mul_excl<<<NC, 1024, 0, st>>>(totals, nt);
+        k_zscan_apply<<<g2, 128, 0, st>>>(zp, q, totals, nt, C->zpp_values.p);
         count_launch(c, 4);
         CUDA_CHECK(cudaGetLastError());
         tr.mark("zpp launches");
-        CUDA_CHECK(cudaStreamSynchronize(st));
-        tr.mark("zpp kernels done");
         commit_from_values(C, C->zpp, C->zpp_values.p, n);
         tr.mark("zpp commit launched");
     }
-    tr.mark("zpp frees");
     std::vector<digest_t> zpp_cap = read_cap(C, C->zpp.tree);
     for (auto& dg : zpp_cap) ch.observe_digest(dg);
     CUDA_CHECK(cudaEventRecord(ev[2], st));
@@ -883,26 +881,27 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     PolyBatch* oracles[4] = {&C->cs, &C->wires, &C->zpp, &C->quot};
     const int widths[4] = {P, W, nzp, nq};
     const int total = P + W + nzp + nq;
-    struct { u64* p; } ztab0 = {ensure(C->ws.ztab0, 2 * n)}, ztab1 = {ensure(C->ws.ztab1, 2 * n)};
-    k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0.p, n, zeta);
-    k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1.p, n, zeta_next);
+    u64* ztab0 = ensure(C->ws.ztab0, 2 * n);
+    u64* ztab1 = ensure(C->ws.ztab1, 2 * n);
+    k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0, n, zeta);
+    k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1, n, zeta_next);
     count_launch(c, 2);
     const int nsplit = (int)((n + EVAL_SPLIT - 1) / EVAL_SPLIT);
     std::vector<e2> op(total), zs_next(NC);
     {
-        struct { e2* p; } partial = {ensure(C->ws.partial, (size_t)(total + NC) * nsplit)};
+        e2* partial = ensure(C->ws.partial, (size_t)(total + NC) * nsplit);
         int off = 0;
         for (int o = 0; o < 4; o++) {
             dim3 grid(widths[o], nsplit);
-            k_eval_polys<<<grid, 256, 0, st>>>(oracles[o]->coeffs.p, n, n, ztab0.p, partial.p + (size_t)off * nsplit, nsplit);
+            k_eval_polys<<<grid, 256, 0, st>>>(oracles[o]->coeffs.p, n, n, ztab0, partial + (size_t)off * nsplit, nsplit);
             off += widths[o];
         }
         dim3 grid(NC, nsplit);
-        k_eval_polys<<<grid, 256, 0, st>>>(C->zpp.coeffs.p, n, n, ztab1.p, partial.p + (size_t)total * nsplit, nsplit);
+        k_eval_polys<<<grid, 256, 0, st>>>(C->zpp.coeffs.p, n, n, ztab1, partial + (size_t)total * nsplit, nsplit);
         count_launch(c, 5);
         CUDA_CHECK(cudaGetLastError());
         std::vector<e2> hp((size_t)(total + NC) * nsplit);
-        CUDA_CHECK(cudaMemcpyAsync(hp.data(), partial.p, hp.size() * sizeof(e2), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(hp.data(), partial, hp.size() * sizeof(e2), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         for (int i = 0; i < total + NC; i++) {
             e2 s = e2_make(0, 0);
@@ -919,7 +918,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     // 10. FRI
     e2 fri_alpha = ch.get_e2();
     const int nl = d.num_fri_layers;
-    struct { u64* p; } fin = {ensure(C->ws.fin, 2 * n)};  // final polynomial, re | im
+    u64* fin = ensure(C->ws.fin, 2 * n);  // final polynomial, re | im
     {
         std::vector<e2> apow(total);
         e2 a = e2_make(1, 0);
@@ -927,8 +926,8 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             apow[j] = a;
             a = e2_mul(a, fri_alpha);
         }
-        struct { e2* p; } d_apow = {ensure(C->ws.apow, total)};
-        CUDA_CHECK(cudaMemcpyAsync(d_apow.p, apow.data(), sizeof(e2) * total, cudaMemcpyHostToDevice, st));
+        e2* d_apow = ensure(C->ws.apow, total);
+        CUDA_CHECK(cudaMemcpyAsync(d_apow, apow.data(), sizeof(e2) * total, cudaMemcpyHostToDevice, st));
         CombineArgs ca = {};
         for (int o = 0; o < 4; o++) {
             ca.coeffs[o] = oracles[o]->coeffs.p;
@@ -937,8 +936,8 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         }
         ca.num_challenges = NC;
         ca.logn = logn;
-        struct { u64* p; } u = {ensure(C->ws.u, 4 * n)};
-        k_fri_combine<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ca, d_apow.p, ztab0.p, ztab1.p, u.p);
+        u64* u = ensure(C->ws.u, 4 * n);
+        k_fri_combine<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ca, d_apow, ztab0, ztab1, u);
         // tables of inverse powers (reuse the forward tables' storage after the combine)
         e2 zi0, zi1;  // inverse in F_{p^2}: z^-1 = conj(z) / norm(z)
         {
@@ -950,15 +949,15 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             zi0 = inv2(zeta);
             zi1 = inv2(zeta_next);
         }
-        k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0.p, n, zi0);
-        k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1.p, n, zi1);
+        k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0, n, zi0);
+        k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1, n, zi1);
         size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
-        struct { u64* p; } totals = {ensure(C->ws.totals, 4 * nt)};
+        u64* totals = ensure(C->ws.totals, 4 * nt);
         dim3 g2((unsigned)((nt + 127) / 128), 4);
-        k_sscan_totals<<<g2, 128, 0, st>>>(u.p, totals.p, n, nt);
-        k_scan_add_suffix_excl<<<4, 1024, 0, st>>>(totals.p, nt);
+        k_sscan_totals<<<g2, 128, 0, st>>>(u, totals, n, nt);
+        k_scan_add_suffix_excl<<<4, 1024, 0, st>>>(totals, nt);
         e2 alpha_nc = e2_pow(fri_alpha, (u64)NC);
-        k_sscan_apply<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(u.p, totals.p, n, nt, ztab0.p, ztab1.p, alpha_nc, fin.p);
+        k_sscan_apply<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(u, totals, n, nt, ztab0, ztab1, alpha_nc, fin);
         count_launch(c, 6);
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaStreamSynchronize(st));
@@ -970,13 +969,14 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     if ((int)layers.size() != nl) layers.resize(nl);
     std::vector<e2> fri_betas(nl);
     C->fri_caps.clear();
-    struct { u64* p; } coeffs_a = {ensure(C->ws.coeffs_a, 2 * n)}, coeffs_b = {nullptr};
-    CUDA_CHECK(cudaMemcpyAsync(coeffs_a.p, fin.p, 16 * n, cudaMemcpyDeviceToDevice, st));
-    u64* cur_coeffs = coeffs_a.p;
+    u64* coeffs_a = ensure(C->ws.coeffs_a, 2 * n);
+    u64* coeffs_b = nullptr;
+    CUDA_CHECK(cudaMemcpyAsync(coeffs_a, fin, 16 * n, cudaMemcpyDeviceToDevice, st));
+    u64* cur_coeffs = coeffs_a;
     size_t m = n;  // number of (possibly) non-zero coefficients
     int logm = logn;
     u64 shift = GL_GEN;
-    if (nl) coeffs_b.p = ensure(C->ws.coeffs_b, 2 * (n >> d.reduction_arity_bits[0]) + 2);
+    if (nl) coeffs_b = ensure(C->ws.coeffs_b, 2 * (n >> d.reduction_arity_bits[0]) + 2);
     for (int l = 0; l < nl; l++) {
         Layer& L = layers[l];
         L.ab = d.reduction_arity_bits[l];
@@ -994,7 +994,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         e2 beta = ch.get_e2();
         fri_betas[l] = beta;
         size_t m2 = m >> L.ab;
-        u64* nxt = (cur_coeffs == coeffs_a.p) ? coeffs_b.p : coeffs_a.p;
+        u64* nxt = (cur_coeffs == coeffs_a) ? coeffs_b : coeffs_a;
         k_fri_fold<<<(unsigned)((m2 + 127) / 128), 128, 0, st>>>(cur_coeffs, m, nxt, m2, arity, beta);
         count_launch(c);
         CUDA_CHECK(cudaGetLastError());
@@ -1023,14 +1023,14 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     if (forced_pow) {
         pow_witness = *forced_pow;
     } else {
-        struct { unsigned long long* p; } best = {ensure(C->ws.best, 1)};
+        unsigned long long* best = ensure(C->ws.best, 1);
         const u64 batch = (u64)1 << 20;
         for (u64 start = 0;; start += batch) {
-            CUDA_CHECK(cudaMemsetAsync(best.p, 0xff, 8, st));
-            k_pow_search<<<(unsigned)(batch / 128), 128, 0, st>>>(ch, start, batch, d.pow_bits, best.p);
+            CUDA_CHECK(cudaMemsetAsync(best, 0xff, 8, st));
+            k_pow_search<<<(unsigned)(batch / 128), 128, 0, st>>>(ch, start, batch, d.pow_bits, best);
             count_launch(c);
             unsigned long long hb = 0;
-            CUDA_CHECK(cudaMemcpyAsync(&hb, best.p, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(&hb, best, 8, cudaMemcpyDeviceToHost, st));
             CUDA_CHECK(cudaStreamSynchronize(st));
             if (hb != ~0ULL) {
                 pow_witness = hb;
@@ -1068,14 +1068,15 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
 
     // query rounds: gather opened rows and Merkle paths on the device, one D2H
     // d_idx: global leaf indices (FRI layers, replicated); d_lidx: indices into this rank's leaves (0 for queries it does not own)
-    struct { u32* p; } d_idx = {ensure(C->ws.idx, 2 * NQ)}, d_lidx = {d_idx.p + NQ};
+    u32* d_idx = ensure(C->ws.idx, 2 * NQ);
+    u32* d_lidx = d_idx + NQ;
     std::vector<u32> idx2(2 * NQ);
     for (int q = 0; q < NQ; q++) {
         idx2[q] = indices[q];
         bool mine = indices[q] >= C->j0 && indices[q] < C->j0 + C->lde_l;
         idx2[NQ + q] = mine ? (u32)(indices[q] - C->j0) : 0;
     }
-    CUDA_CHECK(cudaMemcpyAsync(d_idx.p, idx2.data(), 8 * NQ, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(d_idx, idx2.data(), 8 * NQ, cudaMemcpyHostToDevice, st));
     size_t row_words = 0, path_digests = 0;
     size_t row_off[4 + P2G_MAX_FRI_LAYERS], path_off[4 + P2G_MAX_FRI_LAYERS];
     int path_len[4 + P2G_MAX_FRI_LAYERS];
@@ -1093,14 +1094,14 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         path_len[4 + l] = (int)layers[l].tree.tree.levels.size() - 1;
         path_digests += (size_t)NQ * path_len[4 + l];
     }
-    struct { u64* p; } d_rows = {ensure(C->ws.rows, row_words)};
-    struct { digest_t* p; } d_paths = {ensure(C->ws.paths, path_digests + 1)};
+    u64* d_rows = ensure(C->ws.rows, row_words);
+    digest_t* d_paths = ensure(C->ws.paths, path_digests + 1);
     for (int o = 0; o < 4; o++) {
         int cnt = NQ * widths[o];
-        k_gather_rows<<<(cnt + 127) / 128, 128, 0, st>>>(oracles[o]->lde.p, C->lde_l, widths[o], d_lidx.p, NQ, d_rows.p + row_off[o]);
+        k_gather_rows<<<(cnt + 127) / 128, 128, 0, st>>>(oracles[o]->lde.p, C->lde_l, widths[o], d_lidx, NQ, d_rows + row_off[o]);
         if (path_len[o] > 0) {
             int pc = NQ * path_len[o];
-            k_gather_paths<<<(pc + 127) / 128, 128, 0, st>>>(oracles[o]->d_levels.p, path_len[o], d_lidx.p, NQ, 0, d_paths.p + path_off[o]);
+            k_gather_paths<<<(pc + 127) / 128, 128, 0, st>>>(oracles[o]->d_levels.p, path_len[o], d_lidx, NQ, 0, d_paths + path_off[o]);
         }
         count_launch(c, 2);
     }
@@ -1110,12 +1111,12 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             sh += layers[l].ab;
             int arity = 1 << layers[l].ab;
             int cnt = NQ * 2 * arity;
-            k_gather_fri_rows<<<(cnt + 127) / 128, 128, 0, st>>>(layers[l].values.p, layers[l].cur, arity, d_idx.p, NQ, sh,
-                                                                 d_rows.p + row_off[4 + l]);
+            k_gather_fri_rows<<<(cnt + 127) / 128, 128, 0, st>>>(layers[l].values.p, layers[l].cur, arity, d_idx, NQ, sh,
+                                                                 d_rows + row_off[4 + l]);
             if (path_len[4 + l] > 0) {
                 int pc = NQ * path_len[4 + l];
-                k_gather_paths<<<(pc + 127) / 128, 128, 0, st>>>(layers[l].tree.d_levels.p, path_len[4 + l], d_idx.p, NQ, sh,
-                                                                 d_paths.p + path_off[4 + l]);
+                k_gather_paths<<<(pc + 127) / 128, 128, 0, st>>>(layers[l].tree.d_levels.p, path_len[4 + l], d_idx, NQ, sh,
+                                                                 d_paths + path_off[4 + l]);
             }
             count_launch(c, 2);
         }
@@ -1123,8 +1124,8 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     CUDA_CHECK(cudaGetLastError());
     std::vector<u64> h_rows(row_words);
     std::vector<digest_t> h_paths(path_digests + 1);
-    CUDA_CHECK(cudaMemcpyAsync(h_rows.data(), d_rows.p, 8 * row_words, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(h_paths.data(), d_paths.p, sizeof(digest_t) * path_digests, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_rows.data(), d_rows, 8 * row_words, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_paths.data(), d_paths, sizeof(digest_t) * path_digests, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (C->world > 1) {
         // opened rows and paths of the four committed oracles come from the rank that owns the leaf
