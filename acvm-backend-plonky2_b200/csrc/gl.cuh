@@ -204,6 +204,17 @@ GL_HD u64 glf_mul(u64 a, u64 b) {
 #endif
 }
 
+// x * 2^S for a compile-time 0 <= S < 96, x: N -> C.  2 is a 192nd root of unity in this field (2^96 = -1) and plonky2's
+// roots of unity of order <= 64 are powers of two (omega_64 = 2^3, omega_8 = 2^24, omega_4 = 2^48), so the twiddles of the last
+// six stages of every transform are shifts: two 64-bit shifts and one 128-bit reduction instead of four wide multiplies.
+template <int S>
+GL_HD u64 gl_shl(u64 x) {
+    static_assert(S >= 0 && S < 96, "shift out of range");
+    if (S == 0) return gl_canon(x);
+    if (S < 64) return gl_reduce128(x >> (64 - (S ? S : 1)), x << S);
+    return gl_shl<(S >= 64 ? S - 48 : 0)>(gl_shl<48>(x));
+}
+
 // Sum of products with ONE reduction at the end: acc += a * b for a, b: N.  The 128-bit products are accumulated exactly --
 // even limbs (a0 b0 + a1 b1 2^64) in `e`, cross terms (a0 b1 + a1 b0) in `o` -- so on the device each term costs 4
 // IMAD.WIDE.U32 and 3 carry adds and no modular reduction.  Holds up to 2^31 terms.

@@ -97,13 +97,32 @@ __device__ __forceinline__ u64 tab_pow(const u64* tab, int split, u32 i) {
 __device__ __forceinline__ int phys(int e) { return e + (e >> 4); }
 __host__ __device__ inline size_t tile_words(size_t elems) { return (elems + (elems >> 4) + 3) & ~(size_t)1; }   // even: TMA dst 16 B aligned
 
+// v * omega_{2h}^{+-kk} for the compile-time-unrolled (h, kk) of a LAST round: omega_{2h} = 2^(96 / h), so the factor is 2^S with
+// S = 96 kk / h forward and -2^(96 - S) inverse (the caller folds the sign into its add / sub).  Returns v 2^S resp. v 2^(96-S).
+template <int R>
+__device__ __forceinline__ u64 shl_by_index(u64 v, int, int h, int kk, bool inv) {
+    const int S = inv ? 96 - 96 * kk / h : 96 * kk / h;   // h in {1,2,4,8}, 0 < kk < h: multiples of 12 in (0, 96)
+    switch (S) {
+    case 12: return gl_shl<12>(v);
+    case 24: return gl_shl<24>(v);
+    case 36: return gl_shl<36>(v);
+    case 48: return gl_shl<48>(v);
+    case 60: return gl_shl<60>(v);
+    case 72: return gl_shl<72>(v);
+    case 84: return gl_shl<84>(v);
+    default: return v;   // unreachable
+    }
+}
+
 // One register round: R butterfly stages [s0, s0 + R) of the 2^a-point sub-transforms of the tile.  A thread owns the 2^R
 // elements that differ in bits [a-s0-R, a-s0) of m, runs the R stages on them in registers (radix-2^R, 2^(R-1) R butterflies,
 // 2^R - 1 twiddle loads) and writes them back: the tile makes one shared-memory round trip per R stages instead of one per
 // stage.  Forward = decimation in frequency (stage order s0 .. s0+R-1), inverse = decimation in time (reverse order).
-template <int R, bool INV>
+// LAST: the round that ends the sub-transform (s0 + R == a).  Its twiddles are omega_{2h}^kk with 2h <= 2^R <= 16, i.e. the
+// compile-time powers of two 2^(96 kk / h): multiplication-free butterflies, no twiddle loads.
+template <int R, bool INV, bool LAST>
 __device__ __forceinline__ void reg_round(u64* __restrict__ sm, const u64* __restrict__ s_tw, int a, int s0, int logq, int log_tasks) {
-    const int lo_bits = a - s0 - R;
+    const int lo_bits = LAST ? 0 : a - s0 - R;
     const int A = 1 << a;
     const int lo_mask = (1 << lo_bits) - 1, q_mask = (1 << logq) - 1;
     for (int task = threadIdx.x; task < (1 << log_tasks); task += blockDim.x) {
@@ -118,21 +137,33 @@ __device__ __forceinline__ void reg_round(u64* __restrict__ sm, const u64* __res
             const int i = INV ? R - 1 - ii : ii;
             const int h = 1 << (R - 1 - i);
             const u64* tw = s_tw + (A - (A >> (s0 + i)));
-            const bool unit = (h == 1) && (lo_bits == 0);   // last stage of the sub-transform: every twiddle is 1
 #pragma unroll
             for (int kk = 0; kk < h; kk++) {
-                const u64 w = unit ? 1 : tw[(kk << lo_bits) | lo];
+                u64 w = 0;
+                if (!LAST) w = tw[(kk << lo_bits) | lo];
 #pragma unroll
                 for (int g = 0; g < (1 << R); g += 2 * h) {
                     u64 u = x[g + kk], v = x[g + kk + h];
-                    if (INV) {
-                        if (!unit) v = glf_mul(v, w);
+                    if (LAST) {
+                        // forward: (u + v, (u - v) 2^S), S = 96 kk / h;  inverse: v 2^-S = -v 2^(96 - S)
+                        if (kk == 0) {
+                            x[g] = glf_add(u, v);
+                            x[g + h] = gl_sub(u, v);
+                        } else if (INV) {
+                            v = shl_by_index<R>(v, 0, h, kk, true);
+                            x[g + kk] = gl_sub(u, v);
+                            x[g + kk + h] = glf_add(u, v);
+                        } else {
+                            x[g + kk] = glf_add(u, v);
+                            x[g + kk + h] = shl_by_index<R>(gl_sub(u, v), 0, h, kk, false);
+                        }
+                    } else if (INV) {
+                        v = glf_mul(v, w);
                         x[g + kk] = glf_add(u, v);
                         x[g + kk + h] = gl_sub(u, v);
                     } else {
                         x[g + kk] = glf_add(u, v);
-                        v = gl_sub(u, v);
-                        x[g + kk + h] = unit ? v : glf_mul(v, w);
+                        x[g + kk + h] = glf_mul(gl_sub(u, v), w);
                     }
                 }
             }
@@ -143,25 +174,41 @@ __device__ __forceinline__ void reg_round(u64* __restrict__ sm, const u64* __res
     __syncthreads();
 }
 
-// all `a` stages of the tile: rounds of RMAX stages, then one round with the remainder
+// all `a` stages of the tile: one round with the remainder a % RMAX, then rounds of RMAX stages -- the last round (the one with
+// the multiplication-free twiddles) is a full one
 template <bool INV, int RMAX>
 __device__ __forceinline__ void tile_butterflies(u64* sm, const u64* s_tw, int a, int logq, int log_elems) {
     const int rem = a % RMAX, full = a / RMAX;
     if (!INV) {
         int s0 = 0;
-        for (int r = 0; r < full; r++, s0 += RMAX) reg_round<RMAX, false>(sm, s_tw, a, s0, logq, log_elems - RMAX);
-        if (rem == 3) reg_round<3, false>(sm, s_tw, a, s0, logq, log_elems - 3);
-        else if (rem == 2) reg_round<2, false>(sm, s_tw, a, s0, logq, log_elems - 2);
-        else if (rem == 1) reg_round<1, false>(sm, s_tw, a, s0, logq, log_elems - 1);
-    } else {
-        int s0 = a - rem;
-        if (rem == 3) reg_round<3, true>(sm, s_tw, a, s0, logq, log_elems - 3);
-        else if (rem == 2) reg_round<2, true>(sm, s_tw, a, s0, logq, log_elems - 2);
-        else if (rem == 1) reg_round<1, true>(sm, s_tw, a, s0, logq, log_elems - 1);
-        for (int r = 0; r < full; r++) {
-            s0 -= RMAX;
-            reg_round<RMAX, true>(sm, s_tw, a, s0, logq, log_elems - RMAX);
+        if (full == 0) {
+            if (rem == 3) reg_round<3, false, true>(sm, s_tw, a, 0, logq, log_elems - 3);
+            else if (rem == 2) reg_round<2, false, true>(sm, s_tw, a, 0, logq, log_elems - 2);
+            else if (rem == 1) reg_round<1, false, true>(sm, s_tw, a, 0, logq, log_elems - 1);
+            return;
         }
+        if (rem == 3) reg_round<3, false, false>(sm, s_tw, a, 0, logq, log_elems - 3);
+        else if (rem == 2) reg_round<2, false, false>(sm, s_tw, a, 0, logq, log_elems - 2);
+        else if (rem == 1) reg_round<1, false, false>(sm, s_tw, a, 0, logq, log_elems - 1);
+        s0 = rem;
+        for (int r = 0; r + 1 < full; r++, s0 += RMAX) reg_round<RMAX, false, false>(sm, s_tw, a, s0, logq, log_elems - RMAX);
+        reg_round<RMAX, false, true>(sm, s_tw, a, s0, logq, log_elems - RMAX);
+    } else {
+        if (full == 0) {
+            if (rem == 3) reg_round<3, true, true>(sm, s_tw, a, 0, logq, log_elems - 3);
+            else if (rem == 2) reg_round<2, true, true>(sm, s_tw, a, 0, logq, log_elems - 2);
+            else if (rem == 1) reg_round<1, true, true>(sm, s_tw, a, 0, logq, log_elems - 1);
+            return;
+        }
+        int s0 = a - RMAX;
+        reg_round<RMAX, true, true>(sm, s_tw, a, s0, logq, log_elems - RMAX);
+        for (int r = 0; r + 1 < full; r++) {
+            s0 -= RMAX;
+            reg_round<RMAX, true, false>(sm, s_tw, a, s0, logq, log_elems - RMAX);
+        }
+        if (rem == 3) reg_round<3, true, false>(sm, s_tw, a, 0, logq, log_elems - 3);
+        else if (rem == 2) reg_round<2, true, false>(sm, s_tw, a, 0, logq, log_elems - 2);
+        else if (rem == 1) reg_round<1, true, false>(sm, s_tw, a, 0, logq, log_elems - 1);
     }
 }
 
