@@ -349,13 +349,15 @@ const int MAX_CONTIG_LOG = 11;
 const int MAX_STRIDED_LOG = 10;
 
 // forward-order pass plan: strided passes (largest block first) then one contiguous pass
-std::vector<int> make_plan(int logn) {
+std::vector<int> make_plan(int logn, bool inverse = false) {
     std::vector<int> plan;
     if (logn <= MAX_CONTIG_LOG) {
         plan.push_back(logn);
         return plan;
     }
-    int last = std::min(ntt_last_log(), MAX_CONTIG_LOG);
+    // the inverse transform's contiguous pass gathers 8 blocks per tile (64-byte runs of the natural-order input), so its
+    // sub-transform is kept at 2^10 to stay at two resident tiles per SM
+    int last = inverse ? std::min(10, ntt_last_log()) : std::min(ntt_last_log(), MAX_CONTIG_LOG);
     int rem = logn - last;
     int cnt = (rem + MAX_STRIDED_LOG - 1) / MAX_STRIDED_LOG;
     for (int i = 0; i < cnt; i++) {
@@ -468,7 +470,7 @@ void run_forward(DevCtx* c, const XformDesc& d) {
 
 void run_inverse(DevCtx* c, const XformDesc& d) {
     set_smem_attrs();
-    std::vector<int> plan = make_plan(d.logn);
+    std::vector<int> plan = make_plan(d.logn, true);
     int np = (int)plan.size();
     // inverse order: contiguous pass first, then strided passes with growing blocks
     int done = 0;
