@@ -23,11 +23,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "proofs/sec on a 2^20-row ACIR circuit (ECDSA-shaped, 234 wires, Keccak config)"
 # constants read off the committed ncu --set full captures (profiles/r1_summary.md section 3)
-NCU = {"lde_traffic_over_algorithmic": 6.18 / 2.265, "keccak_traffic_over_algorithmic": 15.98 / 15.70,
-       "lde_limiter": "integer ALU pipe 76% active, FMA pipe 23%, DRAM 905 GB/s: issue-bound 64-bit modular arithmetic, not HBM-bound",
+NCU = {"lde_traffic_over_algorithmic": 6.26 / 2.265, "keccak_traffic_over_algorithmic": 15.98 / 15.70,
+       "lde_limiter": "integer ALU pipe 64-67% active, FMA pipe 21-22%, DRAM 1.08 TB/s: issue-bound 64-bit modular arithmetic, not HBM-bound",
        "keccak_limiter": "integer ALU pipe 99.7% active (LOP3/SHF): at the hardware floor for Keccak-f",
-       "files": ["profiles/r1d_ntt_ncu_raw.csv", "profiles/r1d_keccak_ncu_raw.csv", "profiles/r1h_launches_bench.csv"]}
-UNIT = "proofs/s"
+       "files": ["profiles/r1k_ntt_ncu_raw.csv", "profiles/r1k_keccak_ncu_raw.csv", "profiles/r1k_launches_bench.csv"]}
 
 
 def parse():
