@@ -22,6 +22,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "proofs/sec on a 2^20-row ACIR circuit (ECDSA-shaped, 234 wires, Keccak config)"
+UNIT = "proofs/s"
 # constants read off the committed ncu --set full captures (profiles/r1_summary.md section 3)
 NCU = {"lde_traffic_over_algorithmic": 6.26 / 2.265, "keccak_traffic_over_algorithmic": 15.98 / 15.70,
        "lde_limiter": "integer ALU pipe 64-67% active, FMA pipe 21-22%, DRAM 1.08 TB/s: issue-bound 64-bit modular arithmetic, not HBM-bound",
