@@ -71,6 +71,35 @@ __device__ __forceinline__ u64 v1_sub(u64 a, u64 b) {
     return v1_fix_sub_eps(d, br);
 }
 
+
+// ---- variant 2: carry fixes as compare + predicated/selected adds (no IMAD.WIDE fixes) ----
+__device__ __forceinline__ u64 v2_canon(u64 x) { u64 y = x + 0xFFFFFFFFULL; return y < x ? y : x; }
+__device__ __forceinline__ u64 v2_add(u64 a, u64 b) {   // C, C -> C
+    u64 s = a + b;
+    u64 y = s + 0xFFFFFFFFULL;
+    return (s < a || y < s) ? y : s;
+}
+__device__ __forceinline__ u64 v2_mul(u64 a, u64 b) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), r0, r1, r2, r3;
+    asm("{\n\t"
+        "mul.lo.u32 %0, %4, %6;\n\t"
+        "mul.hi.u32 %1, %4, %6;\n\t"
+        "mul.lo.u32 %2, %5, %7;\n\t"
+        "mul.hi.u32 %3, %5, %7;\n\t"
+        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
+        "madc.hi.cc.u32 %2, %4, %7, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "}" : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    u64 lo = ((u64)r1 << 32) | r0;
+    u64 t = gl_sub(lo, (u64)r3);
+    u64 u = ((u64)r2 << 32) - r2;
+    u64 x = t + u;
+    if (x < u) x += 0xFFFFFFFFULL;
+    return v2_canon(x);
+}
 template <int V>
 __global__ void k_bfly(u64* data, int iters, u64 w0) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,9 +117,15 @@ __global__ void k_bfly(u64* data, int iters, u64 w0) {
                 if (V == 0) {
                     x[k] = gl_add(u, v);
                     x[k + h] = gl_mul(gl_sub(u, v), w);
-                } else {
+                } else if (V == 1) {
                     x[k] = v1_add(u, v);
                     x[k + h] = v1_mul(v1_sub(u, v), w);
+                } else if (V == 2) {
+                    x[k] = v2_add(u, v);
+                    x[k + h] = v2_mul(gl_sub(u, v), w);
+                } else {
+                    x[k] = glf_add(u, v);
+                    x[k + h] = glf_mul(gl_sub(u, v), w);
                 }
             }
         }
@@ -113,17 +148,20 @@ int main() {
     h[0] = GL_P - 1; h[1] = GL_P - 1; h[2] = 0; h[3] = GL_P - 1; h[4] = 1; h[5] = 0xFFFFFFFFULL; h[6] = 0xFFFFFFFF00000000ULL; h[7] = 0x100000000ULL;
     const int iters = 64;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    for (int v = 0; v < 2; v++) {
+    for (int v = 0; v < 4; v++) {
         float best = 1e9;
         for (int rep = 0; rep < 4; rep++) {
             cudaMemcpy(d, h, nthr * 64, cudaMemcpyHostToDevice);
             cudaEventRecord(a);
             if (v == 0) k_bfly<0><<<nthr / 256, 256>>>(d, iters, 12345678901234567ULL);
-            else k_bfly<1><<<nthr / 256, 256>>>(d, iters, 12345678901234567ULL);
+            else if (v == 1) k_bfly<1><<<nthr / 256, 256>>>(d, iters, 12345678901234567ULL);
+            else if (v == 2) k_bfly<2><<<nthr / 256, 256>>>(d, iters, 12345678901234567ULL);
+            else k_bfly<3><<<nthr / 256, 256>>>(d, iters, 12345678901234567ULL);
             cudaEventRecord(b); cudaEventSynchronize(b);
             float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
         }
         cudaMemcpy(v ? h1 : h0, d, nthr * 64, cudaMemcpyDeviceToHost);
+        if (v) { size_t bad = 0; for (size_t i = 0; i < nthr * 8; i++) bad += h0[i] != h1[i]; printf("  variant %d vs 0 mismatches: %zu\n", v, bad); }
         double bf = (double)nthr * iters * 12;
         printf("variant %d: %.3f ms  %.1f G butterflies/s  (err %s)\n", v, best, bf / best / 1e6, cudaGetErrorString(cudaGetLastError()));
     }
