@@ -96,7 +96,11 @@ struct StageTimer {  // RAII: accumulates elapsed ms of a stream segment into *a
 
 // ---- ntt.cu: transforms over column-major batches (column c at base + c*col_stride) ----
 // values on <omega_N> in natural order -> coefficients in natural order (PolynomialValues::ifft)
-void ntt_ifft(DevCtx* c, const u64* d_values, size_t in_cs, u64* d_coeffs, size_t out_cs, int logn, int ncols);
+// peer_coeffs (npeer pointers, may be 0): the same position in other GPUs' coefficient buffers (same out_cs); the last pass stores
+// its results there too (P2P over NVLink) -- the fused "inverse NTT + all-gather" of coset-sharded proofs
+#define P2G_MAX_PEERS 7
+void ntt_ifft(DevCtx* c, const u64* d_values, size_t in_cs, u64* d_coeffs, size_t out_cs, int logn, int ncols, int npeer = 0,
+              u64* const* peer_coeffs = nullptr);
 // coefficients (natural, N) -> values on shift*<omega_{N<<rate_bits}> in LEAF order (index j <-> point shift*omega^bitrev(j))
 // (PolynomialBatch::lde_values followed by reverse_index_bits_in_place)
 // z0 / nzl: only the cosets [z0, z0 + nzl) are produced (coset-sharded proofs), at d_lde[col * out_cs + (z - z0) * N + i];

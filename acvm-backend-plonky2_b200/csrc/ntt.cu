@@ -42,6 +42,10 @@ struct PassArgs {
     int gather;                // contiguous inverse pass: input is in natural order, gather bit-reversed runs
     u32 nz;                    // cosets per tile
     int col_fast;              // grid = (columns, tiles * nz): the columns of one (tile, coset) are adjacent in launch order
+    // coset-sharded proofs: the final pass of the inverse transform also stores every result into the same place of each peer
+    // GPU's coefficient buffer (P2P stores over NVLink), so the column blocks are exchanged by the kernel that computes them
+    int npeer;
+    u64* peer_out[P2G_MAX_PEERS];
 };
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -251,6 +255,8 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_strided(PassArg
         if (INV && stab) v = glf_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
         if (a.scale != 1) v = gl_mul(v, a.scale);
         out[idx] = v;
+        if (INV)
+            for (int p = 0; p < a.npeer; p++) a.peer_out[p][(size_t)col * a.out_cs + idx] = v;
     }
 }
 
@@ -296,6 +302,8 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_contig(PassArgs
         if (INV && stab) v = gl_mul(v, tab_pow(stab, a.stab_split, (u32)idx));
         if (a.scale != 1) v = gl_mul(v, a.scale);
         out[idx] = v;
+        if (INV)
+            for (int p = 0; p < a.npeer; p++) a.peer_out[p][(size_t)col * a.out_cs + idx] = v;
     }
 }
 
@@ -416,6 +424,8 @@ struct XformDesc {
     int stab_full;
     u64 scale;
     bool natural_input;  // inverse only
+    int npeer;           // inverse only: peer copies of the output written by the last pass
+    u64* const* peer_out;
 };
 
 void run_forward(DevCtx* c, const XformDesc& d) {
@@ -491,6 +501,8 @@ void run_inverse(DevCtx* c, const XformDesc& d) {
             a.stab = d.stab;
             a.stab_split = d.stab_split;
             a.stab_zs = d.stab_zs;
+            a.npeer = d.npeer;
+            for (int p = 0; p < d.npeer; p++) a.peer_out[p] = d.peer_out[p];
         }
         if (first) {
             int lognb = d.logn - a.loga;
@@ -630,10 +642,13 @@ const u64* DevCtx::get_coset_tabs(int logn, int rate_bits, u64 shift, int* split
 // ---------------------------------------------------------------------------------------------------------------------
 // public transforms
 // ---------------------------------------------------------------------------------------------------------------------
-void ntt_ifft(DevCtx* c, const u64* d_values, size_t in_cs, u64* d_coeffs, size_t out_cs, int logn, int ncols) {
+void ntt_ifft(DevCtx* c, const u64* d_values, size_t in_cs, u64* d_coeffs, size_t out_cs, int logn, int ncols, int npeer,
+              u64* const* peer_coeffs) {
     if (ncols <= 0) return;
     StageTimer tm(c, &c->ntt_ms);
     XformDesc d = {};
+    d.npeer = logn > 0 ? npeer : 0;
+    d.peer_out = peer_coeffs;
     d.in = d_values;
     d.in_cs = in_cs;
     d.out = d_coeffs;

@@ -14,6 +14,7 @@
 #include <chrono>
 #include <stdio.h>
 #include <stdlib.h>
+#include <unistd.h>
 namespace {
 
 // P2G_TRACE=1: host wall-clock trace of the prove stages on stderr (debugging aid)
@@ -397,6 +398,12 @@ struct p2g_circuit {
     int loglde_l = 0;
     p2g_allgather_fn allgather = nullptr;
     void* allgather_user = nullptr;
+    // peer views of every other rank's wires.coeffs buffer (same process: the pointer itself; another process: CUDA IPC
+    // mapping).  When all ranks could map all peers, the inverse NTT of the trace stores its column block straight into the
+    // peers over NVLink and the coefficient all-gather disappears; otherwise the NCCL all-gather is used.
+    int npeer = 0;
+    u64* peer_coeffs[P2G_MAX_PEERS] = {};
+    std::vector<void*> ipc_opened;
     // host-trace upload, pipelined with the inverse NTT: column chunks go up on `copy` while earlier chunks are transformed
     struct Upload {
         cudaStream_t copy = nullptr;
@@ -410,6 +417,7 @@ struct p2g_circuit {
     ~p2g_circuit() {
         for (cudaEvent_t e : up.pool) cudaEventDestroy(e);
         if (up.copy) cudaStreamDestroy(up.copy);
+        for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
         free_child_ctx(ctx);
     }
 };
@@ -461,16 +469,79 @@ void ifft_columns(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t valu
     if (b.coeffs.n != want) b.coeffs.alloc(want);
     int c0, c1;
     const bool sharded = column_block(C, b.ncols, &c0, &c1);
+    // fused exchange: only for the trace (the buffer the peers mapped at create time)
+    const bool fused = sharded && C->npeer == C->world - 1 && &b == &C->wires;
+    u64* peers[P2G_MAX_PEERS];
+    auto peer_ptrs = [&](int col) {
+        for (int p = 0; p < C->npeer; p++) peers[p] = C->peer_coeffs[p] + (size_t)col * C->n;
+        return fused ? C->npeer : 0;
+    };
     if (up) {   // chunks of [c0, c1) arrive on the copy stream; transform each as soon as it is there
         for (auto& ch : up->chunks) {
             int a = std::get<0>(ch), e = std::get<1>(ch);
             CUDA_CHECK(cudaStreamWaitEvent(C->ctx->stream, std::get<2>(ch), 0));
-            ntt_ifft(C->ctx, d_values + (size_t)a * values_cs, values_cs, b.coeffs.p + (size_t)a * C->n, C->n, C->logn, e - a);
+            int np = peer_ptrs(a);
+            ntt_ifft(C->ctx, d_values + (size_t)a * values_cs, values_cs, b.coeffs.p + (size_t)a * C->n, C->n, C->logn, e - a, np, peers);
         }
     } else {
-        ntt_ifft(C->ctx, d_values + (size_t)c0 * values_cs, values_cs, b.coeffs.p + (size_t)c0 * C->n, C->n, C->logn, c1 - c0);
+        int np = peer_ptrs(c0);
+        ntt_ifft(C->ctx, d_values + (size_t)c0 * values_cs, values_cs, b.coeffs.p + (size_t)c0 * C->n, C->n, C->logn, c1 - c0, np, peers);
     }
-    if (sharded) shard_allgather(C, b.coeffs.p + (size_t)C->rank * per * C->n, b.coeffs.p, (size_t)per * C->n * 8, true);
+    if (fused) {
+        // every rank's block has been stored into every buffer once all kernels have completed: drain, then a (tiny) barrier
+        CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));
+        int one = 1;
+        std::vector<int> all(C->world);
+        shard_allgather(C, &one, all.data(), sizeof(int), false);
+    } else if (sharded) {
+        shard_allgather(C, b.coeffs.p + (size_t)C->rank * per * C->n, b.coeffs.p, (size_t)per * C->n * 8, true);
+    }
+}
+
+// Map every peer's wires.coeffs buffer (called once at create, after the buffer exists).  All ranks agree on the outcome.
+void setup_peers(p2g_circuit* C) {
+    if (C->world == 1 || getenv("P2G_NO_PEER")) return;
+    struct Info {
+        int pid, device;
+        unsigned long long ptr;
+        cudaIpcMemHandle_t h;
+    };
+    Info mine = {};
+    mine.pid = (int)getpid();
+    mine.device = C->ctx->device;
+    mine.ptr = (unsigned long long)C->wires.coeffs.p;
+    bool ok = cudaIpcGetMemHandle(&mine.h, C->wires.coeffs.p) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    std::vector<Info> all(C->world);
+    shard_allgather(C, &mine, all.data(), sizeof(Info), false);
+    int np = 0;
+    for (int r = 0; r < C->world && ok; r++) {
+        if (r == C->rank) continue;
+        u64* q = nullptr;
+        if (all[r].pid == mine.pid) {   // another handle of this process (thread-group ranks)
+            if (all[r].device != mine.device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+                cudaGetLastError();
+            }
+            q = (u64*)all[r].ptr;
+        } else {
+            void* m = nullptr;
+            if (cudaIpcOpenMemHandle(&m, all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+                C->ipc_opened.push_back(m);
+                q = (u64*)m;
+            } else {
+                cudaGetLastError();
+                ok = false;
+            }
+        }
+        if (ok) C->peer_coeffs[np++] = q;
+    }
+    int flag = ok ? 1 : 0;
+    std::vector<int> flags(C->world);
+    shard_allgather(C, &flag, flags.data(), sizeof(int), false);
+    for (int f : flags) ok = ok && f;
+    C->npeer = ok ? np : 0;
 }
 void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs, const p2g_circuit::Upload* up = nullptr) {
     if (up && C->world == 1) {
@@ -664,6 +735,7 @@ static int circuit_create_impl(const p2g_circuit_desc* desc, int device, int ran
         C->quot.ncols = nq;
         C->quot.coeffs.alloc(padded(nq) * n);
         C->quot.lde.alloc((size_t)nq * C->lde_l);
+        setup_peers(C);
         *out = C;
     });
     if (rc != P2G_OK && C) delete C;
@@ -1403,7 +1475,8 @@ extern "C" int p2g_circuit_read(p2g_circuit* C, int what, void* out, size_t* len
             hsrc = packed.data();
             sz = packed.size();
         };
-        if (what != P2G_BUF_CS_CAP && !C->proved) throw p2g_error(P2G_EBADARG, "p2g_circuit_read: no proof has been produced yet");
+        u64 info[4] = {(u64)C->rank, (u64)C->world, (u64)C->npeer, (u64)(C->npeer == C->world - 1 && C->world > 1)};
+        if (what != P2G_BUF_CS_CAP && what != P2G_BUF_SHARD_INFO && !C->proved) throw p2g_error(P2G_EBADARG, "p2g_circuit_read: no proof has been produced yet");
         switch (what) {
         case P2G_BUF_WIRES_CAP: cap_of(C->last_caps[0]); break;
         case P2G_BUF_ZS_PP_CAP: cap_of(C->last_caps[1]); break;
@@ -1420,6 +1493,7 @@ extern "C" int p2g_circuit_read(p2g_circuit* C, int what, void* out, size_t* len
             hsrc = packed.data();
             sz = packed.size();
             break;
+        case P2G_BUF_SHARD_INFO: hsrc = info; sz = sizeof(info); break;
         case P2G_BUF_WIRES_LDE: dsrc = C->wires.lde.p; sz = (size_t)d.num_wires * C->lde_l * 8; break;   // this rank's leaves
         default: throw p2g_error(P2G_EBADARG, "p2g_circuit_read: unknown buffer");
         }

@@ -17,7 +17,7 @@ P2G_OK, P2G_EBADARG, P2G_ENOMEM, P2G_ECUDA, P2G_ENCCL, P2G_EUNSAT, P2G_ESMALLBUF
 HASH_KECCAK25, HASH_POSEIDON = 0, 1
 HASHER_ID = {"keccak25": 0, "poseidon": 1, 0: 0, 1: 1}
 (BUF_WIRES_CAP, BUF_ZS_PP_CAP, BUF_QUOTIENT_CAP, BUF_CS_CAP, BUF_ZS_PP_VALUES, BUF_QUOTIENT_CHUNKS, BUF_WIRES_COEFFS,
- BUF_CHALLENGES, BUF_FINAL_POLY, BUF_FRI_CAPS, BUF_WIRES_LDE) = range(11)
+ BUF_CHALLENGES, BUF_FINAL_POLY, BUF_FRI_CAPS, BUF_WIRES_LDE, BUF_SHARD_INFO) = range(12)
 
 
 class P2GError(RuntimeError):

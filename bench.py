@@ -284,6 +284,7 @@ def main():
             sc0 = p2g.synth.SyntheticCircuit(args.degree_bits, args.workload, config=cfg, num_public_inputs=4,
                                              seed=0xAC1D + 3, pinned=True)
         sdata = p2g.CircuitData(sc0.common, sc0.constants_sigmas, device=local_rank, shard=grp)
+        shard_info = sdata.read(p2g.lib.BUF_SHARD_INFO)
         wh = sc0._wires_t
         wd = wh.cuda()
         for _ in range(args.warmup):
@@ -299,6 +300,8 @@ def main():
                    "e2e_ms_per_proof": ms_se / args.steps, "h2d_bytes_per_rank": int(souts_e[0].timings.get("h2d_bytes", 0)),
                    "collectives_per_proof": grp.calls // max(1, 2 * (args.warmup + args.steps) + 1),
                    "identical_bytes_on_all_ranks": same,
+                   "matches_single_gpu_bytes": (souts[0].to_bytes() == outs[0].to_bytes()) if rank == 0 else None,
+                   "inverse_ntt_exchange": "peer stores over NVLink, fused into the transform" if int(shard_info[3]) else "NCCL all-gather",
                    "stages_ms": {k: round(sum(o.timings[k] for o in souts) / args.steps, 3)
                                  for k in ["wires_commit_ms", "zs_pp_ms", "quotient_ms", "openings_ms", "fri_ms", "total_ms"]}}
         sdata.close()
@@ -354,7 +357,8 @@ def main():
         }
         if sharded is not None:
             line["sharded_proof"] = dict(sharded, note=f"ONE proof of the same circuit coset-sharded across the {world} GPUs "
-                                                      "(NCCL all-gathers of coefficient blocks, subtree caps, quotient values, opened rows)")
+                                                      "(trace coefficients exchanged by peer stores fused into the inverse NTT; NCCL all-gathers of subtree caps, "
+                                                      "quotient values and opened rows)")
         if not args.no_cpu_baseline and world == 1:
             bits = pick_cpu_sample_bits(p2g, args)
             dt, cores = cpu_sample_proof(p2g, args, bits, 300)

@@ -175,7 +175,10 @@ size_t p2g_proof_size_bound(const p2g_circuit* c);
  * [r * 8N/world, (r+1) * 8N/world) of every oracle = whole LDE cosets = whole Merkle-cap subtrees: their LDE, leaf and
  * subtree hashing, their share of the quotient evaluation and of the query openings.  `allgather` is called by the
  * library (same sequence on every rank) whenever ranks exchange data -- inverse-NTT column blocks, Merkle subtree caps,
- * quotient values, opened rows; the host binds it to NCCL (torch.distributed / ncclAllGather).  It must gather `bytes`
+ * quotient values, opened rows; the host binds it to NCCL (torch.distributed / ncclAllGather).  When every rank can map every
+ * other rank's coefficient buffer (CUDA IPC across processes, plain pointers inside one process) the largest exchange -- the
+ * inverse-NTT column blocks of the trace -- does not go through the callback at all: the final inverse-NTT pass stores its
+ * results straight into the peers over NVLink (P2G_BUF_SHARD_INFO reports it; P2G_NO_PEER=1 disables it).  It must gather `bytes`
  * from every rank into recv (world * bytes, rank order); send may alias recv + rank * bytes (in-place).  is_device:
  * both buffers are device memory on the handle's device, and all prior work on them has completed.  Return 0 on success.
  * Every rank passes the same desc, the same wires and public inputs to p2g_prove; all ranks return the same bytes. */
@@ -195,7 +198,8 @@ enum p2g_buffer {
     P2G_BUF_CHALLENGES = 7,     /* u64: betas[nc], gammas[nc], alphas[nc], zeta[2], fri_alpha[2], fri_betas[2*L], pow_witness, indices[q] */
     P2G_BUF_FINAL_POLY = 8,     /* ext coefficients (2 u64 each)                                                       */
     P2G_BUF_FRI_CAPS = 9,       /* num_fri_layers x 2^cap_height digests                                               */
-    P2G_BUF_WIRES_LDE = 10      /* num_wires x 8N/world u64, col-major, leaf (bit-reversed) order: this rank's leaves    */
+    P2G_BUF_WIRES_LDE = 10,     /* num_wires x 8N/world u64, col-major, leaf (bit-reversed) order: this rank's leaves    */
+    P2G_BUF_SHARD_INFO = 11     /* u64: rank, world, mapped peers, 1 if the inverse-NTT column exchange runs over peer memory */
 };
 int p2g_circuit_read(p2g_circuit* c, int what, void* out, size_t* len /* in: capacity, out: bytes */);
 

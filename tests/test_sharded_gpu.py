@@ -28,6 +28,8 @@ def test_sharded_proof_bytes_match_oracle(p2g, corc, degree_bits, workload, npi,
     def rank_main(rank, member):
         with p2g.CircuitData(sc.common, sc.constants_sigmas, device=0, shard=member) as data:
             assert data.constants_sigmas_cap == cap and data.circuit_digest == dg
+            info = data.read(p2g.lib.BUF_SHARD_INFO)
+            assert (int(info[0]), int(info[1])) == (rank, world) and int(info[3]) == 1    # peers mapped: fused exchange active
             a = data.prove(sc.wires, sc.public_inputs)
             b = data.prove(sc.wires, sc.public_inputs, timings=False)      # buffers reused
             caps = [bytes(data.read(w, np.uint8)) for w in (p2g.lib.BUF_WIRES_CAP, p2g.lib.BUF_ZS_PP_CAP, p2g.lib.BUF_QUOTIENT_CAP)]
@@ -49,3 +51,18 @@ def test_sharded_create_rejects_bad_world(p2g):
     member.world = 16      # > 2^rate_bits
     with pytest.raises(p2g.P2GError):
         p2g.CircuitData(sc.common, sc.constants_sigmas, shard=member)
+
+
+def test_sharded_without_peer_memory_uses_the_allgather(p2g, corc, monkeypatch):
+    """P2G_NO_PEER=1: the inverse-NTT column blocks go through the allgather callback instead of peer stores; same bytes."""
+    from helpers import oracle_prove_and_verify
+    monkeypatch.setenv("P2G_NO_PEER", "1")
+    sc = p2g.synth.SyntheticCircuit(12, "ecdsa", config=p2g.CircuitConfig.wide_ecc_config(), num_public_inputs=1, seed=4012)
+    ref_bytes, _ = oracle_prove_and_verify(corc, sc)
+    group = p2g.sharding.ThreadGroup(4)
+
+    def rank_main(rank, member):
+        with p2g.CircuitData(sc.common, sc.constants_sigmas, device=0, shard=member) as data:
+            assert int(data.read(p2g.lib.BUF_SHARD_INFO)[3]) == 0
+            return data.prove(sc.wires, sc.public_inputs).to_bytes()
+    assert all(b == ref_bytes for b in group.run(rank_main))
