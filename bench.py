@@ -191,7 +191,6 @@ def main():
         run_reference(args, rank, world)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_product

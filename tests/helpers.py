@@ -1,5 +1,4 @@
 """Shared test helpers: bridge between the product's CommonCircuitData and the oracle's CommonData."""
-import numpy as np
 
 
 def oracle_cd(common):

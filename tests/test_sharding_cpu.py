@@ -1,7 +1,6 @@
 """CPU coverage of the N > 1 path (world_size 2, gloo): the shard plan, the torch.distributed binding of p2g_allgather_fn
 (host buffers, in-place and out-of-place), and the property the sharding rests on -- the leaves a rank owns are whole LDE
 cosets whose Merkle subtrees end exactly at its cap entries, so all-gathering per-rank subtree caps gives the oracle's cap."""
-import ctypes as C
 import os
 import socket
 import sys
