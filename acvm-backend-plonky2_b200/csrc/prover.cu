@@ -15,6 +15,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <unistd.h>
+
+#include <thread>
 namespace {
 
 // P2G_TRACE=1: host wall-clock trace of the prove stages on stderr (debugging aid)
@@ -413,10 +415,20 @@ struct p2g_circuit {
         cudaEvent_t last = nullptr;
         bool active = false;
         double bytes = 0;
+        // pageable caller memory: chunks are first copied (multi-threaded) into a ring of pinned staging buffers, so the DMA
+        // runs at full PCIe rate instead of the driver's single-threaded bounce copy
+        static const int NSTAGE = 3;
+        u64* stage[NSTAGE] = {};
+        size_t stage_words = 0;
+        cudaEvent_t stage_free[NSTAGE] = {};
     } up;
     ~p2g_circuit() {
         for (cudaEvent_t e : up.pool) cudaEventDestroy(e);
         if (up.copy) cudaStreamDestroy(up.copy);
+        for (int i = 0; i < Upload::NSTAGE; i++) {
+            if (up.stage[i]) cudaFreeHost(up.stage[i]);
+            if (up.stage_free[i]) cudaEventDestroy(up.stage_free[i]);
+        }
         for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
         free_child_ctx(ctx);
     }
@@ -1398,10 +1410,51 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
                 }
                 return up.pool[used++];
             };
-            auto copy_cols = [&](int a, int e) {
-                CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)a * n, wires + (size_t)a * n, (size_t)(e - a) * n * 8,
-                                           cudaMemcpyHostToDevice, up.copy));
-                up.bytes += (double)(e - a) * n * 8;
+            // is the caller's buffer page-locked?  (cudaHostAlloc / p2g_host_alloc / cudaHostRegister)
+            bool pinned = false;
+            {
+                cudaPointerAttributes attr;
+                if (cudaPointerGetAttributes(&attr, wires) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+                else cudaGetLastError();
+            }
+            int slot = 0;
+            int step = std::max(1, std::min(32, (int)(((size_t)64 << 20) / (n * 8)) + 1));   // >= 64 MB per chunk ...
+            std::function<void(int, int)> copy_cols = [&](int a, int e) {
+                if (e - a > step && !pinned) {   // staging buffers hold one chunk: split longer runs
+                    for (int x = a; x < e; x += step) copy_cols(x, std::min(e, x + step));
+                    return;
+                }
+                const size_t words = (size_t)(e - a) * n;
+                const u64* src = wires + (size_t)a * n;
+                if (!pinned && words * 8 >= ((size_t)1 << 20)) {
+                    // stage through pinned memory: wait for the slot's previous DMA, fill it with 8 threads, DMA from it
+                    if (up.stage_words < words) {
+                        CUDA_CHECK(cudaStreamSynchronize(up.copy));
+                        for (int i = 0; i < p2g_circuit::Upload::NSTAGE; i++) {
+                            if (up.stage[i]) cudaFreeHost(up.stage[i]);
+                            up.stage[i] = nullptr;
+                            CUDA_CHECK(cudaHostAlloc((void**)&up.stage[i], words * 8, cudaHostAllocDefault));
+                            if (!up.stage_free[i]) CUDA_CHECK(cudaEventCreateWithFlags(&up.stage_free[i], cudaEventDisableTiming));
+                            CUDA_CHECK(cudaEventRecord(up.stage_free[i], up.copy));
+                        }
+                        up.stage_words = words;
+                    }
+                    CUDA_CHECK(cudaEventSynchronize(up.stage_free[slot]));
+                    u64* dst = up.stage[slot];
+                    const int T = 8;
+                    std::thread th[T];
+                    for (int t = 0; t < T; t++) {
+                        size_t lo = words * t / T, hi = words * (t + 1) / T;
+                        th[t] = std::thread([=] { memcpy(dst + lo, src + lo, (hi - lo) * 8); });
+                    }
+                    for (int t = 0; t < T; t++) th[t].join();
+                    CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)a * n, dst, words * 8, cudaMemcpyHostToDevice, up.copy));
+                    CUDA_CHECK(cudaEventRecord(up.stage_free[slot], up.copy));
+                    slot = (slot + 1) % p2g_circuit::Upload::NSTAGE;
+                } else {
+                    CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)a * n, src, words * 8, cudaMemcpyHostToDevice, up.copy));
+                }
+                up.bytes += (double)words * 8;
             };
             up.chunks.clear();
             up.bytes = 0;
@@ -1415,7 +1468,6 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
             ev_start = up.start;
             int c0, c1;
             column_block(C, W, &c0, &c1);
-            int step = std::max(1, std::min(32, (int)(((size_t)64 << 20) / (n * 8)) + 1));   // >= 64 MB per chunk ...
             step = std::max(step, (c1 - c0 + 7) / 8);                                         // ... and at most 8 chunks for small traces
             for (int a = c0; a < c1; a += step) {
                 int e = std::min(c1, a + step);
