@@ -91,3 +91,32 @@ def test_allgather_binding_and_cap_decomposition_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_thread_group_allgather_host_buffers(p2g):
+    """The in-process rank group used by the single-GPU sharded tests: host-buffer exchange, out-of-place and in-place."""
+    world, n = 4, 1000
+    group = p2g.sharding.ThreadGroup(world)
+
+    def rank_main(rank, member):
+        cb = member.callback()
+        mine = np.full(n, rank + 1, dtype=np.uint8)
+        out = np.zeros(n * world, dtype=np.uint8)
+        assert cb(None, mine.ctypes.data, out.ctypes.data, n, 0) == 0
+        buf = np.zeros(n * world, dtype=np.uint8)
+        buf[rank * n:(rank + 1) * n] = 10 + rank
+        assert cb(None, buf.ctypes.data + rank * n, buf.ctypes.data, n, 0) == 0
+        return out, buf
+    for out, buf in group.run(rank_main):
+        assert all((out[r * n:(r + 1) * n] == r + 1).all() and (buf[r * n:(r + 1) * n] == 10 + r).all() for r in range(world))
+
+
+def test_thread_group_propagates_rank_errors(p2g):
+    group = p2g.sharding.ThreadGroup(2)
+
+    def rank_main(rank, member):
+        if rank == 1:
+            raise RuntimeError("rank 1 failed")
+        member.allgather(0, 0, 0, False)      # would wait for rank 1 forever without the barrier abort
+    with pytest.raises(Exception):
+        group.run(rank_main)
