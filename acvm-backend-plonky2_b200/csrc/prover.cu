@@ -1414,8 +1414,13 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
             bool pinned = false;
             {
                 cudaPointerAttributes attr;
-                if (cudaPointerGetAttributes(&attr, wires) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
-                else cudaGetLastError();
+                if (cudaPointerGetAttributes(&attr, wires) == cudaSuccess) {
+                    if (attr.type == cudaMemoryTypeDevice)
+                        throw p2g_error(P2G_EBADARG, "p2g_prove: wires is device memory; use p2g_prove_device");
+                    pinned = attr.type == cudaMemoryTypeHost;
+                } else {
+                    cudaGetLastError();
+                }
             }
             int slot = 0;
             int step = std::max(1, std::min(32, (int)(((size_t)64 << 20) / (n * 8)) + 1));   // >= 64 MB per chunk ...
