@@ -141,6 +141,16 @@ def test_error_codes(p2g):
             data.prove(w, sc.public_inputs)
         assert ei.value.code == p2g.lib.P2G_EBADARG
         assert data.prove(sc.wires, sc.public_inputs).to_bytes()       # the handle stays usable after an error
+        # a device pointer handed to the host-memory entry point is refused, not dereferenced on the host
+        import ctypes as C
+        import torch
+        d_w = torch.from_numpy(sc.wires.view(np.int64)).cuda()
+        out = C.create_string_buffer(p2g.lib.lib().p2g_proof_size_bound(data._h))
+        ln = C.c_size_t(len(out))
+        pis = np.array(sc.public_inputs, dtype=np.uint64)
+        rc = p2g.lib.lib().p2g_prove(data._h, C.c_void_p(d_w.data_ptr()), pis.ctypes.data_as(C.c_void_p), len(pis), None, out,
+                                     C.byref(ln), None)
+        assert rc == p2g.lib.P2G_EBADARG and b"p2g_prove_device" in p2g.lib.lib().p2g_last_error()
 
 
 @pytest.mark.parametrize("workload,wires", [("all_gates", 234), ("ecdsa", 234), ("all_gates", 136)])
