@@ -309,8 +309,22 @@ static e2 eval_base_poly_e2(const u64* coeffs, size_t n, e2 z) {
 }
 
 /* ---------------- the prover ---------------- */
+/* ORC_TRACE=1: wall-clock seconds per stage on stderr (used to see where the CPU baseline spends its time) */
+static double orc_now(void) { return omp_get_wtime(); }
+#define ORC_MARK(what)                                                                    \
+    do {                                                                                  \
+        if (orc_trace) {                                                                  \
+            double t__ = orc_now();                                                       \
+            fprintf(stderr, "[orc] %-28s %8.3f s\n", what, t__ - orc_last);                 \
+            orc_last = t__;                                                               \
+        }                                                                                 \
+    } while (0)
+
 ORC_EXPORT int orc_prove(orc_ctx* c, const u64* wires_in, const u64* public_inputs, size_t n_pi, const u64* forced_pow,
                          u8* out, size_t* out_len) {
+    const int orc_trace = getenv("ORC_TRACE") != NULL;
+    double orc_last = orc_now();
+
     const p2g_circuit_desc* d = &c->d;
     if (n_pi != d->num_public_inputs) { snprintf(c->err, sizeof c->err, "public input count"); return P2G_EBADARG; }
     const int n = c->n, lde = c->lde, logn = d->degree_bits, loglde = logn + d->rate_bits;
@@ -325,11 +339,13 @@ ORC_EXPORT int orc_prove(orc_ctx* c, const u64* wires_in, const u64* public_inpu
     u64 pi_hash[4] = {0, 0, 0, 0};
     if (n_pi) poseidon_hash_no_pad(public_inputs, n_pi, pi_hash);
 
+    ORC_MARK("pi hash");
     /* 2. wires commitment */
     u64* wv = (u64*)malloc((size_t)W * n * 8);
     memcpy(wv, wires_in, (size_t)W * n * 8);
     batch_from_values(c, &c->wires, wv, W, logn);
 
+    ORC_MARK("wires commit");
     /* 3-4. challenger */
     challenger ch;
     ch_init(&ch, h);
@@ -340,6 +356,7 @@ ORC_EXPORT int orc_prove(orc_ctx* c, const u64* wires_in, const u64* public_inpu
     for (int i = 0; i < NC; i++) betas[i] = ch_get(&ch);
     for (int i = 0; i < NC; i++) gammas[i] = ch_get(&ch);
 
+    ORC_MARK("challenger");
     /* 5. Z and partial products (A.7) */
     int nzp = NC * (1 + NPP);
     u64* zp = (u64*)malloc((size_t)nzp * n * 8); /* [Z_0..Z_{NC-1}, PP_0[0..NPP), PP_1[0..NPP)] x N */
@@ -396,9 +413,11 @@ ORC_EXPORT int orc_prove(orc_ctx* c, const u64* wires_in, const u64* public_inpu
     batch_from_values(c, &c->zs_pp, zp, nzp, logn);
     ch_observe_cap(&ch, mtree_cap(&c->zs_pp.tree), mtree_ncap(&c->zs_pp.tree));
 
+    ORC_MARK("z/pp + commit");
     /* 6. alphas */
     for (int i = 0; i < NC; i++) alphas[i] = ch_get(&ch);
 
+    ORC_MARK("alphas");
     /* 7. quotient (A.8) */
     int nq = NC * QDF;
     u64* qv = (u64*)malloc((size_t)NC * lde * 8); /* natural order values per challenge */
@@ -470,12 +489,14 @@ ORC_EXPORT int orc_prove(orc_ctx* c, const u64* wires_in, const u64* public_inpu
     batch_from_coeffs(c, &c->quot, qc, nq, logn);
     ch_observe_cap(&ch, mtree_cap(&c->quot.tree), mtree_ncap(&c->quot.tree));
 
+    ORC_MARK("quotient + commit");
     /* 8. zeta */
     e2 zeta = ch_get_e2(&ch);
     if (e2_eq(e2_pow(zeta, n), e2_make(1, 0))) { snprintf(c->err, sizeof c->err, "Opening point is in the subgroup."); return P2G_EUNSAT; }
     u64 g = gl_root_of_unity(logn);
     e2 zeta_next = e2_mul_base(zeta, g);
 
+    ORC_MARK("zeta");
     /* 9. openings (A.9) */
     batch* oracles[4] = {&c->cs, &c->wires, &c->zs_pp, &c->quot};
     int widths[4] = {C + R, W, nzp, nq};
@@ -496,6 +517,7 @@ ORC_EXPORT int orc_prove(orc_ctx* c, const u64* wires_in, const u64* public_inpu
     for (int i = 0; i < total; i++) ch_observe_e2(&ch, op[i]);
     for (int cc = 0; cc < NC; cc++) ch_observe_e2(&ch, zs_next[cc]);
 
+    ORC_MARK("openings");
     /* 10. FRI (A.10) */
     e2 fri_alpha = ch_get_e2(&ch);
     e2* fin = (e2*)calloc((size_t)lde, sizeof(e2)); /* final_poly coefficients, padded to lde */
