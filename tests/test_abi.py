@@ -46,3 +46,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle|liborc", txt, flags=re.M), f
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: the header must compile as C (no C++-isms, no torch / CUDA types in the signatures)."""
+    import subprocess
+    src = tmp_path / "use_p2g.c"
+    src.write_text('#include "p2g.h"\n'
+                   'int main(void) { p2g_circuit_desc d; d.struct_size = (uint32_t)sizeof d; (void)d;\n'
+                   '  return p2g_version() == P2G_VERSION && p2g_last_error() != 0 ? 0 : 1; }\n')
+    exe = tmp_path / "use_p2g"
+    libdir = os.path.join(ROOT, "acvm-backend-plonky2_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libp2g.so", "-Wl,-rpath," + libdir])
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "p2g.h")).read(), flags=re.S)   # declarations only
+    assert "torch" not in hdr and "cudaStream" not in hdr and "std::" not in hdr
+    assert subprocess.run([str(exe)]).returncode == 0        # p2g_version / p2g_last_error need no GPU
