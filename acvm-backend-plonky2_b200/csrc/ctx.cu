@@ -67,25 +67,46 @@ DevCtx* new_child_ctx(int device) {
 void free_child_ctx(DevCtx* c) {
     if (!c || !c->parent) return;
     cudaStreamSynchronize(c->stream);
+    resolve_timers(c);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
 
+// Stage timers never block the host: both events are recorded on the stream and parked in the context; resolve_timers() reads
+// them once, after the proof's final synchronisation.  (Round 1 synchronised in the destructor, which serialised the host
+// against the device whenever a caller asked for timings.)
+static cudaEvent_t timer_event(DevCtx* c) {
+    if (!c->ev_pool.empty()) {
+        cudaEvent_t e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
 StageTimer::StageTimer(DevCtx* ctx, float* accum) : c(ctx), acc(accum) {
     if (!c->timing) return;
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
+    a = timer_event(c);
+    b = timer_event(c);
     cudaEventRecord(a, c->stream);
 }
 StageTimer::~StageTimer() {
     if (!a) return;
     cudaEventRecord(b, c->stream);
-    cudaEventSynchronize(b);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    *acc += ms;
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
+    c->ev_pending.emplace_back(a, b, acc);
+}
+void resolve_timers(DevCtx* c) {
+    for (auto& t : c->ev_pending) {
+        cudaEvent_t a = std::get<0>(t), b = std::get<1>(t);
+        float ms = 0;
+        if (cudaEventSynchronize(b) == cudaSuccess && cudaEventElapsedTime(&ms, a, b) == cudaSuccess) *std::get<2>(t) += ms;
+        else cudaGetLastError();
+        c->ev_pool.push_back(a);
+        c->ev_pool.push_back(b);
+    }
+    c->ev_pending.clear();
 }
 
 int guard(const std::function<void()>& f) {
@@ -166,7 +187,7 @@ extern "C" int p2g_merkle_cap(const uint64_t* leaves_colmajor, uint32_t log_leav
         dbuf<u64> in(nl * ncols);
         CUDA_CHECK(cudaMemcpyAsync(in.p, leaves_colmajor, nl * ncols * 8, cudaMemcpyHostToDevice, c->stream));
         MerkleTree t;
-        merkle_build(c, &t, in.p, nl, (int)log_leaves, (int)ncols, (int)cap_height, (int)hasher);
+        merkle_build(c, &t, in.p, nl, (int)log_leaves, (int)ncols, (int)cap_height, (int)hasher, false, true);
         std::vector<digest_t> cap(t.ncap());
         CUDA_CHECK(cudaMemcpyAsync(cap.data(), t.cap(), sizeof(digest_t) * cap.size(), cudaMemcpyDeviceToHost, c->stream));
         std::vector<digest_t> lv;

@@ -70,10 +70,12 @@ struct DevCtx {
     // accounting of the current prove call
     unsigned launches = 0;
     double ntt_bytes = 0, merkle_bytes = 0;
-    float ntt_ms = 0, merkle_ms = 0, leaf_ms = 0, lde_ms = 0;
+    float ntt_ms = 0, merkle_ms = 0, leaf_ms = 0, lde_ms = 0, quot_ms = 0;
     double leaf_bytes = 0, lde_bytes = 0;
     unsigned leaf_launches = 0, lde_launches = 0;
-    bool timing = false;  // when set, NTT / Merkle entry points bracket themselves with events (adds syncs)
+    bool timing = false;  // when set, NTT / Merkle entry points bracket themselves with events (recorded, not waited on)
+    std::vector<cudaEvent_t> ev_pool;                                       // reusable timing events
+    std::vector<std::tuple<cudaEvent_t, cudaEvent_t, float*>> ev_pending;   // recorded pairs, read by resolve_timers()
 
     const u64* get_tw(int log, bool inverse);
     const u64* get_twist(int logB, bool inverse, int* split);
@@ -86,7 +88,8 @@ DevCtx* get_ctx(int device);          // the device's root context
 DevCtx* new_child_ctx(int device);    // own stream, shares the root's tables
 void free_child_ctx(DevCtx* c);
 
-struct StageTimer {  // RAII: accumulates elapsed ms of a stream segment into *acc when ctx->timing is on
+void resolve_timers(DevCtx* c);   // after a stream synchronisation: adds every recorded segment to its accumulator
+struct StageTimer {  // RAII: accumulates elapsed ms of a stream segment into *acc when ctx->timing is on (no host sync)
     DevCtx* c;
     float* acc;
     cudaEvent_t a = nullptr, b = nullptr;
@@ -121,7 +124,7 @@ struct MerkleTree {
 // leaves: column-major [ncols][nleaves] (leaf j = {col_0[j], col_1[j], ...}); interleave2: leaf = `ncols/2` consecutive
 // (c0,c1) pairs taken from two columns re/im at positions [j*ncols/2, (j+1)*ncols/2)  (FRI layer leaves)
 void merkle_build(DevCtx* c, MerkleTree* t, const u64* d_leaves, size_t col_stride, int log_leaves, int ncols,
-                  int cap_height, int hasher, bool fri_layout = false);
+                  int cap_height, int hasher, bool fri_layout = false, bool allow_clamp = false);
 
 // ---- launch helper ----
 inline void count_launch(DevCtx* c, unsigned n = 1) { c->launches += n; }

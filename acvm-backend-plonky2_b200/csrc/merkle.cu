@@ -101,9 +101,13 @@ __global__ void __launch_bounds__(128) k_nodes(int h, const digest_t* __restrict
 }  // namespace
 
 void merkle_build(DevCtx* c, MerkleTree* t, const u64* d_leaves, size_t col_stride, int log_leaves, int ncols, int cap_height,
-                  int hasher, bool fri_layout) {
+                  int hasher, bool fri_layout, bool allow_clamp) {
     StageTimer tm(c, &c->merkle_ms);
-    if (cap_height > log_leaves) cap_height = log_leaves;
+    if (cap_height > log_leaves) {
+        // plonky2's MerkleTree::new asserts here; only the stand-alone test entry point (p2g_merkle_cap) may clamp
+        if (!allow_clamp) throw p2g_error(P2G_EBADARG, "merkle_build: fewer than 2^cap_height leaves");
+        cap_height = log_leaves;
+    }
     t->log_leaves = log_leaves;
     t->cap_height = cap_height;
     t->hasher = hasher;

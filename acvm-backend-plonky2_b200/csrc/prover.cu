@@ -578,13 +578,28 @@ void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_
 }
 // the 2^cap_height cap of an oracle: this rank's subtree roots, all-gathered when sharded (the one collective of the
 // commitment)
-std::vector<digest_t> read_cap(p2g_circuit* C, const MerkleTree& t, bool sharded = true) {
-    std::vector<digest_t> mine(t.ncap());
-    CUDA_CHECK(cudaMemcpyAsync(mine.data(), t.cap(), sizeof(digest_t) * mine.size(), cudaMemcpyDeviceToHost, C->ctx->stream));
+// `status` (optional, sharded proofs): a rank-local failure flag that travels with the cap.  On return it holds the OR over all
+// ranks, so every rank takes the same decision before the next collective (a rank that threw on its own would leave the
+// others blocked in it).
+std::vector<digest_t> read_cap(p2g_circuit* C, const MerkleTree& t, bool sharded = true, int* status = nullptr) {
+    std::vector<digest_t> mine(t.ncap() + 1);
+    CUDA_CHECK(cudaMemcpyAsync(mine.data(), t.cap(), sizeof(digest_t) * t.ncap(), cudaMemcpyDeviceToHost, C->ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));
-    if (C->world == 1 || !sharded) return mine;
-    std::vector<digest_t> cap(mine.size() * C->world);
-    shard_allgather(C, mine.data(), cap.data(), sizeof(digest_t) * mine.size(), false);
+    if (C->world == 1 || !sharded) {
+        mine.pop_back();
+        return mine;
+    }
+    memset(&mine.back(), 0, sizeof(digest_t));
+    mine.back().w[0] = status ? (u64)*status : 0;
+    const size_t per = mine.size();
+    std::vector<digest_t> all(per * C->world), cap;
+    shard_allgather(C, mine.data(), all.data(), sizeof(digest_t) * per, false);
+    int any = 0;
+    for (int r = 0; r < C->world; r++) {
+        cap.insert(cap.end(), all.begin() + r * per, all.begin() + r * per + (per - 1));
+        any |= (int)all[r * per + per - 1].w[0];
+    }
+    if (status) *status = any;
     return cap;
 }
 
@@ -628,12 +643,57 @@ void validate_desc(const p2g_circuit_desc* d) {
         red += d->reduction_arity_bits[i];
     }
     if (red > d->degree_bits) bad("FRI schedule longer than the polynomial");
+    if (d->num_selectors > d->num_constants) bad("num_selectors > num_constants");
+    if (d->pow_bits > 64) bad("pow_bits > 64");
+    if (d->cap_height > d->degree_bits + d->rate_bits) bad("cap_height exceeds the LDE tree height");
+    {   // every FRI layer's tree must have at least 2^cap_height leaves (plonky2's MerkleTree::new asserts the same)
+        u32 bits = d->degree_bits + d->rate_bits;
+        for (u32 i = 0; i < d->num_fri_layers; i++) {
+            bits -= d->reduction_arity_bits[i];
+            if (bits < d->cap_height) bad("FRI layer has fewer than 2^cap_height leaves");
+        }
+    }
     for (u32 g = 0; g < d->num_gates; g++) {
         const p2g_gate& gt = d->gates[g];
         if (gt.kind >= P2G_GATE_KIND_COUNT) bad("unknown gate kind");
         if (gt.selector_index >= d->num_selectors || gt.group_lo > g || gt.group_hi <= g || gt.group_hi > d->num_gates) bad("selector data");
+        // wires / gate-local constants / constraints implied by (kind, params): the same formulas as circuit.py and p2g.hpp
+        const u32* p = gt.params;
+        uint64_t rw = 0, rc = 0, nk = 0;
+        switch (gt.kind) {
+        case P2G_GATE_NOOP: break;
+        case P2G_GATE_CONSTANT: rw = rc = nk = p[0]; break;
+        case P2G_GATE_PUBLIC_INPUT: rw = nk = 4; break;
+        case P2G_GATE_ARITHMETIC: rw = 4ull * p[0]; rc = 2; nk = p[0]; break;
+        case P2G_GATE_BASE_SUM:
+            if (p[0] < 2 || p[0] > 256) bad("BaseSumGate base out of range");
+            rw = 1ull + p[1]; nk = 1ull + p[1];
+            break;
+        case P2G_GATE_POSEIDON: rw = 135; nk = 123; break;
+        case P2G_GATE_RANDOM_ACCESS:
+            if (p[0] > 6) bad("RandomAccessGate bits > 6");
+            rw = (2ull + (1ull << p[0])) * p[1] + p[2] + (uint64_t)p[1] * p[0];
+            rc = p[2];
+            nk = (p[0] + 2ull) * p[1] + p[2];
+            break;
+        case P2G_GATE_U32_ARITHMETIC: rw = 38ull * p[0]; nk = 36ull * p[0]; break;
+        case P2G_GATE_U32_ADD_MANY: rw = (p[0] + 3ull) * p[1] + 18ull * p[1]; nk = 21ull * p[1]; break;
+        case P2G_GATE_U32_SUBTRACTION: rw = 21ull * p[0]; nk = 19ull * p[0]; break;
+        case P2G_GATE_U32_RANGE_CHECK: rw = 17ull * p[0]; nk = 17ull * p[0]; break;
+        case P2G_GATE_COMPARISON: {
+            if (p[1] == 0 || p[0] == 0) bad("ComparisonGate num_bits / num_chunks must be positive");
+            const uint64_t cb = (p[0] + p[1] - 1) / p[1];
+            if (cb > 8) bad("ComparisonGate chunk bits > 8");
+            rw = 4 + 5ull * p[1] + cb + 1;
+            nk = 6 + 5ull * p[1] + cb;
+            break;
+        }
+        default: break;
+        }
+        if (rw > d->num_wires) bad("gate needs more wires than num_wires");
+        if (rc + d->num_selectors > d->num_constants) bad("gate needs more constants than num_constants - num_selectors");
+        if (nk != gt.num_constraints) bad("gate num_constraints does not match (kind, params)");
         if (gt.num_constraints > d->num_gate_constraints) bad("gate num_constraints > num_gate_constraints");
-        if (gt.kind == P2G_GATE_RANDOM_ACCESS && gt.params[0] > 6) bad("RandomAccessGate bits > 6");
     }
 }
 
@@ -848,7 +908,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         }
         CUDA_CHECK(cudaMemcpyAsync(&bad_wire, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     }
-    std::vector<digest_t> wires_cap = read_cap(C, C->wires.tree);   // synchronises the stream
+    std::vector<digest_t> wires_cap = read_cap(C, C->wires.tree, true, &bad_wire);   // synchronises the stream; flag OR-ed over ranks
     if (bad_wire) throw p2g_error(P2G_EBADARG, "p2g_prove: non-canonical wire value (>= p)");
     CUDA_CHECK(cudaEventRecord(ev[1], st));
     tr.mark("wires commit");
@@ -903,7 +963,6 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     for (int i = 0; i < NC; i++) alphas[i] = ch.get();
 
     // 7. quotient
-    float quotient_kernel_ms = 0;
     {
         static thread_local QuotientParams qp;
         memset(&qp, 0, sizeof(qp));
@@ -932,20 +991,14 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         // quotient values land in quot.lde's first NC columns region?  No: they are transformed in place into the
         // chunk coefficients, so evaluate straight into quot.coeffs viewed as [NC][8N]
         u64* qv = C->quot.coeffs.p;
-        cudaEvent_t qa, qb;
-        CUDA_CHECK(cudaEventCreate(&qa));
-        CUDA_CHECK(cudaEventCreate(&qb));
-        CUDA_CHECK(cudaEventRecord(qa, st));
-        quotient_eval(c, qp, C->cs.lde.p, C->wires.lde.p, C->zpp.lde.p, C->xs.p, C->l0s.p, qv, C->lde_l, C->j0, lde);
-        CUDA_CHECK(cudaEventRecord(qb, st));
+        {
+            StageTimer tq(c, &c->quot_ms);
+            quotient_eval(c, qp, C->cs.lde.p, C->wires.lde.p, C->zpp.lde.p, C->xs.p, C->l0s.p, qv, C->lde_l, C->j0, lde);
+        }
         if (C->world > 1)   // every rank needs all 8N quotient values for the size-8N inverse transform
             for (int cc = 0; cc < NC; cc++)
                 shard_allgather(C, qv + (size_t)cc * lde + C->j0, qv + (size_t)cc * lde, C->lde_l * 8, true);
         ntt_coset_ifft_leaforder(c, qv, lde, C->loglde, NC, GL_GEN);
-        CUDA_CHECK(cudaEventSynchronize(qb));
-        cudaEventElapsedTime(&quotient_kernel_ms, qa, qb);
-        cudaEventDestroy(qa);
-        cudaEventDestroy(qb);
         // [NC][8N] coefficients == [NC*QDF][N] chunk polynomials
         commit_from_coeffs(C, C->quot);
     }
@@ -1339,6 +1392,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     C->last_caps[2] = quot_cap;
     C->proved = true;
 
+    resolve_timers(c);
     if (tm) {
         float t;
         cudaEventElapsedTime(&t, ev[0], ev[1]); tm->wires_commit_ms = t;
@@ -1349,7 +1403,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         cudaEventElapsedTime(&t, ev[5], ev[6]); tm->d2h_ms = t;
         cudaEventElapsedTime(&t, ev_start ? ev_start : ev[0], ev[6]); tm->total_ms = t;
         if (ev_start && C->up.last) { cudaEventElapsedTime(&t, ev_start, C->up.last); tm->h2d_ms = t; } else tm->h2d_ms = 0;
-        tm->quotient_kernel_ms = quotient_kernel_ms;
+        tm->quotient_kernel_ms = c->quot_ms;
         tm->ntt_ms = c->ntt_ms;
         tm->merkle_ms = c->merkle_ms;
         tm->ntt_bytes = c->ntt_bytes;
@@ -1376,12 +1430,16 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
         if (n_pi != C->d.num_public_inputs) throw p2g_error(P2G_EBADARG, "p2g_prove: public input count");
         for (size_t i = 0; i < n_pi; i++)
             if (public_inputs[i] >= GL_P) throw p2g_error(P2G_EBADARG, "p2g_prove: non-canonical public input");
+        if (!out) {   // size query: answered from the bound, nothing is proved
+            *out_len = p2g_proof_size_bound(C);
+            throw p2g_error(P2G_ESMALLBUF, "p2g_prove: out is NULL; *out_len holds a sufficient buffer size");
+        }
         std::lock_guard<std::mutex> lk(C->mu);
         DevCtx* c = C->ctx;
         CUDA_CHECK(cudaSetDevice(c->device));
         c->launches = 0;
         c->ntt_bytes = c->merkle_bytes = c->leaf_bytes = c->lde_bytes = 0;
-        c->ntt_ms = c->merkle_ms = c->leaf_ms = c->lde_ms = 0;
+        c->ntt_ms = c->merkle_ms = c->leaf_ms = c->lde_ms = c->quot_ms = 0;
         c->leaf_launches = c->lde_launches = 0;
         c->timing = tm != nullptr;
         if (tm) memset(tm, 0, sizeof(*tm));

@@ -38,10 +38,43 @@ def build(force=False):
     return so
 
 
-def lib():
-    global _LIB
+_NATIVE_NOTE = "generic x86-64 build (-O3)"
+
+
+def build_native():
+    """CPU-baseline build: the same sources with -march=native, compiled ON THE MACHINE THAT RUNS IT (the .so is keyed by the
+    host's CPU flags, so a library built in the development container is never executed on a different CPU).  Returns the
+    path, or None when no compiler is available (the portable build is used instead and the bench line says so)."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    key = hashlib.sha256(flags.encode()).hexdigest()[:12]
+    out_dir = os.path.join(_HERE, "_native")
+    so = os.path.join(out_dir, f"liborc_native_{key}.so")
+    srcs = [os.path.join(_HERE, "c", f) for f in os.listdir(os.path.join(_HERE, "c"))]
+    if os.path.exists(so) and all(os.path.getmtime(s) <= os.path.getmtime(so) for s in srcs):
+        return so
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["make", "-C", _HERE, "-s", "native", f"NATIVE_OUT={so}"])
+        return so
+    except Exception:
+        return None
+
+
+def lib(native=False):
+    """native=True (bench.py's CPU arms only, before any other use in the process): load the -march=native build."""
+    global _LIB, _NATIVE_NOTE
     if _LIB is None:
-        _LIB = C.CDLL(build())
+        path = None
+        if native:
+            path = build_native()
+            if path:
+                _NATIVE_NOTE = "built on this host with gcc -O3 -march=native -funroll-loops, OpenMP"
+        _LIB = C.CDLL(path or build())
         _LIB.orc_last_error.restype = C.c_char_p
         _LIB.orc_last_error.argtypes = [C.c_void_p]
         _LIB.orc_destroy.argtypes = [C.c_void_p]
@@ -221,3 +254,7 @@ def eval_gate_constraints(cd, constants, wires, pi_hash):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def build_note():
+    return _NATIVE_NOTE
