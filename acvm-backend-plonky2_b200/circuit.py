@@ -349,6 +349,23 @@ class CircuitData:
         return self._run(_lib.lib().p2g_prove, w.ctypes.data_as(C.c_void_p), public_inputs, forced_pow_witness, timings,
                          0 if compressed else None)
 
+    def prove_columns(self, wire_columns, public_inputs=(), forced_pow_witness=None, timings=True, compressed=False):
+        """`wire_columns`: num_wires separate 1-D uint64 arrays of N values each -- `MatrixWitness.wire_values` as plonky2 holds
+        it (`Vec<Vec<F>>`, one allocation per column), handed over as column pointers without building a flat copy."""
+        W, n = self.common.config.num_wires, self.common.degree()
+        if len(wire_columns) != W:
+            raise ValueError(f"expected {W} wire columns, got {len(wire_columns)}")
+        cols = []
+        for c in wire_columns:
+            a = np.ascontiguousarray(c, dtype=np.uint64)
+            if a.shape != (n,):
+                raise ValueError(f"every wire column must have shape ({n},), got {a.shape}")
+            cols.append(a)
+        ptrs = (C.c_void_p * W)(*[a.ctypes.data for a in cols])
+        fn = lambda h, _w, pis, npi, fp, out, ln, tm: _lib.lib().p2g_prove_columns(h, ptrs, pis, npi, fp, 1 if compressed else 0,
+                                                                                   out, ln, tm)
+        return self._run(fn, None, public_inputs, forced_pow_witness, timings, None)
+
     def read(self, what, dtype=np.uint64):
         """Intermediates of the last proof (enum p2g_buffer), for parity tests."""
         ln = C.c_size_t(0)

@@ -345,6 +345,157 @@ __device__ __forceinline__ void eval_gate_kind(const GateDev& g, u32 op_lo, u32 
     }
 }
 
+// sum_j limb_j 4^j by Horner with shifts, exact in 96 bits (up to 16 limbs of 64 bits): acc = 4 acc + l is two funnel
+// shifts, one shift and a 96-bit add -- no multiply -- and one reduction at the end.
+struct gl_h4 {
+    u32 w0, w1, w2;
+    __device__ __forceinline__ void clear() { w0 = w1 = w2 = 0; }
+    __device__ __forceinline__ void push(u64 l) {   // l: any u64
+        w2 = __funnelshift_l(w1, w2, 2);
+        w1 = __funnelshift_l(w0, w1, 2);
+        w0 <<= 2;
+        asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+            : "+r"(w0), "+r"(w1), "+r"(w2) : "r"((u32)l), "r"((u32)(l >> 32)));
+    }
+    __device__ __forceinline__ u64 reduce() const { return gl_reduce128((u64)w2, ((u64)w1 << 32) | w0); }   // -> C
+};
+
+// true for the gates whose 2-bit limb range checks l(l-1)(l-2)(l-3) are evaluated by the limb sweep of quotient.cu
+__host__ __device__ inline bool gate_has_limb4_sweep(u32 kind, const u32* p) {
+    switch (kind) {
+    case P2G_GATE_U32_ARITHMETIC: case P2G_GATE_U32_ADD_MANY: case P2G_GATE_U32_SUBTRACTION: case P2G_GATE_U32_RANGE_CHECK:
+        return gate_num_ops(kind, p) > 0;
+    case P2G_GATE_BASE_SUM: return p[0] == 4 && p[1] >= 1 && p[1] <= 16;
+    default: return false;
+    }
+}
+
+// The same gates WITHOUT their limb range checks (those come from the sweep): every other constraint, with the reference's
+// numbering (arithmetic_u32.rs:289-348, add_many_u32.rs:151-192, subtraction_u32.rs:234-271, range_check_u32.rs:95-117; plonky2
+// gates/base_sum.rs).  Limb recombinations use gl_h4.
+template <int KIND, class W, class S>
+__device__ __forceinline__ void eval_gate_nonlimb(const GateDev& g, const W& w, S& sink) {
+    const u32* p = g.params;
+    switch (KIND) {
+    case P2G_GATE_BASE_SUM: {
+        const u32 nl = p[1];
+        gl_h4 sum;
+        sum.clear();
+        for (int k = (int)nl - 1; k >= 0; k--) sum.push(w(1 + k));
+        sink.seek(0);
+        sink.emit(gl_sub(sum.reduce(), w(0)));
+        break;
+    }
+    case P2G_GATE_U32_ARITHMETIC: {
+        const u32 ops = p[0];
+        for (u32 i = 0; i < ops; i++) {
+            const u32 q = 6 * i;
+            u64 computed = gl_add(gl_mul(w(q), w(q + 1)), w(q + 2));
+            u64 lo = w(q + 3), hi = w(q + 4), inv = w(q + 5);
+            u64 hi_not_max = gl_sub(gl_mul(inv, gl_sub(0xFFFFFFFFULL, hi)), 1);
+            sink.seek(36 * i);
+            sink.emit(glz_mul(hi_not_max, lo));
+            sink.emit(gl_sub(gl_add(gl_mul(hi, 1ULL << 32), lo), computed));
+            const u32 lw = 6 * ops + 32 * i;
+            gl_h4 clo, chi;
+            clo.clear();
+            chi.clear();
+#pragma unroll 1
+            for (int b = 1; b >= 0; b--) {   // batches of 8 + 8 independent loads
+                u64 A[8], B[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    A[j] = w(lw + 8 * b + j);
+                    B[j] = w(lw + 16 + 8 * b + j);
+                }
+#pragma unroll
+                for (int j = 7; j >= 0; j--) {
+                    clo.push(A[j]);
+                    chi.push(B[j]);
+                }
+            }
+            sink.seek(36 * i + 34);
+            sink.emit(gl_sub(clo.reduce(), lo));
+            sink.emit(gl_sub(chi.reduce(), hi));
+        }
+        break;
+    }
+    case P2G_GATE_U32_ADD_MANY: {
+        const u32 na = p[0], ops = p[1];
+        for (u32 i = 0; i < ops; i++) {
+            const u32 q = (na + 3) * i;
+            u64 computed = 0;
+            for (u32 j = 0; j <= na; j++) computed = gl_add(computed, w(q + j));  // addends then carry-in
+            u64 res = w(q + na + 1), carry = w(q + na + 2);
+            sink.seek(21 * i);
+            sink.emit(gl_sub(gl_add(gl_mul(carry, 1ULL << 32), res), computed));
+            const u32 lw = (na + 3) * ops + 18 * i;
+            gl_h4 cres;
+            cres.clear();
+#pragma unroll 1
+            for (int b = 1; b >= 0; b--) {
+                u64 A[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) A[j] = w(lw + 8 * b + j);
+#pragma unroll
+                for (int j = 7; j >= 0; j--) cres.push(A[j]);
+            }
+            u64 l16 = w(lw + 16), l17 = w(lw + 17);
+            sink.seek(21 * i + 19);
+            sink.emit(gl_sub(cres.reduce(), res));
+            sink.emit(gl_sub(gl_add(glz_mul_small(l17, 4), l16), carry));
+        }
+        break;
+    }
+    case P2G_GATE_U32_SUBTRACTION: {
+        const u32 ops = p[0];
+        for (u32 i = 0; i < ops; i++) {
+            const u32 q = 5 * i;
+            u64 initial = gl_sub(gl_sub(w(q), w(q + 1)), w(q + 2));
+            u64 res = w(q + 3), bout = w(q + 4);
+            sink.seek(19 * i);
+            sink.emit(gl_sub(res, gl_add(initial, gl_mul(bout, 1ULL << 32))));
+            const u32 lw = 5 * ops + 16 * i;
+            gl_h4 comb;
+            comb.clear();
+#pragma unroll 1
+            for (int b = 1; b >= 0; b--) {
+                u64 A[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) A[j] = w(lw + 8 * b + j);
+#pragma unroll
+                for (int j = 7; j >= 0; j--) comb.push(A[j]);
+            }
+            sink.seek(19 * i + 17);
+            sink.emit(gl_sub(comb.reduce(), res));
+            sink.emit(glz_mul(bout, gl_sub(1, bout)));
+        }
+        break;
+    }
+    case P2G_GATE_U32_RANGE_CHECK: {
+        const u32 nl = p[0];
+        for (u32 i = 0; i < nl; i++) {
+            const u32 aw = nl + 16 * i;
+            gl_h4 comb;
+            comb.clear();
+#pragma unroll 1
+            for (int b = 1; b >= 0; b--) {
+                u64 A[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) A[j] = w(aw + 8 * b + j);
+#pragma unroll
+                for (int j = 7; j >= 0; j--) comb.push(A[j]);
+            }
+            sink.seek(17 * i);
+            sink.emit(gl_sub(comb.reduce(), w(i)));
+        }
+        break;
+    }
+    default:
+        break;
+    }
+}
+
 // runtime-kind dispatch (stand-alone gate evaluation)
 template <class W, class K, class S>
 __device__ void eval_gate_unfiltered(const GateDev& g, u32 op_lo, u32 op_hi, const W& w, const K& c, const u64* pi_hash, S& sink) {

@@ -978,7 +978,8 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             qp.betas[cc] = betas[cc];
             qp.gammas[cc] = gammas[cc];
             for (int r = 0; r < R; r++) qp.beta_k[cc][r] = gl_mul(betas[cc], C->k_is[r]);
-            int nterms = NC * (2 + NPP) + d.num_gate_constraints;
+            // alpha^k for every constraint term, and at least up to num_wires (the limb sweep weights wire w by alpha^w)
+            int nterms = std::min<int>(P2G_MAX_TERMS, std::max<int>(NC * (2 + NPP) + d.num_gate_constraints, W));
             u64 a = 1;
             for (int k = 0; k < nterms; k++) {
                 qp.apow[cc][k] = a;
@@ -993,7 +994,9 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         u64* qv = C->quot.coeffs.p;
         {
             StageTimer tq(c, &c->quot_ms);
-            quotient_eval(c, qp, C->cs.lde.p, C->wires.lde.p, C->zpp.lde.p, C->xs.p, C->l0s.p, qv, C->lde_l, C->j0, lde);
+            static thread_local LimbPlan lp;
+            const bool sweep = quotient_limb_plan(qp, W, alphas, &lp);
+            quotient_eval(c, qp, sweep ? &lp : nullptr, C->cs.lde.p, C->wires.lde.p, C->zpp.lde.p, C->xs.p, C->l0s.p, qv, C->lde_l, C->j0, lde);
         }
         if (C->world > 1)   // every rank needs all 8N quotient values for the size-8N inverse transform
             for (int cc = 0; cc < NC; cc++)
@@ -1423,10 +1426,16 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     if (small) throw p2g_error(P2G_ESMALLBUF, "output buffer too small");
 }
 
+// wires: one [W][N] block (host or device), or cols: W pointers to N-element host columns (MatrixWitness.wire_values as plonky2
+// holds it) -- exactly one of the two
 static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u64* public_inputs, size_t n_pi,
-                       const u64* forced_pow, uint8_t* out, size_t* out_len, p2g_timings* tm, bool compressed = false) {
+                       const u64* forced_pow, uint8_t* out, size_t* out_len, p2g_timings* tm, bool compressed = false,
+                       const u64* const* cols = nullptr) {
     return guard([&] {
-        if (!C || !wires || !out_len || (n_pi && !public_inputs)) throw p2g_error(P2G_EBADARG, "p2g_prove: null argument");
+        if (!C || (!wires && !cols) || !out_len || (n_pi && !public_inputs)) throw p2g_error(P2G_EBADARG, "p2g_prove: null argument");
+        if (cols)
+            for (u32 i = 0; i < C->d.num_wires; i++)
+                if (!cols[i]) throw p2g_error(P2G_EBADARG, "p2g_prove_columns: null column pointer");
         if (n_pi != C->d.num_public_inputs) throw p2g_error(P2G_EBADARG, "p2g_prove: public input count");
         for (size_t i = 0; i < n_pi; i++)
             if (public_inputs[i] >= GL_P) throw p2g_error(P2G_EBADARG, "p2g_prove: non-canonical public input");
@@ -1469,17 +1478,19 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
                 return up.pool[used++];
             };
             // is the caller's buffer page-locked?  (cudaHostAlloc / p2g_host_alloc / cudaHostRegister)
-            bool pinned = false;
-            {
+            bool pinned = true;
+            for (int i = 0; i < (cols ? W : 1); i++) {
                 cudaPointerAttributes attr;
-                if (cudaPointerGetAttributes(&attr, wires) == cudaSuccess) {
+                if (cudaPointerGetAttributes(&attr, cols ? cols[i] : wires) == cudaSuccess) {
                     if (attr.type == cudaMemoryTypeDevice)
                         throw p2g_error(P2G_EBADARG, "p2g_prove: wires is device memory; use p2g_prove_device");
-                    pinned = attr.type == cudaMemoryTypeHost;
+                    pinned = pinned && attr.type == cudaMemoryTypeHost;
                 } else {
                     cudaGetLastError();
+                    pinned = false;
                 }
             }
+            auto col_ptr = [&](int col) { return cols ? cols[col] : wires + (size_t)col * n; };
             int slot = 0;
             int step = std::max(1, std::min(32, (int)(((size_t)64 << 20) / (n * 8)) + 1));   // >= 64 MB per chunk ...
             std::function<void(int, int)> copy_cols = [&](int a, int e) {
@@ -1488,7 +1499,6 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
                     return;
                 }
                 const size_t words = (size_t)(e - a) * n;
-                const u64* src = wires + (size_t)a * n;
                 if (!pinned && words * 8 >= ((size_t)1 << 20)) {
                     // stage through pinned memory: wait for the slot's previous DMA, fill it with 8 threads, DMA from it
                     if (up.stage_words < words) {
@@ -1507,15 +1517,25 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
                     const int T = 8;
                     std::thread th[T];
                     for (int t = 0; t < T; t++) {
+                        // words [lo, hi) of the chunk, column by column (the columns need not be adjacent in host memory)
                         size_t lo = words * t / T, hi = words * (t + 1) / T;
-                        th[t] = std::thread([=] { memcpy(dst + lo, src + lo, (hi - lo) * 8); });
+                        th[t] = std::thread([=] {
+                            for (size_t x = lo; x < hi;) {
+                                const size_t col = x / n, r = x % n, run = std::min(n - r, hi - x);
+                                memcpy(dst + x, col_ptr(a + (int)col) + r, run * 8);
+                                x += run;
+                            }
+                        });
                     }
                     for (int t = 0; t < T; t++) th[t].join();
                     CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)a * n, dst, words * 8, cudaMemcpyHostToDevice, up.copy));
                     CUDA_CHECK(cudaEventRecord(up.stage_free[slot], up.copy));
                     slot = (slot + 1) % p2g_circuit::Upload::NSTAGE;
+                } else if (!cols) {
+                    CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)a * n, col_ptr(a), words * 8, cudaMemcpyHostToDevice, up.copy));
                 } else {
-                    CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)a * n, src, words * 8, cudaMemcpyHostToDevice, up.copy));
+                    for (int x = a; x < e; x++)
+                        CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)x * n, col_ptr(x), n * 8, cudaMemcpyHostToDevice, up.copy));
                 }
                 up.bytes += (double)words * 8;
             };
@@ -1566,6 +1586,15 @@ extern "C" int p2g_prove_compressed(p2g_circuit* c, const uint64_t* wires, int w
                                     p2g_timings* timings) {
     return prove_entry(c, wires, wires_on_device != 0, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings,
                        true);
+}
+// The witness as plonky2 holds it: MatrixWitness.wire_values is Vec<Vec<F>>, one heap allocation per wire column (SURVEY 8a row
+// a3), so the shim passes the W column pointers and never flattens 1.96 GB on the host.  Columns in pageable memory are staged
+// through the library's pinned ring by several host threads; page-locked columns (cudaHostRegister) are copied directly.
+extern "C" int p2g_prove_columns(p2g_circuit* c, const uint64_t* const* wire_columns, const uint64_t* public_inputs,
+                                 size_t num_public_inputs, const uint64_t* forced_pow_witness, int compressed, uint8_t* out,
+                                 size_t* out_len, p2g_timings* timings) {
+    return prove_entry(c, nullptr, false, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings,
+                       compressed != 0, wire_columns);
 }
 extern "C" int p2g_prove_device(p2g_circuit* c, const uint64_t* d_wires, const uint64_t* public_inputs, size_t num_public_inputs,
                                 const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len, p2g_timings* timings) {

@@ -11,6 +11,9 @@
 #include "internal.h"
 #include "quotient.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 // The per-proof parameters (alpha powers, beta k_i, gate table: ~13 KB) travel as a __grid_constant__ kernel parameter: they
 // sit in the constant bank (uniform, broadcast reads) and nothing is shared between proofs in flight on other streams.
 namespace {
@@ -134,6 +137,94 @@ __global__ void __launch_bounds__(256) k_quotient_gate(const __grid_constant__ Q
     if (P.num_challenges > 1) out[OL + j] = a1;
 }
 
+// Limb sweep + the rest of the u32 gates, one pass over the wires (quotient.h LimbPlan).  Replaces the k_quotient_gate<7..10>
+// launches (and BaseSum<4>): those evaluated l(l-1)(l-2)(l-3) once per (gate, limb) -- 1300 times per point for the ECDSA mix
+// on 234 wires -- and re-read the limb columns once per gate.  Here a point's thread walks the wire axis once: check(w), up to
+// four multiply-accumulates into the running prefixes, and at every window boundary one `filter * prefix * coef` term.  The
+// gates' remaining constraints (recombinations, carries) follow in the same kernel while the block's columns are L2-resident.
+__global__ void __launch_bounds__(256) k_quotient_limb(const __grid_constant__ QuotientParams P, const __grid_constant__ LimbPlan LP,
+                                                       const u64* __restrict__ cs, const u64* __restrict__ wires,
+                                                       u64* __restrict__ out_, int scale_now, size_t L, size_t j0, size_t OL) {
+    __shared__ u64 fsh[P2G_MAX_LIMB_GATES][256];
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= L) return;
+    u64* __restrict__ out = out_ + j0;
+    const int tid = threadIdx.x;
+    const bool many = P.num_selectors > 1;
+    for (int s = 0; s < LP.ngates; s++) {
+        const int g = LP.gate[s];
+        const GateDev& gd = P.gates[g];
+        fsh[s][tid] = gate_filter(gd, g, __ldg(cs + (size_t)gd.selector_index * L + j), many);
+    }
+    gl_acc acc0, acc1, A0, A1, B0, B1;
+    acc0.clear(); acc1.clear(); A0.clear(); A1.clear(); B0.clear(); B1.clear();
+    int e = 0;
+    const int ne = LP.nevents;
+    for (int w = LP.wmin; w <= LP.wmax; w++) {
+        if (e < ne && LP.ev[e].pos == w) {
+            int cur_dir = -1;
+            u64 r0 = 0, r1 = 0;
+            do {
+                const LimbEvent& E = LP.ev[e];
+                if ((int)E.dir != cur_dir) {
+                    cur_dir = E.dir;
+                    r0 = cur_dir ? B0.reduce() : A0.reduce();
+                    r1 = cur_dir ? B1.reduce() : A1.reduce();
+                }
+                const u64 f = fsh[E.slot][tid];
+                acc0.mac(glz_mul(f, r0), E.coef[0]);
+                acc1.mac(glz_mul(f, r1), E.coef[1]);
+                e++;
+            } while (e < ne && LP.ev[e].pos == w);
+        }
+        if (w == LP.wmax) break;
+        const unsigned need = LP.need[w];
+        if (need) {
+            const u64 ck = limb4_check(__ldg(wires + (size_t)w * L + j));
+            if (need & 1) {
+                A0.mac(ck, P.apow[0][w]);
+                A1.mac(ck, P.apow[1][w]);
+            }
+            if (need & 2) {
+                B0.mac(ck, LP.bpow[0][w]);
+                B1.mac(ck, LP.bpow[1][w]);
+            }
+        }
+    }
+    // everything else these gates constrain
+    auto wire = [&](int i) -> u64 { return __ldg(wires + (size_t)i * L + j); };
+    const int off = P.num_challenges * (2 + P.num_partial_products);
+    for (int s = 0; s < LP.ngates; s++) {
+        const GateDev& gd = P.gates[LP.gate[s]];
+        WeightedSink sink;
+        sink.a0.clear();
+        sink.a1.clear();
+        sink.k = sink.base = off;
+        sink.ap0 = P.apow[0];
+        sink.ap1 = P.apow[1];
+        switch (gd.kind) {
+        case P2G_GATE_BASE_SUM: eval_gate_nonlimb<P2G_GATE_BASE_SUM>(gd, wire, sink); break;
+        case P2G_GATE_U32_ARITHMETIC: eval_gate_nonlimb<P2G_GATE_U32_ARITHMETIC>(gd, wire, sink); break;
+        case P2G_GATE_U32_ADD_MANY: eval_gate_nonlimb<P2G_GATE_U32_ADD_MANY>(gd, wire, sink); break;
+        case P2G_GATE_U32_SUBTRACTION: eval_gate_nonlimb<P2G_GATE_U32_SUBTRACTION>(gd, wire, sink); break;
+        case P2G_GATE_U32_RANGE_CHECK: eval_gate_nonlimb<P2G_GATE_U32_RANGE_CHECK>(gd, wire, sink); break;
+        default: break;
+        }
+        const u64 f = fsh[s][tid];
+        acc0.mac(f, sink.a0.reduce());
+        acc1.mac(f, sink.a1.reduce());
+    }
+    u64 a0 = gl_add(out[j], acc0.reduce());
+    u64 a1 = P.num_challenges > 1 ? gl_add(out[OL + j], acc1.reduce()) : 0;
+    if (scale_now) {
+        const u64 zhi = P.zh_inv[bitrev32((u32)((j0 + j) >> P.logn), P.rate_bits)];
+        a0 = gl_mul(a0, zhi);
+        a1 = gl_mul(a1, zhi);
+    }
+    out[j] = a0;
+    if (P.num_challenges > 1) out[OL + j] = a1;
+}
+
 struct StoreSink {  // stand-alone entry point: out[k][pt] += filter * constraint_k
     u64* out;
     size_t np, pt;
@@ -187,20 +278,101 @@ void quotient_points(DevCtx* c, u64* d_xs, u64* d_l0s, int logn, int rate_bits, 
     count_launch(c);
 }
 
-void quotient_eval(DevCtx* c, const QuotientParams& qp, const u64* d_cs, const u64* d_wires, const u64* d_zpp, const u64* d_xs,
-                   const u64* d_l0s, u64* d_out, size_t npts, size_t j0, size_t out_stride) {
+bool quotient_limb_plan(const QuotientParams& qp, int num_wires, const u64* alphas, LimbPlan* lp) {
+    memset(lp, 0, sizeof *lp);
+    if (getenv("P2G_QUOTIENT_GATE_MAJOR") || num_wires > P2G_MAX_WIRES) return false;
+    const int NC = qp.num_challenges, off = NC * (2 + qp.num_partial_products);
+    u64 ainv[2] = {0, 0};
+    for (int c = 0; c < NC; c++) {
+        if (alphas[c] == 0) return false;
+        ainv[c] = gl_inv(alphas[c]);
+    }
+    auto apow = [&](int c, long e) { return e >= 0 ? gl_pow(alphas[c], (u64)e) : gl_pow(ainv[c], (u64)(-e)); };
+    struct Win { int slot, lo, len, k0, dir; };   // limb j of the window sits on wire lo + j, constraint k0 + j (dir 0) or k0 - j (dir 1)
+    std::vector<Win> wins;
+    for (int g = 0; g < qp.num_gates; g++) {
+        const GateDev& gd = qp.gates[g];
+        const u32* p = gd.params;
+        if (!gd.num_constraints || !gate_has_limb4_sweep(gd.kind, p)) continue;
+        if (lp->ngates == P2G_MAX_LIMB_GATES) return false;
+        const int slot = lp->ngates++;
+        lp->gate[slot] = g;
+        switch (gd.kind) {
+        case P2G_GATE_BASE_SUM: wins.push_back({slot, 1, (int)p[1], 1, 0}); break;
+        case P2G_GATE_U32_ARITHMETIC:
+            for (u32 i = 0; i < p[0]; i++) wins.push_back({slot, (int)(6 * p[0] + 32 * i), 32, (int)(36 * i + 33), 1});
+            break;
+        case P2G_GATE_U32_ADD_MANY:
+            for (u32 i = 0; i < p[1]; i++) wins.push_back({slot, (int)((p[0] + 3) * p[1] + 18 * i), 18, (int)(21 * i + 18), 1});
+            break;
+        case P2G_GATE_U32_SUBTRACTION:
+            for (u32 i = 0; i < p[0]; i++) wins.push_back({slot, (int)(5 * p[0] + 16 * i), 16, (int)(19 * i + 16), 1});
+            break;
+        case P2G_GATE_U32_RANGE_CHECK:
+            for (u32 i = 0; i < p[0]; i++) wins.push_back({slot, (int)(p[0] + 16 * i), 16, (int)(17 * i + 1), 0});
+            break;
+        default: break;
+        }
+    }
+    if (wins.empty()) return false;
+    // boundary events, merged per (position, direction, gate)
+    std::map<std::tuple<int, int, int>, std::pair<u64, u64>> evs;
+    lp->wmin = num_wires;
+    lp->wmax = 0;
+    for (const Win& wn : wins) {
+        if (wn.lo + wn.len > num_wires) return false;
+        u64 cf[2] = {0, 0};
+        for (int c = 0; c < NC; c++) cf[c] = apow(c, wn.dir ? (long)off + wn.k0 + wn.lo : (long)off + wn.k0 - wn.lo);
+        auto& hi = evs[std::make_tuple(wn.lo + wn.len, wn.dir, wn.slot)];
+        auto& lo = evs[std::make_tuple(wn.lo, wn.dir, wn.slot)];
+        hi.first = gl_add(hi.first, cf[0]);
+        hi.second = gl_add(hi.second, cf[1]);
+        lo.first = gl_sub(lo.first, cf[0]);
+        lo.second = gl_sub(lo.second, cf[1]);
+        for (int w = wn.lo; w < wn.lo + wn.len; w++) lp->need[w] |= wn.dir ? 2 : 1;
+        lp->wmin = std::min(lp->wmin, wn.lo);
+        lp->wmax = std::max(lp->wmax, wn.lo + wn.len);
+    }
+    for (auto& kv : evs) {
+        if (kv.second.first == 0 && kv.second.second == 0) continue;
+        if (lp->nevents == P2G_MAX_LIMB_EVENTS) return false;
+        LimbEvent& E = lp->ev[lp->nevents++];
+        E.pos = (unsigned short)std::get<0>(kv.first);
+        E.dir = (unsigned char)std::get<1>(kv.first);
+        E.slot = (unsigned char)std::get<2>(kv.first);
+        E.coef[0] = kv.second.first;
+        E.coef[1] = kv.second.second;
+    }
+    for (int c = 0; c < NC; c++) {
+        u64 x = 1;
+        for (int w = 0; w < num_wires; w++) {
+            lp->bpow[c][w] = x;
+            x = gl_mul(x, ainv[c]);
+        }
+    }
+    return true;
+}
+
+void quotient_eval(DevCtx* c, const QuotientParams& qp, const LimbPlan* lp, const u64* d_cs, const u64* d_wires, const u64* d_zpp,
+                   const u64* d_xs, const u64* d_l0s, u64* d_out, size_t npts, size_t j0, size_t out_stride) {
     const int TH = 256;
     const unsigned grid = (unsigned)((npts + TH - 1) / TH);
-    int last = -1;
-    for (int g = 0; g < qp.num_gates; g++)
-        if (qp.gates[g].num_constraints) last = g;
-    k_quotient_perm<<<grid, TH, 0, c->stream>>>(qp, d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, last < 0, npts, j0, out_stride);
-    count_launch(c);
-    for (int g = 0; g <= last; g++) {
+    // launch list: gates with constraints that the limb sweep does not cover, then the sweep; the last launch divides by Z_H
+    std::vector<int> solo;
+    for (int g = 0; g < qp.num_gates; g++) {
         const GateDev& gd = qp.gates[g];
         if (!gd.num_constraints) continue;
+        if (lp && gate_has_limb4_sweep(gd.kind, gd.params)) continue;
+        solo.push_back(g);
+    }
+    const bool sweep = lp != nullptr;
+    k_quotient_perm<<<grid, TH, 0, c->stream>>>(qp, d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, solo.empty() && !sweep, npts, j0, out_stride);
+    count_launch(c);
+    for (size_t i = 0; i < solo.size(); i++) {
+        const int g = solo[i];
+        const GateDev& gd = qp.gates[g];
         const u32 nops = gate_num_ops(gd.kind, gd.params);
-        const int fin = g == last;
+        const int fin = (i + 1 == solo.size()) && !sweep;
         switch (gd.kind) {
 #define P2G_LAUNCH(KIND) case KIND: k_quotient_gate<KIND><<<grid, TH, 0, c->stream>>>(qp, d_cs, d_wires, d_out, g, 0, nops, fin, npts, j0, out_stride); break;
             P2G_LAUNCH(P2G_GATE_CONSTANT) P2G_LAUNCH(P2G_GATE_PUBLIC_INPUT) P2G_LAUNCH(P2G_GATE_ARITHMETIC)
@@ -210,6 +382,10 @@ void quotient_eval(DevCtx* c, const QuotientParams& qp, const u64* d_cs, const u
 #undef P2G_LAUNCH
         default: throw p2g_error(P2G_EBADARG, "quotient: unknown gate kind");
         }
+        count_launch(c);
+    }
+    if (sweep) {
+        k_quotient_limb<<<grid, TH, 0, c->stream>>>(qp, *lp, d_cs, d_wires, d_out, 1, npts, j0, out_stride);
         count_launch(c);
     }
     CUDA_CHECK(cudaGetLastError());

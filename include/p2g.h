@@ -168,6 +168,16 @@ int p2g_prove_compressed(p2g_circuit* c, const uint64_t* wires, int wires_on_dev
                          size_t num_public_inputs, const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len,
                          p2g_timings* timings);
 
+/* Same, taking the witness the way plonky2 holds it: `MatrixWitness.wire_values` is a `Vec<Vec<F>>` with one allocation per
+ * wire column (plonky2 iop/witness.rs; reached from prove_action.rs:96 through `PartitionWitness::full_witness()`, SURVEY 8a row
+ * a3).  wire_columns[i] points at the N canonical u64 of column i (GoldilocksField is a transparent u64), so the Rust shim passes
+ * num_wires pointers and never builds a flat copy.  compressed: 0 = ProofWithPublicInputs::to_bytes, 1 = the CLI's compressed
+ * file format.  Pageable columns are staged through a pinned ring by several host threads; page-locked ones are copied directly. */
+int p2g_prove_columns(p2g_circuit* c, const uint64_t* const* wire_columns, const uint64_t* public_inputs,
+                      size_t num_public_inputs, const uint64_t* forced_pow_witness, int compressed, uint8_t* out,
+                      size_t* out_len, p2g_timings* timings);
+
+/* Upper bound of the proof size; also what p2g_prove* return in *out_len (with P2G_ESMALLBUF) when out == NULL. */
 size_t p2g_proof_size_bound(const p2g_circuit* c);
 
 /* ---- multi-GPU (one process per GPU): coset sharding, SURVEY 8(e) ----------------------------------------------

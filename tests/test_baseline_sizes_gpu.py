@@ -83,19 +83,19 @@ def test_config3_ecdsa_2_20_bytes(p2g, corc):
 
 def test_config4_range_2_22(p2g, corc):
     """configs[4]: 2^22 rows, AssertZero + RANGE, five FRI layers, three-pass NTT plans.  With enough host memory and cores the
-    oracle proves it too (bytes compared); otherwise the proof must at least be accepted by the oracle verifier and equal the
-    8-way coset-sharded proof."""
+    oracle proves it too (bytes compared; ~130 GB of host memory); otherwise the proof must at least be accepted by the oracle
+    verifier and equal the 2-way coset-sharded proof (two handles of this size fit one GPU's 180 GB, eight do not)."""
     from helpers import oracle_cd
     from oracle.pyref import proof, verifier
     sc = p2g.synth.SyntheticCircuit(22, "range", num_public_inputs=0, seed=0xAC1D + 4)
-    if _host_ram_gb() >= 220 and (os.cpu_count() or 1) >= 16 and not os.environ.get("P2G_SKIP_ORACLE_2_22"):
+    if _host_ram_gb() >= 150 and (os.cpu_count() or 1) >= 16 and not os.environ.get("P2G_SKIP_ORACLE_2_22"):
         _compare_with_oracle(p2g, corc, sc, [4, 4, 4, 4, 4])
         return
     cd = oracle_cd(sc.common)
     with p2g.CircuitData(sc.common, sc.constants_sigmas) as data:
         want = data.prove(sc.wires, sc.public_inputs, timings=False).to_bytes()
         verifier.verify(proof.parse_uncompressed(want, cd), cd, data.constants_sigmas_cap, data.circuit_digest)
-    group = p2g.sharding.ThreadGroup(8)
+    group = p2g.sharding.ThreadGroup(2)
 
     def rank_main(rank, member):
         with p2g.CircuitData(sc.common, sc.constants_sigmas, device=0, shard=member) as d:
@@ -104,7 +104,7 @@ def test_config4_range_2_22(p2g, corc):
         assert got == want
 
 
-@pytest.mark.parametrize("log_n", [20, 21, 22, 23, 24])
+@pytest.mark.parametrize("log_n", [20, 21, 22, 23, 24, 25])
 def test_coset_ifft_leaforder_large_matches_oracle(p2g, corc, log_n):
     """The quotient's size-8N coset inverse transform at the sizes of configs[2..4] (two- and three-pass plans)."""
     rng = np.random.default_rng(900 + log_n)

@@ -105,6 +105,35 @@ def test_prove_from_device_tensor_and_forced_pow(p2g, corc):
             assert ei.value.code == p2g.lib.P2G_EUNSAT
 
 
+def test_prove_columns_takes_the_witness_as_plonky2_holds_it(p2g, corc):
+    """p2g_prove_columns: one pointer per MatrixWitness.wire_values[col] (separately allocated columns); same bytes as the flat
+    matrix, uncompressed and compressed, and a null column is refused."""
+    import ctypes as C
+    sc = p2g.synth.SyntheticCircuit(13, "ecdsa", num_public_inputs=2, seed=78)   # 2^13 x 8 B columns: staged through the ring
+    cols = [np.array(sc.wires[i], copy=True) for i in range(sc.wires.shape[0])]    # 234 separate heap allocations
+    with p2g.CircuitData(sc.common, sc.constants_sigmas) as data:
+        flat = data.prove(sc.wires, sc.public_inputs)
+        got = data.prove_columns(cols, sc.public_inputs)
+        assert got.to_bytes() == flat.to_bytes()
+        assert got.timings["h2d_bytes"] == sc.wires.nbytes
+        assert (data.prove_columns(cols, sc.public_inputs, compressed=True).to_bytes()
+                == data.prove(sc.wires, sc.public_inputs, compressed=True).to_bytes())
+        with pytest.raises(ValueError):
+            data.prove_columns(cols[:-1], sc.public_inputs)
+        ptrs = (C.c_void_p * len(cols))(*[a.ctypes.data for a in cols])
+        ptrs[5] = None
+        out = C.create_string_buffer(p2g.lib.lib().p2g_proof_size_bound(data._h))
+        ln = C.c_size_t(len(out))
+        pis = np.array(sc.public_inputs, dtype=np.uint64)
+        rc = p2g.lib.lib().p2g_prove_columns(data._h, ptrs, pis.ctypes.data_as(C.c_void_p), len(pis), None, 0, out, C.byref(ln), None)
+        assert rc == p2g.lib.P2G_EBADARG
+        # size query: out == NULL answers from the bound without proving
+        ln = C.c_size_t(0)
+        rc = p2g.lib.lib().p2g_prove(data._h, sc.wires.ctypes.data_as(C.c_void_p), pis.ctypes.data_as(C.c_void_p), len(pis), None, None,
+                                     C.byref(ln), None)
+        assert rc == p2g.lib.P2G_ESMALLBUF and ln.value == p2g.lib.lib().p2g_proof_size_bound(data._h)
+
+
 def test_invalid_witness_is_rejected_by_the_verifier(p2g, corc):
     """The reference's negative tests panic in witness generation (before the seam); at the seam a bad trace still yields
     bytes, and those must NOT verify."""
