@@ -373,12 +373,14 @@ __host__ __device__ inline bool gate_has_limb4_sweep(u32 kind, const u32* p) {
 // The same gates WITHOUT their limb range checks (those come from the sweep): every other constraint, with the reference's
 // numbering (arithmetic_u32.rs:289-348, add_many_u32.rs:151-192, subtraction_u32.rs:234-271, range_check_u32.rs:95-117; plonky2
 // gates/base_sum.rs).  Limb recombinations use gl_h4.
+// Evaluates ops [op_lo, op_hi) of the gate (BaseSum: a single op).
 template <int KIND, class W, class S>
-__device__ __forceinline__ void eval_gate_nonlimb(const GateDev& g, const W& w, S& sink) {
+__device__ __forceinline__ void eval_gate_nonlimb(const GateDev& g, u32 op_lo, u32 op_hi, const W& w, S& sink) {
     const u32* p = g.params;
     switch (KIND) {
     case P2G_GATE_BASE_SUM: {
         const u32 nl = p[1];
+        if (op_hi <= op_lo) break;
         gl_h4 sum;
         sum.clear();
         for (int k = (int)nl - 1; k >= 0; k--) sum.push(w(1 + k));
@@ -388,7 +390,7 @@ __device__ __forceinline__ void eval_gate_nonlimb(const GateDev& g, const W& w, 
     }
     case P2G_GATE_U32_ARITHMETIC: {
         const u32 ops = p[0];
-        for (u32 i = 0; i < ops; i++) {
+        for (u32 i = op_lo; i < op_hi; i++) {
             const u32 q = 6 * i;
             u64 computed = gl_add(gl_mul(w(q), w(q + 1)), w(q + 2));
             u64 lo = w(q + 3), hi = w(q + 4), inv = w(q + 5);
@@ -422,7 +424,7 @@ __device__ __forceinline__ void eval_gate_nonlimb(const GateDev& g, const W& w, 
     }
     case P2G_GATE_U32_ADD_MANY: {
         const u32 na = p[0], ops = p[1];
-        for (u32 i = 0; i < ops; i++) {
+        for (u32 i = op_lo; i < op_hi; i++) {
             const u32 q = (na + 3) * i;
             u64 computed = 0;
             for (u32 j = 0; j <= na; j++) computed = gl_add(computed, w(q + j));  // addends then carry-in
@@ -449,7 +451,7 @@ __device__ __forceinline__ void eval_gate_nonlimb(const GateDev& g, const W& w, 
     }
     case P2G_GATE_U32_SUBTRACTION: {
         const u32 ops = p[0];
-        for (u32 i = 0; i < ops; i++) {
+        for (u32 i = op_lo; i < op_hi; i++) {
             const u32 q = 5 * i;
             u64 initial = gl_sub(gl_sub(w(q), w(q + 1)), w(q + 2));
             u64 res = w(q + 3), bout = w(q + 4);
@@ -474,7 +476,7 @@ __device__ __forceinline__ void eval_gate_nonlimb(const GateDev& g, const W& w, 
     }
     case P2G_GATE_U32_RANGE_CHECK: {
         const u32 nl = p[0];
-        for (u32 i = 0; i < nl; i++) {
+        for (u32 i = op_lo; i < op_hi; i++) {
             const u32 aw = nl + 16 * i;
             gl_h4 comb;
             comb.clear();

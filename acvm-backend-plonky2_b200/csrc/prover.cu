@@ -312,6 +312,17 @@ __global__ void k_check_canonical(const u64* __restrict__ v, size_t count, int* 
     if (bad) *flag = 1;
 }
 
+// p2g_prove_columns hands over plonky2's in-memory GoldilocksField words, which may be any representative < 2^64 (its add / sub
+// leave values in [p, 2^64) with probability ~2^-32): reduce them in the library's staging buffer instead of refusing them
+__global__ void k_canonicalize(u64* __restrict__ v, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) {
+        const u64 x = v[i];
+        if (x >= GL_P) v[i] = x - GL_P;
+    }
+}
+
 // query phase gathers
 __global__ void k_gather_rows(const u64* __restrict__ lde, size_t cs, int ncols, const u32* __restrict__ idx, int nq,
                               u64* __restrict__ out) {
@@ -414,6 +425,7 @@ struct p2g_circuit {
         cudaEvent_t start = nullptr, routed = nullptr;    // routed: columns [0, R) needed by the Z computation (sharded only)
         cudaEvent_t last = nullptr;
         bool active = false;
+        bool canon = false;   // reduce the uploaded words mod p before anything reads them (p2g_prove_columns)
         double bytes = 0;
         // pageable caller memory: chunks are first copied (multi-threaded) into a ring of pinned staging buffers, so the DMA
         // runs at full PCIe rate instead of the driver's single-threaded bounce copy
@@ -475,6 +487,14 @@ bool column_block(const p2g_circuit* C, int ncols, int* c0, int* c1) {
     *c1 = std::min(ncols, *c0 + per);
     return true;
 }
+// uploaded chunk [a, e) of the staging buffer: reduce mod p in place when the caller handed over raw GoldilocksField words
+void canon_chunk(p2g_circuit* C, const p2g_circuit::Upload* up, const u64* d_values, size_t values_cs, int a, int e) {
+    if (!up || !up->canon || e <= a) return;
+    const size_t cnt = (size_t)(e - a) * values_cs;
+    const unsigned blocks = (unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 16);
+    k_canonicalize<<<blocks, 256, 0, C->ctx->stream>>>(const_cast<u64*>(d_values) + (size_t)a * values_cs, cnt);
+    count_launch(C->ctx);
+}
 void ifft_columns(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t values_cs, const p2g_circuit::Upload* up = nullptr) {
     const int per = (b.ncols + C->world - 1) / C->world;
     size_t want = (size_t)per * C->world * C->n;
@@ -492,6 +512,7 @@ void ifft_columns(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t valu
         for (auto& ch : up->chunks) {
             int a = std::get<0>(ch), e = std::get<1>(ch);
             CUDA_CHECK(cudaStreamWaitEvent(C->ctx->stream, std::get<2>(ch), 0));
+            canon_chunk(C, up, d_values, values_cs, a, e);
             int np = peer_ptrs(a);
             ntt_ifft(C->ctx, d_values + (size_t)a * values_cs, values_cs, b.coeffs.p + (size_t)a * C->n, C->n, C->logn, e - a, np, peers);
         }
@@ -565,6 +586,7 @@ void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_
         for (auto& ch : up->chunks) {
             int a = std::get<0>(ch), e = std::get<1>(ch);
             CUDA_CHECK(cudaStreamWaitEvent(c->stream, std::get<2>(ch), 0));
+            canon_chunk(C, up, d_values, values_cs, a, e);
             ntt_ifft(c, d_values + (size_t)a * values_cs, values_cs, b.coeffs.p + (size_t)a * C->n, C->n, C->logn, e - a);
             ntt_lde(c, b.coeffs.p + (size_t)a * C->n, C->n, b.lde.p + (size_t)a * C->lde_l, C->lde_l, C->logn, C->d.rate_bits, e - a,
                     GL_GEN, C->z0, C->nzl);
@@ -863,7 +885,8 @@ extern "C" size_t p2g_proof_size_bound(const p2g_circuit* c) {
 // prove
 // =====================================================================================================================
 static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inputs, size_t n_pi, const u64* forced_pow,
-                       uint8_t* out, size_t* out_len, p2g_timings* tm, cudaEvent_t ev_start, bool compressed) {
+                       uint8_t* out, size_t* out_len, p2g_timings* tm, cudaEvent_t ev_start, bool compressed,
+                       bool canonicalize = false) {
     DevCtx* c = C->ctx;
     const p2g_circuit_desc& d = C->d;
     const size_t n = C->n, lde = C->lde;
@@ -899,8 +922,12 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         int c0, c1;
         column_block(C, W, &c0, &c1);
         const int ranges[3][2] = {{c0, c1}, {0, std::min(c0, R)}, {std::max(c1, 0), std::max(c1, R)}};
-        for (auto& rg : ranges) {
+        for (int ri = 0; ri < 3; ri++) {
+            const int* rg = ranges[ri];
             if (rg[1] <= rg[0]) continue;
+            // raw GoldilocksField words (p2g_prove_columns): the block was reduced chunk by chunk before its inverse NTT; the routed
+            // columns outside the block are reduced here, before the Z computation reads them
+            if (canonicalize && ri > 0) canon_chunk(C, &C->up, d_wires, n, rg[0], rg[1]);
             size_t cnt = (size_t)(rg[1] - rg[0]) * n;
             unsigned blocks = (unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 16);
             k_check_canonical<<<blocks, 256, 0, st>>>(d_wires + (size_t)rg[0] * n, cnt, flag);
@@ -1540,6 +1567,7 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
                 up.bytes += (double)words * 8;
             };
             up.chunks.clear();
+            up.canon = cols != nullptr;
             up.bytes = 0;
             up.routed = nullptr;
             // the copy stream must not overwrite the staging buffer while the previous proof's kernels still read it
@@ -1570,7 +1598,7 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
             up.active = true;
             d_wires = C->wires_values.p;
         }
-        prove_impl(C, d_wires, public_inputs, n_pi, forced_pow, out, out_len, tm, ev_start, compressed);
+        prove_impl(C, d_wires, public_inputs, n_pi, forced_pow, out, out_len, tm, ev_start, compressed, cols != nullptr);
         up.active = false;
     });
 }

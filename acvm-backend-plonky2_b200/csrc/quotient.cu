@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(256) k_quotient_gate(const __grid_constant__ Q
 // on 234 wires -- and re-read the limb columns once per gate.  Here a point's thread walks the wire axis once: check(w), up to
 // four multiply-accumulates into the running prefixes, and at every window boundary one `filter * prefix * coef` term.  The
 // gates' remaining constraints (recombinations, carries) follow in the same kernel while the block's columns are L2-resident.
-__global__ void __launch_bounds__(256) k_quotient_limb(const __grid_constant__ QuotientParams P, const __grid_constant__ LimbPlan LP,
+#define SWEEP_B 4
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_quotient_limb(const __grid_constant__ QuotientParams P, const __grid_constant__ LimbPlan LP,
                                                        const u64* __restrict__ cs, const u64* __restrict__ wires,
                                                        u64* __restrict__ out_, int scale_now, size_t L, size_t j0, size_t OL) {
     __shared__ u64 fsh[P2G_MAX_LIMB_GATES][256];
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) k_quotient_limb(const __grid_constant__ Q
     acc0.clear(); acc1.clear(); A0.clear(); A1.clear(); B0.clear(); B1.clear();
     int e = 0;
     const int ne = LP.nevents;
-    for (int w = LP.wmin; w <= LP.wmax; w++) {
+    auto events_at = [&](int w) {   // boundary events at wire position w (the prefixes cover wires < w)
         if (e < ne && LP.ev[e].pos == w) {
             int cur_dir = -1;
             u64 r0 = 0, r1 = 0;
@@ -177,42 +179,59 @@ __global__ void __launch_bounds__(256) k_quotient_limb(const __grid_constant__ Q
                 e++;
             } while (e < ne && LP.ev[e].pos == w);
         }
-        if (w == LP.wmax) break;
-        const unsigned need = LP.need[w];
-        if (need) {
-            const u64 ck = limb4_check(__ldg(wires + (size_t)w * L + j));
-            if (need & 1) {
-                A0.mac(ck, P.apow[0][w]);
-                A1.mac(ck, P.apow[1][w]);
-            }
-            if (need & 2) {
-                B0.mac(ck, LP.bpow[0][w]);
-                B1.mac(ck, LP.bpow[1][w]);
-            }
-        }
-    }
-    // everything else these gates constrain
+    };
     auto wire = [&](int i) -> u64 { return __ldg(wires + (size_t)i * L + j); };
     const int off = P.num_challenges * (2 + P.num_partial_products);
-    for (int s = 0; s < LP.ngates; s++) {
-        const GateDev& gd = P.gates[LP.gate[s]];
-        WeightedSink sink;
-        sink.a0.clear();
-        sink.a1.clear();
-        sink.k = sink.base = off;
-        sink.ap0 = P.apow[0];
-        sink.ap1 = P.apow[1];
-        switch (gd.kind) {
-        case P2G_GATE_BASE_SUM: eval_gate_nonlimb<P2G_GATE_BASE_SUM>(gd, wire, sink); break;
-        case P2G_GATE_U32_ARITHMETIC: eval_gate_nonlimb<P2G_GATE_U32_ARITHMETIC>(gd, wire, sink); break;
-        case P2G_GATE_U32_ADD_MANY: eval_gate_nonlimb<P2G_GATE_U32_ADD_MANY>(gd, wire, sink); break;
-        case P2G_GATE_U32_SUBTRACTION: eval_gate_nonlimb<P2G_GATE_U32_SUBTRACTION>(gd, wire, sink); break;
-        case P2G_GATE_U32_RANGE_CHECK: eval_gate_nonlimb<P2G_GATE_U32_RANGE_CHECK>(gd, wire, sink); break;
-        default: break;
+    for (int ph = 0; ph < LP.nphases; ph++) {
+        // 1. sweep the strip, SWEEP_B independent loads at a time (one load per iteration leaves the thread waiting on DRAM)
+        const int w_end = LP.cut[ph + 1];
+        for (int w0 = LP.cut[ph]; w0 < w_end; w0 += SWEEP_B) {
+            u64 v[SWEEP_B];
+#pragma unroll
+            for (int i = 0; i < SWEEP_B; i++) v[i] = (w0 + i < w_end && LP.need[w0 + i]) ? wire(w0 + i) : 0;
+#pragma unroll
+            for (int i = 0; i < SWEEP_B; i++) {
+                const int w = w0 + i;
+                if (w >= w_end) break;
+                events_at(w);
+                const unsigned need = LP.need[w];
+                if (need) {
+                    const u64 ck = limb4_check(v[i]);
+                    if (need & 1) {
+                        A0.mac(ck, P.apow[0][w]);
+                        A1.mac(ck, P.apow[1][w]);
+                    }
+                    if (need & 2) {
+                        B0.mac(ck, LP.bpow[0][w]);
+                        B1.mac(ck, LP.bpow[1][w]);
+                    }
+                }
+            }
         }
-        const u64 f = fsh[s][tid];
-        acc0.mac(f, sink.a0.reduce());
-        acc1.mac(f, sink.a1.reduce());
+        if (ph + 1 == LP.nphases) events_at(LP.wmax);
+        // 2. everything else the ops of this strip constrain (recombinations, carries, borrows)
+        for (int s = 0; s < LP.ngates; s++) {
+            const u32 op_lo = LP.oplo[s][ph], op_hi = LP.oplo[s][ph + 1];
+            if (op_hi <= op_lo) continue;
+            const GateDev& gd = P.gates[LP.gate[s]];
+            WeightedSink sink;
+            sink.a0.clear();
+            sink.a1.clear();
+            sink.k = sink.base = off;
+            sink.ap0 = P.apow[0];
+            sink.ap1 = P.apow[1];
+            switch (gd.kind) {
+            case P2G_GATE_BASE_SUM: eval_gate_nonlimb<P2G_GATE_BASE_SUM>(gd, op_lo, op_hi, wire, sink); break;
+            case P2G_GATE_U32_ARITHMETIC: eval_gate_nonlimb<P2G_GATE_U32_ARITHMETIC>(gd, op_lo, op_hi, wire, sink); break;
+            case P2G_GATE_U32_ADD_MANY: eval_gate_nonlimb<P2G_GATE_U32_ADD_MANY>(gd, op_lo, op_hi, wire, sink); break;
+            case P2G_GATE_U32_SUBTRACTION: eval_gate_nonlimb<P2G_GATE_U32_SUBTRACTION>(gd, op_lo, op_hi, wire, sink); break;
+            case P2G_GATE_U32_RANGE_CHECK: eval_gate_nonlimb<P2G_GATE_U32_RANGE_CHECK>(gd, op_lo, op_hi, wire, sink); break;
+            default: break;
+            }
+            const u64 f = fsh[s][tid];
+            acc0.mac(f, sink.a0.reduce());
+            acc1.mac(f, sink.a1.reduce());
+        }
     }
     u64 a0 = gl_add(out[j], acc0.reduce());
     u64 a1 = P.num_challenges > 1 ? gl_add(out[OL + j], acc1.reduce()) : 0;
@@ -333,6 +352,30 @@ bool quotient_limb_plan(const QuotientParams& qp, int num_wires, const u64* alph
         lp->wmin = std::min(lp->wmin, wn.lo);
         lp->wmax = std::max(lp->wmax, wn.lo + wn.len);
     }
+    // strips: equal shares of the swept range; an op belongs to the strip in which its limb window ends
+    {
+        int nph = P2G_LIMB_PHASES;
+        if (const char* e = getenv("P2G_LIMB_PHASES")) nph = std::max(1, std::min(P2G_LIMB_PHASES, atoi(e)));
+        const int span = lp->wmax - lp->wmin;
+        nph = std::max(1, std::min(nph, span / 16));
+        lp->nphases = nph;
+        for (int p = 0; p <= nph; p++) lp->cut[p] = lp->wmin + (int)((long)span * p / nph);
+        std::vector<std::vector<int>> cnt(lp->ngates, std::vector<int>(nph, 0));
+        for (const Win& wn : wins) {
+            int p = 0;
+            while (p + 1 < nph && wn.lo + wn.len > lp->cut[p + 1]) p++;
+            cnt[wn.slot][p]++;
+        }
+        for (int s = 0; s < lp->ngates; s++) {
+            int acc = 0;
+            for (int p = 0; p < nph; p++) {
+                lp->oplo[s][p] = (unsigned char)acc;
+                acc += cnt[s][p];
+            }
+            if (acc > 255) return false;
+            lp->oplo[s][nph] = (unsigned char)acc;
+        }
+    }
     for (auto& kv : evs) {
         if (kv.second.first == 0 && kv.second.second == 0) continue;
         if (lp->nevents == P2G_MAX_LIMB_EVENTS) return false;
@@ -385,7 +428,10 @@ void quotient_eval(DevCtx* c, const QuotientParams& qp, const LimbPlan* lp, cons
         count_launch(c);
     }
     if (sweep) {
-        k_quotient_limb<<<grid, TH, 0, c->stream>>>(qp, *lp, d_cs, d_wires, d_out, 1, npts, j0, out_stride);
+        // two blocks per SM (126 registers): the three-block build spills and measured 50 ms against 34 ms (tools/limb_sweep.sh)
+        static const int minb = getenv("P2G_LIMB_MINB") ? atoi(getenv("P2G_LIMB_MINB")) : 2;
+        if (minb == 2) k_quotient_limb<2><<<grid, TH, 0, c->stream>>>(qp, *lp, d_cs, d_wires, d_out, 1, npts, j0, out_stride);
+        else k_quotient_limb<3><<<grid, TH, 0, c->stream>>>(qp, *lp, d_cs, d_wires, d_out, 1, npts, j0, out_stride);
         count_launch(c);
     }
     CUDA_CHECK(cudaGetLastError());

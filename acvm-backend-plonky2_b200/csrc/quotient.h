@@ -39,8 +39,15 @@ struct LimbEvent {
     u32 pad_;
     u64 coef[2];
 };
+// The wire axis is walked in up to P2G_LIMB_PHASES strips [cut[p], cut[p+1]): after a strip's sweep, the other constraints of the
+// ops whose limbs end inside the strip are evaluated, so the limb columns are re-read while the strip is still L2-resident
+// (one strip of the resident threads' columns fits the 126 MB L2; all 234 columns do not).
+#define P2G_LIMB_PHASES 4
 struct LimbPlan {
     int ngates, nevents, wmin, wmax;
+    int nphases;
+    int cut[P2G_LIMB_PHASES + 1];
+    unsigned char oplo[P2G_MAX_LIMB_GATES][P2G_LIMB_PHASES + 1];   // ops [oplo[s][p], oplo[s][p+1]) of gate slot s belong to strip p
     int gate[P2G_MAX_LIMB_GATES];
     unsigned char need[P2G_MAX_WIRES];   // bit 0: wire feeds A, bit 1: wire feeds B
     u64 bpow[2][P2G_MAX_WIRES];          // alpha_c^-w

@@ -170,8 +170,9 @@ int p2g_prove_compressed(p2g_circuit* c, const uint64_t* wires, int wires_on_dev
 
 /* Same, taking the witness the way plonky2 holds it: `MatrixWitness.wire_values` is a `Vec<Vec<F>>` with one allocation per
  * wire column (plonky2 iop/witness.rs; reached from prove_action.rs:96 through `PartitionWitness::full_witness()`, SURVEY 8a row
- * a3).  wire_columns[i] points at the N canonical u64 of column i (GoldilocksField is a transparent u64), so the Rust shim passes
- * num_wires pointers and never builds a flat copy.  compressed: 0 = ProofWithPublicInputs::to_bytes, 1 = the CLI's compressed
+ * a3).  wire_columns[i] points at the N u64 of column i (GoldilocksField is a transparent u64), so the Rust shim passes
+ * num_wires pointers and never builds a flat copy.  Unlike p2g_prove, the words may be ANY representative < 2^64 of the field
+ * element (plonky2's add/sub leave values in [p, 2^64)); the library reduces them on the device.  compressed: 0 = ProofWithPublicInputs::to_bytes, 1 = the CLI's compressed
  * file format.  Pageable columns are staged through a pinned ring by several host threads; page-locked ones are copied directly. */
 int p2g_prove_columns(p2g_circuit* c, const uint64_t* const* wire_columns, const uint64_t* public_inputs,
                       size_t num_public_inputs, const uint64_t* forced_pow_witness, int compressed, uint8_t* out,

@@ -118,6 +118,16 @@ def test_prove_columns_takes_the_witness_as_plonky2_holds_it(p2g, corc):
         assert got.timings["h2d_bytes"] == sc.wires.nbytes
         assert (data.prove_columns(cols, sc.public_inputs, compressed=True).to_bytes()
                 == data.prove(sc.wires, sc.public_inputs, compressed=True).to_bytes())
+        # plonky2's in-memory GoldilocksField may hold any representative < 2^64: x + p for small x is the same field element
+        P = 0xFFFFFFFF00000001
+        raw = [c.copy() for c in cols]
+        bumped = 0
+        for c in raw[::7]:
+            small = np.nonzero(c < np.uint64(0xFFFFFFFF))[0][:50]
+            c[small] += np.uint64(P)
+            bumped += len(small)
+        assert bumped > 0
+        assert data.prove_columns(raw, sc.public_inputs).to_bytes() == flat.to_bytes()
         with pytest.raises(ValueError):
             data.prove_columns(cols[:-1], sc.public_inputs)
         ptrs = (C.c_void_p * len(cols))(*[a.ctypes.data for a in cols])
