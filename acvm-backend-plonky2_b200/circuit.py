@@ -289,6 +289,10 @@ class CircuitData:
         desc, keep = common.fill_desc(constants_sigmas, circuit_digest)
         if shard is None or shard.world == 1:
             _lib.check(_lib.lib().p2g_circuit_create(C.byref(desc), device, C.byref(self._h)))
+        elif getattr(shard, "in_library", False):   # sharding.NcclGroup: the library owns the NCCL communicator
+            idb = C.create_string_buffer(shard.unique_id, len(shard.unique_id))
+            _lib.check(_lib.lib().p2g_circuit_create_sharded_nccl(C.byref(desc), device, shard.rank, shard.world, idb,
+                                                                  C.byref(self._h)))
         else:
             _lib.check(_lib.lib().p2g_circuit_create_sharded(C.byref(desc), device, shard.rank, shard.world,
                                                              shard.callback(), None, C.byref(self._h)))

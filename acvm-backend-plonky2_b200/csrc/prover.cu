@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "internal.h"
+#include "nccl_dyn.h"
 #include "quotient.h"
 
 #include <chrono>
@@ -361,6 +362,7 @@ struct PolyBatch {
     dbuf<u64> lde;     // [ncols][N << rate_bits], leaf order
     MerkleTree tree;
     dbuf<const digest_t*> d_levels;  // device array of level pointers (query gathers)
+    std::vector<const digest_t*> h_levels;   // its host image (kept alive for the asynchronous upload)
 };
 
 }  // namespace
@@ -398,7 +400,7 @@ struct p2g_circuit {
         dbuf<e2> partial, apow;
         dbuf<unsigned long long> best;
         dbuf<u32> idx;
-        dbuf<int> flag;
+        dbuf<int> flag, bar;
         dbuf<digest_t> paths;
         std::vector<FriLayer> layers;
     } ws;
@@ -411,6 +413,11 @@ struct p2g_circuit {
     int loglde_l = 0;
     p2g_allgather_fn allgather = nullptr;
     void* allgather_user = nullptr;
+    // in-library NCCL (p2g_circuit_create_sharded_nccl): collectives are enqueued on the handle's stream, no host round trip
+    ncclComm_t nccl = nullptr;
+    bool nccl_dead = false;        // the communicator was aborted: every later call returns P2G_ENCCL
+    dbuf<uint8_t> nccl_stage;      // device staging of the small host-side gathers (caps, opened rows)
+    unsigned collectives = 0;      // exchanges since create (P2G_BUF_SHARD_INFO)
     // peer views of every other rank's wires.coeffs buffer (same process: the pointer itself; another process: CUDA IPC
     // mapping).  When all ranks could map all peers, the inverse NTT of the trace stores its column block straight into the
     // peers over NVLink and the coefficient all-gather disappears; otherwise the NCCL all-gather is used.
@@ -442,6 +449,10 @@ struct p2g_circuit {
             if (up.stage_free[i]) cudaEventDestroy(up.stage_free[i]);
         }
         for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
+        if (nccl) {
+            if (nccl_dead) nccl_api().CommAbort(nccl);
+            else nccl_api().CommDestroy(nccl);
+        }
         free_child_ctx(ctx);
     }
 };
@@ -453,12 +464,66 @@ void upload_level_ptrs(DevCtx* c, PolyBatch& b) {
     if (nlev <= 0) return;
     std::vector<const digest_t*> p(nlev);
     for (int k = 0; k < nlev; k++) p[k] = b.tree.levels[k].p;
+    if (b.d_levels.n == (size_t)nlev && p == b.h_levels) return;   // trees keep their buffers between proofs
     if (b.d_levels.n != (size_t)nlev) b.d_levels.alloc(nlev);
-    CUDA_CHECK(cudaMemcpyAsync(b.d_levels.p, p.data(), sizeof(void*) * nlev, cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    // stream order is enough for the kernels that read the table (no host synchronisation); only reached when a tree was
+    // (re)allocated: circuit build and the first proof.  The source is pageable memory, which the runtime stages before returning.
+    b.h_levels = p;
+    CUDA_CHECK(cudaMemcpyAsync(b.d_levels.p, b.h_levels.data(), sizeof(void*) * nlev, cudaMemcpyHostToDevice, c->stream));
 }
 
+[[noreturn]] void nccl_fail(p2g_circuit* C, const std::string& what) {
+    // a failed or timed-out collective leaves the communicator unusable: abort it so nothing blocks in it again
+    C->nccl_dead = true;
+    throw p2g_error(P2G_ENCCL, what);
+}
+void nccl_check(p2g_circuit* C, ncclResult_t r, const char* what) {
+    if (r == ncclSuccess || r == ncclInProgress) return;
+    nccl_fail(C, std::string(what) + ": " + nccl_api().GetErrorString(r));
+}
+// Host wait for the handle's stream.  With an NCCL communicator the wait polls, watches the communicator's asynchronous error
+// state and gives up after P2G_NCCL_TIMEOUT_S seconds (default 600): a rank that failed on its own never leaves its peers
+// blocked for ever inside a collective -- they return P2G_ENCCL.
+void stream_sync(p2g_circuit* C) {
+    cudaStream_t st = C->ctx->stream;
+    if (!C->nccl) {
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        return;
+    }
+    static const double limit = getenv("P2G_NCCL_TIMEOUT_S") ? atof(getenv("P2G_NCCL_TIMEOUT_S")) : 600.0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 0;; spin++) {
+        cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess) return;
+        if (q != cudaErrorNotReady) CUDA_CHECK(q);
+        if ((spin & 1023) == 1023) {
+            ncclResult_t ae = ncclSuccess;
+            nccl_check(C, nccl_api().CommGetAsyncError(C->nccl, &ae), "ncclCommGetAsyncError");
+            if (ae != ncclSuccess && ae != ncclInProgress) nccl_fail(C, std::string("NCCL asynchronous error: ") + nccl_api().GetErrorString(ae));
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit)
+                nccl_fail(C, "collective timed out (a peer rank failed or never arrived)");
+        }
+    }
+}
+
+// All-gather `bytes` from every rank into recv (rank order).  Device buffers: enqueued on the handle's stream (NCCL) -- the
+// caller keeps launching; host buffers (caps, opened rows, a few KB): staged through the device, returns when recv is filled.
 void shard_allgather(p2g_circuit* C, const void* send, void* recv, size_t bytes, bool is_device) {
+    C->collectives++;
+    if (C->nccl) {
+        if (C->nccl_dead) throw p2g_error(P2G_ENCCL, "the NCCL communicator of this handle was aborted by an earlier failure");
+        cudaStream_t st = C->ctx->stream;
+        if (is_device) {
+            nccl_check(C, nccl_api().AllGather(send, recv, bytes, ncclUint8, C->nccl, st), "ncclAllGather");
+            return;
+        }
+        uint8_t* stage = ensure(C->nccl_stage, bytes * C->world);
+        CUDA_CHECK(cudaMemcpyAsync(stage + (size_t)C->rank * bytes, send, bytes, cudaMemcpyHostToDevice, st));
+        nccl_check(C, nccl_api().AllGather(stage + (size_t)C->rank * bytes, stage, bytes, ncclUint8, C->nccl, st), "ncclAllGather");
+        CUDA_CHECK(cudaMemcpyAsync(recv, stage, bytes * C->world, cudaMemcpyDeviceToHost, st));
+        stream_sync(C);
+        return;
+    }
     if (is_device) CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));   // the host binding runs on its own stream
     int rc = C->allgather(C->allgather_user, send, recv, bytes, is_device ? 1 : 0);
     if (rc != 0) throw p2g_error(P2G_ENCCL, "allgather callback failed (" + std::to_string(rc) + ")");
@@ -520,9 +585,13 @@ void ifft_columns(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_t valu
         int np = peer_ptrs(c0);
         ntt_ifft(C->ctx, d_values + (size_t)c0 * values_cs, values_cs, b.coeffs.p + (size_t)c0 * C->n, C->n, C->logn, c1 - c0, np, peers);
     }
-    if (fused) {
-        // every rank's block has been stored into every buffer once all kernels have completed: drain, then a (tiny) barrier
-        CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));
+    if (fused && C->nccl) {
+        // every rank's block is in every buffer once all ranks' kernels have completed: a stream-ordered barrier (a 4-byte
+        // all-gather enqueued behind the stores), no host round trip
+        int* bar = ensure(C->ws.bar, (size_t)C->world);
+        shard_allgather(C, bar + C->rank, bar, sizeof(int), true);
+    } else if (fused) {
+        CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));   // drain, then a (tiny) barrier through the callback
         int one = 1;
         std::vector<int> all(C->world);
         shard_allgather(C, &one, all.data(), sizeof(int), false);
@@ -606,7 +675,7 @@ void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_
 std::vector<digest_t> read_cap(p2g_circuit* C, const MerkleTree& t, bool sharded = true, int* status = nullptr) {
     std::vector<digest_t> mine(t.ncap() + 1);
     CUDA_CHECK(cudaMemcpyAsync(mine.data(), t.cap(), sizeof(digest_t) * t.ncap(), cudaMemcpyDeviceToHost, C->ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));
+    stream_sync(C);
     if (C->world == 1 || !sharded) {
         mine.pop_back();
         return mine;
@@ -739,7 +808,7 @@ void fill_gates(QuotientParams& qp, const p2g_circuit* C) {
 // circuit handle
 // =====================================================================================================================
 static int circuit_create_impl(const p2g_circuit_desc* desc, int device, int rank, int world, p2g_allgather_fn allgather,
-                               void* user, p2g_circuit** out) {
+                               void* user, p2g_circuit** out, const uint8_t* nccl_id = nullptr) {
     if (out) *out = nullptr;
     p2g_circuit* C = nullptr;
     int rc = guard([&] {
@@ -747,7 +816,7 @@ static int circuit_create_impl(const p2g_circuit_desc* desc, int device, int ran
         validate_desc(desc);
         int logworld = 0;
         while ((1 << logworld) < world) logworld++;
-        if (world < 1 || (1 << logworld) != world || rank < 0 || rank >= world || (world > 1 && !allgather) ||
+        if (world < 1 || (1 << logworld) != world || rank < 0 || rank >= world || (world > 1 && !allgather && !nccl_id) ||
             logworld > (int)desc->rate_bits || logworld > (int)desc->cap_height)
             throw p2g_error(P2G_EBADARG, "p2g_circuit_create_sharded: world must be a power of two <= 2^min(rate_bits, cap_height), "
                                          "0 <= rank < world, and an allgather callback is required");
@@ -760,6 +829,19 @@ static int circuit_create_impl(const p2g_circuit_desc* desc, int device, int ran
         C->logworld = logworld;
         C->allgather = allgather;
         C->allgather_user = user;
+        if (nccl_id && world > 1) {
+            const NcclApi& api = nccl_api();
+            if (!api.ok) throw p2g_error(P2G_ENCCL, "libnccl.so.2 could not be loaded (set P2G_NCCL_LIB)");
+            ncclUniqueId id;
+            static_assert(sizeof(ncclUniqueId) == P2G_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+            memcpy(&id, nccl_id, sizeof id);
+            CUDA_CHECK(cudaSetDevice(device));
+            ncclResult_t r = api.CommInitRank(&C->nccl, world, id, rank);
+            if (r != ncclSuccess) {
+                C->nccl = nullptr;
+                throw p2g_error(P2G_ENCCL, std::string("ncclCommInitRank: ") + api.GetErrorString(r));
+            }
+        }
         C->gates.assign(desc->gates, desc->gates + desc->num_gates);
         C->k_is.assign(desc->k_is, desc->k_is + desc->num_routed_wires);
         C->d.gates = C->gates.data();
@@ -842,6 +924,29 @@ extern "C" int p2g_circuit_create(const p2g_circuit_desc* desc, int device, p2g_
 extern "C" int p2g_circuit_create_sharded(const p2g_circuit_desc* desc, int device, int rank, int world, p2g_allgather_fn allgather,
                                           void* user, p2g_circuit** out) {
     return circuit_create_impl(desc, device, rank, world, allgather, user, out);
+}
+
+// One process (or thread) per GPU, the library owns the communicator: rank 0 obtains an id with p2g_nccl_unique_id, hands it to the
+// other ranks by any means, and every rank calls this with the same descriptor.  Exchanges are ncclAllGather on the handle's stream.
+extern "C" int p2g_nccl_unique_id(uint8_t* id_out) {
+    return guard([&] {
+        if (!id_out) throw p2g_error(P2G_EBADARG, "p2g_nccl_unique_id: null argument");
+        const NcclApi& api = nccl_api();
+        if (!api.ok) throw p2g_error(P2G_ENCCL, "libnccl.so.2 could not be loaded (set P2G_NCCL_LIB)");
+        ncclUniqueId id;
+        ncclResult_t r = api.GetUniqueId(&id);
+        if (r != ncclSuccess) throw p2g_error(P2G_ENCCL, std::string("ncclGetUniqueId: ") + api.GetErrorString(r));
+        memcpy(id_out, &id, sizeof id);
+    });
+}
+extern "C" int p2g_circuit_create_sharded_nccl(const p2g_circuit_desc* desc, int device, int rank, int world, const uint8_t* nccl_id,
+                                               p2g_circuit** out) {
+    if (world > 1 && !nccl_id) {
+        set_last_error("p2g_circuit_create_sharded_nccl: null id");
+        if (out) *out = nullptr;
+        return P2G_EBADARG;
+    }
+    return circuit_create_impl(desc, device, rank, world, nullptr, nullptr, out, nccl_id);
 }
 
 extern "C" void p2g_circuit_destroy(p2g_circuit* c) {
@@ -1069,7 +1174,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         CUDA_CHECK(cudaGetLastError());
         std::vector<e2> hp((size_t)(total + NC) * nsplit);
         CUDA_CHECK(cudaMemcpyAsync(hp.data(), partial, hp.size() * sizeof(e2), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        stream_sync(C);
         for (int i = 0; i < total + NC; i++) {
             e2 s = e2_make(0, 0);
             for (int k = 0; k < nsplit; k++) s = e2_add(s, hp[(size_t)i * nsplit + k]);
@@ -1127,7 +1232,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         k_sscan_apply<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(u, totals, n, nt, ztab0, ztab1, alpha_nc, fin);
         count_launch(c, 6);
         CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        stream_sync(C);
     }
     tr.mark("fri combine");
     // commit phase
@@ -1176,7 +1281,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         std::vector<u64> tmp(2 * m);
         CUDA_CHECK(cudaMemcpyAsync(tmp.data(), cur_coeffs, 8 * m, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(tmp.data() + m, cur_coeffs + m, 8 * m, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        stream_sync(C);
         for (size_t i = 0; i < m; i++) {
             C->final_poly[2 * i] = tmp[i];
             C->final_poly[2 * i + 1] = tmp[m + i];
@@ -1198,7 +1303,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             count_launch(c);
             unsigned long long hb = 0;
             CUDA_CHECK(cudaMemcpyAsync(&hb, best, 8, cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));
+            stream_sync(C);
             if (hb != ~0ULL) {
                 pow_witness = hb;
                 break;
@@ -1293,7 +1398,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     std::vector<digest_t> h_paths(path_digests + 1);
     CUDA_CHECK(cudaMemcpyAsync(h_rows.data(), d_rows, 8 * row_words, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(h_paths.data(), d_paths, sizeof(digest_t) * path_digests, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    stream_sync(C);
     if (C->world > 1) {
         // opened rows and paths of the four committed oracles come from the rank that owns the leaf
         const size_t rw = (size_t)NQ * total, pd = path_off[3] + (size_t)NQ * path_len[3];
@@ -1415,7 +1520,7 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     wb.u64v(pow_witness);
     for (size_t i = 0; i < n_pi; i++) wb.u64v(public_inputs[i]);
     CUDA_CHECK(cudaEventRecord(ev[6], st));
-    CUDA_CHECK(cudaEventSynchronize(ev[6]));
+    stream_sync(C);
     tr.mark("queries + serialise");
     C->last_caps[0] = wires_cap;
     C->last_caps[1] = zpp_cap;
@@ -1647,7 +1752,8 @@ extern "C" int p2g_circuit_read(p2g_circuit* C, int what, void* out, size_t* len
             hsrc = packed.data();
             sz = packed.size();
         };
-        u64 info[4] = {(u64)C->rank, (u64)C->world, (u64)C->npeer, (u64)(C->npeer == C->world - 1 && C->world > 1)};
+        u64 info[6] = {(u64)C->rank, (u64)C->world, (u64)C->npeer, (u64)(C->npeer == C->world - 1 && C->world > 1),
+                       (u64)(C->nccl != nullptr), (u64)C->collectives};
         if (what != P2G_BUF_CS_CAP && what != P2G_BUF_SHARD_INFO && !C->proved) throw p2g_error(P2G_EBADARG, "p2g_circuit_read: no proof has been produced yet");
         switch (what) {
         case P2G_BUF_WIRES_CAP: cap_of(C->last_caps[0]); break;

@@ -90,6 +90,41 @@ class TorchDistGroup(_Group):
         return 0
 
 
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+def nccl_unique_id():
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the bytes to the other ranks)."""
+    buf = C.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
+    _lib.check(_lib.lib().p2g_nccl_unique_id(buf))
+    return buf.raw
+
+
+class NcclGroup(_Group):
+    """The communicator lives inside libp2g (p2g_circuit_create_sharded_nccl): no callback, every exchange is an ncclAllGather on
+    the handle's stream.  One instance per circuit handle (a communicator is created per handle); `unique_id` = the 128 bytes from
+    nccl_unique_id() on rank 0."""
+    in_library = True
+
+    def __init__(self, rank, world, device, unique_id):
+        if len(unique_id) != NCCL_UNIQUE_ID_BYTES:
+            raise ValueError("unique_id must be the 128 bytes of an ncclUniqueId")
+        self.rank, self.world, self.device, self.unique_id = rank, world, device, bytes(unique_id)
+
+    @classmethod
+    def from_torch_dist(cls, device, group=None):
+        """Rank 0 draws the id, torch.distributed (any backend) carries it to the other ranks: plumbing only."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        cuda = dist.get_backend(group) == "nccl"
+        t = torch.zeros(NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8, device=f"cuda:{device}" if cuda else "cpu")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0, group=group)
+        return cls(rank, world, device, bytes(t.cpu().numpy().tobytes()))
+
+
 class ThreadGroup:
     """`world` ranks as threads of this process.  group.member(r) is rank r's binding; all ranks must make the same calls."""
 

@@ -43,6 +43,8 @@ def parse():
                     help="proofs in flight per GPU (one circuit handle + stream + host thread each); a step is still one proof")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-proof-across-N-GPUs measurement")
+    ap.add_argument("--sharded-callback", action="store_true",
+                    help="N > 1: exchange through the host callback bound to torch.distributed instead of the library's own NCCL communicator")
     ap.add_argument("--cpu-sample-bits", type=int, default=0, help="rows (log2) of the CPU-baseline sample; 0 = auto")
     ap.add_argument("--no-full-size-cpu", action="store_true", help="--impl reference: skip the one full-size CPU proof (samples only)")
     return ap.parse_args()
@@ -327,7 +329,8 @@ def main():
     if world > 1 and not args.no_sharded:
         for hd in handles:
             hd.close()
-        grp = p2g.sharding.TorchDistGroup(device=local_rank)
+        grp = (p2g.sharding.TorchDistGroup(device=local_rank) if args.sharded_callback
+               else p2g.sharding.NcclGroup.from_torch_dist(local_rank))
         sc0 = sc if rank == 0 else None
         if rank != 0:   # every rank proves the SAME circuit and witness
             sc0 = p2g.synth.SyntheticCircuit(args.degree_bits, args.workload, config=cfg, num_public_inputs=4,
@@ -341,13 +344,17 @@ def main():
         ms_sd, souts = timed(lambda k: [sdata.prove(wd, sc0.public_inputs) for _ in range(k)], args.steps)
         sdata.prove(wh, sc0.public_inputs)
         ms_se, souts_e = timed(lambda k: [sdata.prove(wh, sc0.public_inputs) for _ in range(k)], args.steps)
+        shard_info1 = sdata.read(p2g.lib.BUF_SHARD_INFO)
+        sdata.prove(wd, sc0.public_inputs)
+        shard_info2 = sdata.read(p2g.lib.BUF_SHARD_INFO)
         digest = torch.tensor(list(__import__("hashlib").sha256(souts[0].to_bytes()).digest()), device="cuda", dtype=torch.int32)
         gathered = [torch.empty_like(digest) for _ in range(world)]
         dist.all_gather(gathered, digest)
         same = all(bool((g == gathered[0]).all()) for g in gathered)
         sharded = {"proofs_per_s": args.steps / (ms_sd / 1e3), "ms_per_proof": ms_sd / args.steps,
                    "e2e_ms_per_proof": ms_se / args.steps, "h2d_bytes_per_rank": int(souts_e[0].timings.get("h2d_bytes", 0)),
-                   "collectives_per_proof": grp.calls // max(1, 2 * (args.warmup + args.steps) + 1),
+                   "collectives_per_proof": int(shard_info2[5] - shard_info1[5]) if len(shard_info1) > 5 else None,
+                   "communicator": "library-owned NCCL (ncclAllGather on the handle's stream)" if int(shard_info[4]) else "host callback -> torch.distributed",
                    "identical_bytes_on_all_ranks": same,
                    "matches_single_gpu_bytes": (souts[0].to_bytes() == outs[0].to_bytes()) if rank == 0 else None,
                    "inverse_ntt_exchange": "peer stores over NVLink, fused into the transform" if int(shard_info[3]) else "NCCL all-gather",

@@ -197,6 +197,17 @@ typedef int (*p2g_allgather_fn)(void* user, const void* send, void* recv, size_t
 int p2g_circuit_create_sharded(const p2g_circuit_desc* desc, int device, int rank, int world, p2g_allgather_fn allgather,
                                void* user, p2g_circuit** out);
 
+/* The same with the communicator inside the library (SURVEY 8b "Threading"): no callback, the exchanges are ncclAllGather calls
+ * enqueued on the handle's own stream, with no host round trip for device data.  Rank 0 calls p2g_nccl_unique_id and hands
+ * the 128 bytes to the other ranks by any means (MPI, torch.distributed, a file); then every rank -- one process or one thread per
+ * GPU -- calls p2g_circuit_create_sharded_nccl (ncclCommInitRank; collective: returns when all ranks have joined).  libnccl.so.2
+ * is resolved at run time (the copy already loaded in the process, e.g. PyTorch's, else the system one; P2G_NCCL_LIB overrides).
+ * NCCL failures and a peer that never arrives (P2G_NCCL_TIMEOUT_S, default 600 s) return P2G_ENCCL and poison the handle. */
+#define P2G_NCCL_UNIQUE_ID_BYTES 128
+int p2g_nccl_unique_id(uint8_t* id_out /* [P2G_NCCL_UNIQUE_ID_BYTES] */);
+int p2g_circuit_create_sharded_nccl(const p2g_circuit_desc* desc, int device, int rank, int world,
+                                    const uint8_t* nccl_id /* [P2G_NCCL_UNIQUE_ID_BYTES] */, p2g_circuit** out);
+
 /* ---- intermediates of the last prove, for parity tests ---------------------------------------------------------- */
 enum p2g_buffer {
     P2G_BUF_WIRES_CAP = 0,      /* 2^cap_height digests                                                               */
@@ -210,7 +221,8 @@ enum p2g_buffer {
     P2G_BUF_FINAL_POLY = 8,     /* ext coefficients (2 u64 each)                                                       */
     P2G_BUF_FRI_CAPS = 9,       /* num_fri_layers x 2^cap_height digests                                               */
     P2G_BUF_WIRES_LDE = 10,     /* num_wires x 8N/world u64, col-major, leaf (bit-reversed) order: this rank's leaves    */
-    P2G_BUF_SHARD_INFO = 11     /* u64: rank, world, mapped peers, 1 if the inverse-NTT column exchange runs over peer memory */
+    P2G_BUF_SHARD_INFO = 11     /* u64: rank, world, mapped peers, 1 if the inverse-NTT column exchange runs over peer memory,
+                                   1 if the communicator is the library's own NCCL one, exchanges since create */
 };
 int p2g_circuit_read(p2g_circuit* c, int what, void* out, size_t* len /* in: capacity, out: bytes */);
 

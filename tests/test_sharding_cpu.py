@@ -68,6 +68,11 @@ def _worker(rank, world, port, q):
             assert bytes(got) == bytes(np.asarray(full, dtype=np.uint8)), hasher
             c0, c1 = plan["cap_entries"]
             assert bytes(part) == bytes(np.asarray(full, dtype=np.uint8)[c0 * hs:c1 * hs])
+        # 2b. the id of the library-owned NCCL communicator travels from rank 0 over the process group (no GPU needed for the id itself)
+        ng = p2g.sharding.NcclGroup.from_torch_dist(device=None)
+        ids = [None] * world
+        dist.all_gather_object(ids, ng.unique_id)
+        assert (ng.rank, ng.world) == (rank, world) and len(ng.unique_id) == 128 and ids[0] == ids[1] and any(ids[0])
         # 3. the leaves of a rank are whole cosets: coset z of the LDE = size-N transform with shift g * w^bitrev(z)
         assert (hi - lo) % (1 << log_n) == 0 and lo // (1 << log_n) == plan["cosets"][0]
         dist.barrier()
