@@ -353,6 +353,17 @@ class CircuitData:
         return self._run(_lib.lib().p2g_prove, w.ctypes.data_as(C.c_void_p), public_inputs, forced_pow_witness, timings,
                          0 if compressed else None)
 
+    def verifier_data_bytes(self):
+        """`verifier_data().to_bytes(&BackendGateSerializer)`: the file `write_vk` writes (write_vk_action.rs:76-79), from this
+        handle (the CircuitConfig fields the prover does not read default to wide_ecc_config)."""
+        ln = C.c_size_t(0)
+        rc = _lib.lib().p2g_vk_bytes(self._h, None, None, C.byref(ln))
+        if rc != _lib.P2G_ESMALLBUF:
+            _lib.check(rc)
+        out = C.create_string_buffer(ln.value)
+        _lib.check(_lib.lib().p2g_vk_bytes(self._h, None, out, C.byref(ln)))
+        return out.raw[:ln.value]
+
     def prove_columns(self, wire_columns, public_inputs=(), forced_pow_witness=None, timings=True, compressed=False):
         """`wire_columns`: num_wires separate 1-D uint64 arrays of N values each -- `MatrixWitness.wire_values` as plonky2 holds
         it (`Vec<Vec<F>>`, one allocation per column), handed over as column pointers without building a flat copy."""

@@ -29,16 +29,17 @@ inline const NcclApi& nccl_api() {
     static std::once_flag once;
     std::call_once(once, [] {
         void* h = nullptr;
+        // 1. a copy that is already in the process (PyTorch's bundled libnccl.so.2, or one the host preloaded): two NCCL builds
+        //    under one SONAME cannot coexist, so never load a second one next to it; 2. P2G_NCCL_LIB; 3. the system library.
         const char* env = getenv("P2G_NCCL_LIB");
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (h) api.origin = "libnccl.so.2 (already loaded)";
         const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
         for (const char* nm : names) {
+            if (h) break;
             if (!nm) continue;
-            h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // already in the process (e.g. loaded by torch)?
-            if (!h) h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-            if (h) {
-                api.origin = nm;
-                break;
-            }
+            h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (h) api.origin = nm;
         }
         if (!h) return;
         bool all = true;

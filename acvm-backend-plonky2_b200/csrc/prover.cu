@@ -971,6 +971,121 @@ extern "C" int p2g_circuit_cap(const p2g_circuit* c, uint8_t* cap_out, size_t ca
     });
 }
 
+// VerifierCircuitData::to_bytes(&BackendGateSerializer): plonky2 0.2.2 util/serialization.rs write_verifier_circuit_data =
+// write_verifier_only_circuit_data + write_common_circuit_data; usize as u64 LE, bool as u8, field elements as canonical u64 LE.
+extern "C" int p2g_vk_bytes(const p2g_circuit* c, const p2g_vk_config* cfg, uint8_t* out, size_t* out_len) {
+    return guard([&] {
+        if (!c || !out_len) throw p2g_error(P2G_EBADARG, "p2g_vk_bytes: null argument");
+        p2g_vk_config k = {};
+        k.struct_size = sizeof k;
+        k.config_num_constants = 2;
+        k.security_bits = 100;
+        k.max_quotient_degree_factor = 8;
+        k.use_base_arithmetic_gate = 1;
+        k.zero_knowledge = 0;
+        k.reduction_strategy = 1;
+        k.strategy_params[0] = 4;
+        k.strategy_params[1] = 5;
+        if (cfg) {
+            if (cfg->struct_size != sizeof k) throw p2g_error(P2G_EBADARG, "p2g_vk_bytes: p2g_vk_config.struct_size mismatch (ABI)");
+            k = *cfg;
+        }
+        const p2g_circuit_desc& d = c->d;
+        Writer w(out, out ? *out_len : 0);
+        auto usz = [&](u64 x) { w.u64v(x); };
+        auto u32v = [&](u32 x) { w.put(&x, 4); };
+        auto fri_config = [&] {
+            usz(d.rate_bits);
+            usz(d.cap_height);
+            usz(d.num_query_rounds);
+            u32v(d.pow_bits);
+            w.u8v((uint8_t)k.reduction_strategy);
+            if (k.reduction_strategy == 0) {
+                usz(d.num_fri_layers);
+                for (u32 i = 0; i < d.num_fri_layers; i++) usz(d.reduction_arity_bits[i]);
+            } else if (k.reduction_strategy == 1) {
+                usz(k.strategy_params[0]);
+                usz(k.strategy_params[1]);
+            } else {
+                w.u8v(k.strategy_params[0] ? 1 : 0);
+                if (k.strategy_params[0]) usz(k.strategy_params[1]);
+            }
+        };
+        // VerifierOnlyCircuitData
+        usz(d.cap_height);
+        for (const digest_t& dg : c->cs_cap) w.digest(dg, c->hs);
+        w.digest(c->digest, c->hs);
+        // CommonCircuitData: config
+        usz(d.num_wires);
+        usz(d.num_routed_wires);
+        usz(k.config_num_constants);
+        usz(k.security_bits);
+        usz(d.num_challenges);
+        usz(k.max_quotient_degree_factor);
+        w.u8v(k.use_base_arithmetic_gate ? 1 : 0);
+        w.u8v(k.zero_knowledge ? 1 : 0);
+        fri_config();
+        // fri_params
+        fri_config();
+        usz(d.num_fri_layers);
+        for (u32 i = 0; i < d.num_fri_layers; i++) usz(d.reduction_arity_bits[i]);
+        usz(d.degree_bits);
+        w.u8v(k.zero_knowledge ? 1 : 0);
+        // selectors_info
+        usz(d.num_gates);
+        for (u32 g = 0; g < d.num_gates; g++) usz(c->gates[g].selector_index);
+        usz(d.num_selectors);
+        {
+            std::vector<std::pair<u32, u32>> groups(d.num_selectors, {0, 0});
+            for (u32 g = 0; g < d.num_gates; g++) groups[c->gates[g].selector_index] = {c->gates[g].group_lo, c->gates[g].group_hi};
+            for (auto& gr : groups) {
+                usz(gr.first);
+                usz(gr.second);
+            }
+        }
+        usz(d.quotient_degree_factor);
+        usz(d.num_gate_constraints);
+        usz(d.num_constants);
+        usz(d.num_public_inputs);
+        usz(d.num_routed_wires);   // k_is.len()
+        for (u32 i = 0; i < d.num_routed_wires; i++) usz(c->k_is[i]);
+        usz(d.num_partial_products);
+        usz(0);   // num_lookup_polys
+        usz(0);   // num_lookup_selectors
+        usz(0);   // luts.len()
+        // gates: u32 tag = position in BackendGateSerializer's impl_gate_serializer! list (write_vk_action.rs:37-61), then the
+        // gate's own serialize payload
+        usz(d.num_gates);
+        for (u32 g = 0; g < d.num_gates; g++) {
+            const p2g_gate& gt = c->gates[g];
+            const u32* p = gt.params;
+            switch (gt.kind) {
+            case P2G_GATE_ARITHMETIC: u32v(0); usz(p[0]); break;
+            case P2G_GATE_BASE_SUM:
+                if (p[0] != 2 && p[0] != 4) throw p2g_error(P2G_EBADARG, "p2g_vk_bytes: BackendGateSerializer only registers BaseSumGate<2> and <4>");
+                u32v(p[0] == 2 ? 2 : 3);
+                usz(p[1]);
+                break;
+            case P2G_GATE_CONSTANT: u32v(4); usz(p[0]); break;
+            case P2G_GATE_NOOP: u32v(10); break;
+            case P2G_GATE_POSEIDON: u32v(12); break;
+            case P2G_GATE_PUBLIC_INPUT: u32v(13); break;
+            case P2G_GATE_RANDOM_ACCESS: u32v(14); usz(p[0]); usz(p[1]); usz(p[2]); break;
+            case P2G_GATE_COMPARISON: u32v(17); usz(p[0]); usz(p[1]); break;
+            case P2G_GATE_U32_ADD_MANY: u32v(18); usz(p[0]); usz(p[1]); break;
+            case P2G_GATE_U32_ARITHMETIC: u32v(19); usz(p[0]); break;
+            case P2G_GATE_U32_RANGE_CHECK: u32v(20); usz(p[0]); break;
+            case P2G_GATE_U32_SUBTRACTION: u32v(21); usz(p[0]); break;
+            default: throw p2g_error(P2G_EBADARG, "p2g_vk_bytes: unknown gate kind");
+            }
+        }
+        const size_t need = w.len;
+        const bool small = !out || need > w.cap;
+        *out_len = need;
+        if (small) throw p2g_error(P2G_ESMALLBUF, "p2g_vk_bytes: output buffer too small");
+    });
+}
+
 extern "C" size_t p2g_proof_size_bound(const p2g_circuit* c) {
     if (!c) return 0;
     const p2g_circuit_desc& d = c->d;

@@ -61,7 +61,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 # every symbol include/p2g.h declares (tests/test_abi.py checks the header against this list and the built library)
 EXPORTS = ["p2g_version", "p2g_device_count", "p2g_last_error", "p2g_host_alloc", "p2g_host_free", "p2g_circuit_create", "p2g_circuit_destroy",
            "p2g_circuit_cap", "p2g_prove", "p2g_prove_device", "p2g_prove_compressed", "p2g_prove_columns", "p2g_proof_size_bound", "p2g_circuit_create_sharded",
-           "p2g_nccl_unique_id", "p2g_circuit_create_sharded_nccl",
+           "p2g_nccl_unique_id", "p2g_circuit_create_sharded_nccl", "p2g_vk_bytes",
            "p2g_circuit_read", "p2g_ifft", "p2g_lde", "p2g_coset_ifft_leaforder", "p2g_merkle_cap",
            "p2g_poseidon_permute", "p2g_keccak256", "p2g_eval_gate_constraints", "p2g_test_field_ops"]
 
@@ -109,6 +109,7 @@ def lib():
                                                  C.POINTER(C.c_void_p)]
         L.p2g_nccl_unique_id.argtypes = [C.c_void_p]
         L.p2g_circuit_create_sharded_nccl.argtypes = [C.POINTER(DescS), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.p2g_vk_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
         L.p2g_ifft.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
         L.p2g_lde.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
         L.p2g_coset_ifft_leaforder.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]

@@ -93,8 +93,27 @@ class TorchDistGroup(_Group):
 NCCL_UNIQUE_ID_BYTES = 128
 
 
+def preload_nccl():
+    """Inside a Python process PyTorch brings its own libnccl.so.2 (nvidia-nccl wheel), newer than the system one, and a process can
+    hold only one library of that SONAME: load PyTorch's copy first so that libp2g (which takes whatever is already loaded) and a
+    later `import torch` agree.  A host without PyTorch (the Rust CLI) simply gets the system libnccl."""
+    import importlib.util
+    import os
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        path = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(path):
+            C.CDLL(path, mode=C.RTLD_GLOBAL)
+            return path
+    return None
+
+
 def nccl_unique_id():
     """ncclGetUniqueId through the library (rank 0 calls it and hands the bytes to the other ranks)."""
+    preload_nccl()
     buf = C.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
     _lib.check(_lib.lib().p2g_nccl_unique_id(buf))
     return buf.raw
@@ -109,6 +128,7 @@ class NcclGroup(_Group):
     def __init__(self, rank, world, device, unique_id):
         if len(unique_id) != NCCL_UNIQUE_ID_BYTES:
             raise ValueError("unique_id must be the 128 bytes of an ncclUniqueId")
+        preload_nccl()
         self.rank, self.world, self.device, self.unique_id = rank, world, device, bytes(unique_id)
 
     @classmethod

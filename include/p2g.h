@@ -178,6 +178,27 @@ int p2g_prove_columns(p2g_circuit* c, const uint64_t* const* wire_columns, const
                       size_t num_public_inputs, const uint64_t* forced_pow_witness, int compressed, uint8_t* out,
                       size_t* out_len, p2g_timings* timings);
 
+/* ---- verification key -------------------------------------------------------------------------------
+ * `verifier_data().to_bytes(&BackendGateSerializer)` -- the file `write_vk` writes (write_vk_action.rs:76-79) -- from a circuit
+ * handle, so the CLI does not have to rebuild the circuit a second time for it: VerifierOnlyCircuitData (cap height, the
+ * constants_sigmas cap, circuit_digest) followed by CommonCircuitData (config, FRI params, selectors, counts, k_is, gate list
+ * with the tags of the 22-entry BackendGateSerializer list, write_vk_action.rs:37-61, and each gate's own payload, e.g.
+ * add_many_u32.rs:94-97).  The CircuitConfig / FriConfig fields the prover never reads travel in p2g_vk_config (NULL = the
+ * values of CircuitConfig::wide_ecc_config(), circuit_translation/mod.rs:69).  out == NULL or too small: P2G_ESMALLBUF with
+ * the size in *out_len.  plonky2's layout is restated from util/serialization.rs of the un-vendored crate; no VK file is committed
+ * in the reference, so this layout is NOT pinned by a golden vector. */
+typedef struct p2g_vk_config {
+    uint32_t struct_size;                /* = sizeof(p2g_vk_config)                                                          */
+    uint32_t config_num_constants;       /* config.num_constants (2)                                                         */
+    uint32_t security_bits;              /* config.security_bits (100)                                                       */
+    uint32_t max_quotient_degree_factor; /* config.max_quotient_degree_factor (8)                                            */
+    uint32_t use_base_arithmetic_gate;   /* config.use_base_arithmetic_gate (1)                                              */
+    uint32_t zero_knowledge;             /* config.zero_knowledge (0) = fri_params.hiding                                    */
+    uint32_t reduction_strategy;         /* FriReductionStrategy: 0 Fixed(reduction_arity_bits), 1 ConstantArityBits, 2 MinSize */
+    uint32_t strategy_params[2];         /* ConstantArityBits(4, 5); MinSize: {is_some, max}                                 */
+} p2g_vk_config;
+int p2g_vk_bytes(const p2g_circuit* c, const p2g_vk_config* cfg, uint8_t* out, size_t* out_len);
+
 /* Upper bound of the proof size; also what p2g_prove* return in *out_len (with P2G_ESMALLBUF) when out == NULL. */
 size_t p2g_proof_size_bound(const p2g_circuit* c);
 

@@ -302,6 +302,30 @@ class CircuitData {
         pw.proof_bytes.resize(len);
         return pw;
     }
+    // The witness as plonky2 holds it: one pointer per MatrixWitness.wire_values[col] (N words each, any representative < 2^64).
+    ProofWithPublicInputs prove_columns(const std::vector<const uint64_t*>& wire_columns, const std::vector<uint64_t>& public_inputs,
+                                        const uint64_t* forced_pow_witness = nullptr, bool compressed = false) {
+        if (wire_columns.size() != common.config.num_wires) throw std::invalid_argument("one column pointer per wire expected");
+        ProofWithPublicInputs pw;
+        pw.public_inputs = public_inputs;
+        pw.compressed = compressed;
+        pw.proof_bytes.resize(p2g_proof_size_bound(h_));
+        size_t len = pw.proof_bytes.size();
+        check(p2g_prove_columns(h_, wire_columns.data(), public_inputs.data(), public_inputs.size(), forced_pow_witness, compressed ? 1 : 0,
+                                pw.proof_bytes.data(), &len, &pw.timings));
+        pw.proof_bytes.resize(len);
+        return pw;
+    }
+    // verifier_data().to_bytes(&BackendGateSerializer): the file `write_vk` writes (write_vk_action.rs:76-79)
+    std::vector<uint8_t> verifier_data_bytes(const p2g_vk_config* cfg = nullptr) const {
+        size_t len = 0;
+        int rc = p2g_vk_bytes(h_, cfg, nullptr, &len);
+        if (rc != P2G_ESMALLBUF) check(rc);
+        std::vector<uint8_t> out(len);
+        check(p2g_vk_bytes(h_, cfg, out.data(), &len));
+        out.resize(len);
+        return out;
+    }
     p2g_circuit* handle() const { return h_; }
 
   private:

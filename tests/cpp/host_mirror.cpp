@@ -83,6 +83,15 @@ int main(int argc, char** argv) {
             p2g::ProofWithPublicInputs b = data.prove(wires.data(), pis, nullptr, true);
             write_bin(std::string(argv[5]) + ".proof", a.to_bytes());
             write_bin(std::string(argv[5]) + ".cproof", b.to_bytes());
+            // the witness as separately allocated columns (MatrixWitness.wire_values) and the VK file bytes
+            std::vector<std::vector<uint64_t>> colv(cfg.num_wires);
+            std::vector<const uint64_t*> colp(cfg.num_wires);
+            for (uint32_t c = 0; c < cfg.num_wires; c++) {
+                colv[c].assign(wires.begin() + (size_t)c * n, wires.begin() + (size_t)(c + 1) * n);
+                colp[c] = colv[c].data();
+            }
+            if (data.prove_columns(colp, pis).to_bytes() != a.to_bytes()) return 5;
+            write_bin(std::string(argv[5]) + ".vk", data.verifier_data_bytes());
             std::vector<uint8_t> cap;
             for (auto& c : data.constants_sigmas_cap) cap.insert(cap.end(), c.begin(), c.end());
             write_bin(std::string(argv[5]) + ".cap", cap);

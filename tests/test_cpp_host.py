@@ -56,6 +56,7 @@ def test_cpp_circuit_data_proves_the_same_bytes(p2g, exe, tmp_path, bits, worklo
         want = data.prove(sc.wires, sc.public_inputs).to_bytes()
         want_c = data.prove(sc.wires, sc.public_inputs, compressed=True).to_bytes()
         cap = b"".join(data.constants_sigmas_cap)
+        vk = data.verifier_data_bytes()
     (tmp_path / "spec").write_text(spec_text(sc.common, p2g.lib.HASHER_ID[hasher], sc.public_inputs))
     np.ascontiguousarray(sc.constants_sigmas).tofile(tmp_path / "cs.bin")
     np.ascontiguousarray(sc.wires).tofile(tmp_path / "wires.bin")
@@ -65,3 +66,4 @@ def test_cpp_circuit_data_proves_the_same_bytes(p2g, exe, tmp_path, bits, worklo
     assert (tmp_path / "out.proof").read_bytes() == want
     assert (tmp_path / "out.cproof").read_bytes() == want_c
     assert (tmp_path / "out.cap").read_bytes() == cap
+    assert (tmp_path / "out.vk").read_bytes() == vk

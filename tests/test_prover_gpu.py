@@ -144,6 +144,26 @@ def test_prove_columns_takes_the_witness_as_plonky2_holds_it(p2g, corc):
         assert rc == p2g.lib.P2G_ESMALLBUF and ln.value == p2g.lib.lib().p2g_proof_size_bound(data._h)
 
 
+@pytest.mark.parametrize("workload,hasher,npi", [("all_gates", "keccak25", 2), ("ecdsa", "poseidon", 0)])
+def test_verifier_data_bytes_round_trip(p2g, workload, hasher, npi):
+    """p2g_vk_bytes (write_vk_action.rs:76-79) == the oracle's writer, and the oracle's parser reads every field back."""
+    from helpers import oracle_cd
+    from oracle.pyref import vk
+    cfg = p2g.CircuitConfig.wide_ecc_config(hasher=hasher)
+    sc = p2g.synth.SyntheticCircuit(7, workload, config=cfg, num_public_inputs=npi, seed=31)
+    cd = oracle_cd(sc.common)
+    with p2g.CircuitData(sc.common, sc.constants_sigmas) as data:
+        raw = data.verifier_data_bytes()
+        assert raw == vk.serialize_verifier_data(cd, data.constants_sigmas_cap, data.circuit_digest)
+        v = vk.parse_verifier_data(raw, sc.common.hash_size)
+        assert v["constants_sigmas_cap"] == data.constants_sigmas_cap and v["circuit_digest"] == data.circuit_digest
+        assert v["gates"] == [(g.kind, tuple(list(g.params) + [0] * (4 - len(g.params)))[:4]) for g in sc.common.gates]
+        assert v["selector_indices"] == sc.common.selector_indices and v["groups"] == [tuple(x) for x in sc.common.groups]
+        assert v["k_is"] == sc.common.k_is and v["fri_params"]["degree_bits"] == 7
+        assert v["config"]["num_wires"] == 234 and v["config"]["fri_config"]["reduction_strategy"] == ("ConstantArityBits", 4, 5)
+        assert v["num_public_inputs"] == npi and v["num_partial_products"] == 9
+
+
 def test_invalid_witness_is_rejected_by_the_verifier(p2g, corc):
     """The reference's negative tests panic in witness generation (before the seam); at the seam a bad trace still yields
     bytes, and those must NOT verify."""
