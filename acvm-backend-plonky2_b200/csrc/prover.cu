@@ -52,10 +52,10 @@ struct ZppParams {
 // q[c][m][i] = prod_{r in chunk m} (w_r + beta k_r x + gamma) / (w_r + beta sigma_r + gamma) at row i
 __global__ void __launch_bounds__(128) k_zpp_chunks(const __grid_constant__ ZppParams P, const u64* __restrict__ wires, size_t wires_cs,
                                                     const u64* __restrict__ sigmas, const u64* __restrict__ xtab, int xsplit,
-                                                    u64* __restrict__ q) {
+                                                    u64* __restrict__ q, size_t i0, size_t i1) {
     const size_t n = (size_t)1 << P.logn;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // rows [i0, i1): a coset-sharded rank computes its row block
+    if (i >= i1) return;
     const int c = blockIdx.y;
     const u64 x = tab_pow_d(xtab, xsplit, (u32)i);
     const u64 beta = P.betas[c], gamma = P.gammas[c];
@@ -89,19 +89,22 @@ __global__ void __launch_bounds__(128) k_zpp_chunks(const __grid_constant__ ZppP
 #define SCAN_CH 16  // rows per thread in the scans
 
 // phase 1: totals[c][t] = prod over rows of chunk t of prod_m q[c][m][row]
-__global__ void k_zscan_totals(const __grid_constant__ ZppParams P, const u64* __restrict__ q, u64* __restrict__ totals, size_t nt) {
+// chunks [t0, t0 + nt) of 16 rows (a rank's row block); totals is indexed by the local chunk number
+__global__ void k_zscan_totals(const __grid_constant__ ZppParams P, const u64* __restrict__ q, u64* __restrict__ totals, size_t nt,
+                               size_t t0) {
     const size_t n = (size_t)1 << P.logn;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     const int c = blockIdx.y;
     u64 acc = 1;
-    size_t hi = min(n, (t + 1) * SCAN_CH);
-    for (size_t i = t * SCAN_CH; i < hi; i++)
+    size_t hi = min(n, (t0 + t + 1) * SCAN_CH);
+    for (size_t i = (t0 + t) * SCAN_CH; i < hi; i++)
         for (int m = 0; m < P.nchunk; m++) acc = gl_mul(acc, q[((size_t)c * P.nchunk + m) * n + i]);
     totals[(size_t)c * nt + t] = acc;
 }
 // phase 2: exclusive prefix product of totals, one block per challenge
-__global__ void __launch_bounds__(1024) k_scan_mul_excl(u64* totals, size_t nt) {
+// block_total (optional): the product of all nt entries of block b goes to block_total[b]
+__global__ void __launch_bounds__(1024) k_scan_mul_excl(u64* totals, size_t nt, u64* block_total) {
     __shared__ u64 sh[1024];
     u64* tt = totals + (size_t)blockIdx.x * nt;
     const int T = blockDim.x;
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(1024) k_scan_mul_excl(u64* totals, size_t nt) 
         sh[threadIdx.x] = gl_mul(sh[threadIdx.x], v);
         __syncthreads();
     }
+    if (block_total && threadIdx.x == T - 1) block_total[blockIdx.x] = sh[T - 1];
     u64 carry = threadIdx.x ? sh[threadIdx.x - 1] : 1;
     for (size_t i = lo; i < hi; i++) {
         u64 v = tt[i];
@@ -125,15 +129,17 @@ __global__ void __launch_bounds__(1024) k_scan_mul_excl(u64* totals, size_t nt) 
     }
 }
 // phase 3: write Z (column c) and the partial products (column NC + c*NPP + m)
+// rank_totals (sharded): [world][NC] products of every rank's row block; rows of this rank start at Z = prod of the ranks before it
 __global__ void k_zscan_apply(const __grid_constant__ ZppParams P, const u64* __restrict__ q, const u64* __restrict__ totals, size_t nt,
-                              u64* __restrict__ out) {
+                              u64* __restrict__ out, size_t t0, const u64* __restrict__ rank_totals, int rank) {
     const size_t n = (size_t)1 << P.logn;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     const int c = blockIdx.y, NC = P.num_challenges, NPP = P.nchunk - 1;
     u64 z = totals[(size_t)c * nt + t];
-    size_t hi = min(n, (t + 1) * SCAN_CH);
-    for (size_t i = t * SCAN_CH; i < hi; i++) {
+    for (int r = 0; r < rank; r++) z = gl_mul(z, rank_totals[r * NC + c]);
+    size_t hi = min(n, (t0 + t + 1) * SCAN_CH);
+    for (size_t i = (t0 + t) * SCAN_CH; i < hi; i++) {
         out[(size_t)c * n + i] = z;
         u64 acc = z;
         for (int m = 0; m < P.nchunk; m++) {
@@ -148,12 +154,18 @@ __global__ void k_zscan_apply(const __grid_constant__ ZppParams P, const u64* __
 // openings: sum_i c_i z^i in F_{p^2} against a table of powers (plonk/proof.rs OpeningSet::new; App. A.9)
 // ---------------------------------------------------------------------------------------------------------------------
 // tab[0..n) = re(z^i), tab[n..2n) = im(z^i)
+// one square-and-multiply per 16 consecutive powers (a thread per power spent 40 extension multiplies on each)
+#define POW_RUN 16
 __global__ void k_e2_powers(u64* tab, size_t n, e2 z) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * POW_RUN;
     if (i >= n) return;
     e2 p = e2_pow(z, i);
-    tab[i] = p.c0;
-    tab[n + i] = p.c1;
+    const size_t hi = min(n, i + POW_RUN);
+    for (; i < hi; i++) {
+        tab[i] = p.c0;
+        tab[n + i] = p.c1;
+        p = e2_mul(p, z);
+    }
 }
 
 #define EVAL_SPLIT 16384  // coefficients per block
@@ -195,10 +207,10 @@ struct CombineArgs {
 };
 // u[b][0/1][k] = (sum_j alpha^j poly_{b,j}[k]) * z_b^k ;  batch 0 = every polynomial, batch 1 = the Z polynomials
 __global__ void __launch_bounds__(128) k_fri_combine(CombineArgs a, const e2* __restrict__ apow, const u64* __restrict__ ztab0,
-                                                     const u64* __restrict__ ztab1, u64* __restrict__ u) {
+                                                     const u64* __restrict__ ztab1, u64* __restrict__ u, size_t k0, size_t k1) {
     const size_t n = (size_t)1 << a.logn;
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    size_t k = k0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // coefficients [k0, k1): a coset-sharded rank combines its block
+    if (k >= k1) return;
     u64 r0 = 0, r1 = 0, z0 = 0, z1 = 0;
     int j = 0;
     for (int o = 0; o < 4; o++) {
@@ -324,6 +336,24 @@ __global__ void k_canonicalize(u64* __restrict__ v, size_t count) {
     }
 }
 
+// the same two over rows [0, rows) of `ncols` columns of pitch `pitch` (a sharded rank's share of the routed columns)
+__global__ void k_check_canonical_2d(const u64* __restrict__ v, size_t pitch, size_t rows, int ncols, int* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, count = rows * ncols;
+    bool bad = false;
+    for (; i < count; i += stride) bad |= v[(i / rows) * pitch + i % rows] >= GL_P;
+    if (bad) *flag = 1;
+}
+__global__ void k_canonicalize_2d(u64* __restrict__ v, size_t pitch, size_t rows, int ncols) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, count = rows * ncols;
+    for (; i < count; i += stride) {
+        u64* p = v + (i / rows) * pitch + i % rows;
+        const u64 x = *p;
+        if (x >= GL_P) *p = x - GL_P;
+    }
+}
+
 // query phase gathers
 __global__ void k_gather_rows(const u64* __restrict__ lde, size_t cs, int ncols, const u32* __restrict__ idx, int nq,
                               u64* __restrict__ out) {
@@ -396,7 +426,7 @@ struct p2g_circuit {
         int logcur = 0, ab = 0;
     };
     struct {
-        dbuf<u64> q, totals, ztab0, ztab1, u, fin, coeffs_a, coeffs_b, rows;
+        dbuf<u64> q, totals, rank_totals, ztab0, ztab1, u, fin, coeffs_a, coeffs_b, rows;
         dbuf<e2> partial, apow;
         dbuf<unsigned long long> best;
         dbuf<u32> idx;
@@ -408,6 +438,10 @@ struct p2g_circuit {
     // [z0, z0 + nzl) = leaves [j0, j0 + lde_l) of every oracle: their LDE columns, their Merkle subtrees down to the
     // cap entries [cap0, cap0 + ncap_l), their share of the quotient evaluation and of the query openings.
     int rank = 0, world = 1, logworld = 0;
+    // rows [row0, row1) of the trace are this rank's share of the row-parallel stages (Z / partial products, the FRI batch
+    // combination): all of them on a single GPU, N / world consecutive rows when sharded and N / world >= 1024
+    bool row_shard = false;
+    size_t row0 = 0, row1 = 0;
     int z0 = 0, nzl = 0, ncap_l = 0, cap0 = 0;
     size_t lde_l = 0, j0 = 0;
     int loglde_l = 0;
@@ -527,6 +561,26 @@ void shard_allgather(p2g_circuit* C, const void* send, void* recv, size_t bytes,
     if (is_device) CUDA_CHECK(cudaStreamSynchronize(C->ctx->stream));   // the host binding runs on its own stream
     int rc = C->allgather(C->allgather_user, send, recv, bytes, is_device ? 1 : 0);
     if (rc != 0) throw p2g_error(P2G_ENCCL, "allgather callback failed (" + std::to_string(rc) + ")");
+}
+
+// Row blocks of `ncols` columns: rank r holds rows [r * per, (r + 1) * per) of every column (column c at base + c * cs); afterwards
+// every rank holds every row.  NCCL: the per-column in-place all-gathers form one group (one launch); callback: one call per column.
+void shard_allgather_cols(p2g_circuit* C, u64* base, int ncols, size_t cs, size_t per) {
+    if (C->nccl) {
+        if (C->nccl_dead) throw p2g_error(P2G_ENCCL, "the NCCL communicator of this handle was aborted by an earlier failure");
+        C->collectives++;
+        nccl_check(C, nccl_api().GroupStart(), "ncclGroupStart");
+        for (int col = 0; col < ncols; col++) {
+            u64* colp = base + (size_t)col * cs;
+            nccl_check(C, nccl_api().AllGather(colp + (size_t)C->rank * per, colp, per * 8, ncclUint8, C->nccl, C->ctx->stream), "ncclAllGather");
+        }
+        nccl_check(C, nccl_api().GroupEnd(), "ncclGroupEnd");
+        return;
+    }
+    for (int col = 0; col < ncols; col++) {
+        u64* colp = base + (size_t)col * cs;
+        shard_allgather(C, colp + (size_t)C->rank * per, colp, per * 8, true);
+    }
 }
 
 // coefficients already in b.coeffs: LDE of this rank's cosets + their Merkle subtrees
@@ -855,6 +909,9 @@ static int circuit_create_impl(const p2g_circuit_desc* desc, int device, int ran
         C->loglde_l = C->loglde - logworld;
         C->lde_l = C->lde >> logworld;
         C->j0 = (size_t)rank * C->lde_l;
+        C->row_shard = world > 1 && (C->n >> logworld) >= 1024 && !getenv("P2G_NO_ROW_SHARD");
+        C->row0 = C->row_shard ? (size_t)rank * (C->n >> logworld) : 0;
+        C->row1 = C->row_shard ? C->row0 + (C->n >> logworld) : C->n;
         C->nzl = (1 << desc->rate_bits) >> logworld;
         C->z0 = rank * C->nzl;
         C->h = desc->hasher;
@@ -1147,7 +1204,16 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             if (rg[1] <= rg[0]) continue;
             // raw GoldilocksField words (p2g_prove_columns): the block was reduced chunk by chunk before its inverse NTT; the routed
             // columns outside the block are reduced here, before the Z computation reads them
-            if (canonicalize && ri > 0) canon_chunk(C, &C->up, d_wires, n, rg[0], rg[1]);
+            if (ri > 0 && C->up.active) {
+                // only rows [row0, row1) of these columns were uploaded (all rows when the rank is not row-sharded)
+                const size_t rows = C->row1 - C->row0, cnt2 = rows * (size_t)(rg[1] - rg[0]);
+                const unsigned blocks2 = (unsigned)std::min<size_t>((cnt2 + 255) / 256, 148 * 16);
+                u64* base = const_cast<u64*>(d_wires) + (size_t)rg[0] * n + C->row0;
+                if (canonicalize) k_canonicalize_2d<<<blocks2, 256, 0, st>>>(base, n, rows, rg[1] - rg[0]);
+                k_check_canonical_2d<<<blocks2, 256, 0, st>>>(base, n, rows, rg[1] - rg[0], flag);
+                count_launch(c, canonicalize ? 2 : 1);
+                continue;
+            }
             size_t cnt = (size_t)(rg[1] - rg[0]) * n;
             unsigned blocks = (unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 16);
             k_check_canonical<<<blocks, 256, 0, st>>>(d_wires + (size_t)rg[0] * n, cnt, flag);
@@ -1185,18 +1251,24 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         }
         int xsplit;
         const u64* xtab = c->get_powtab(logn, gl_root_of_unity(logn), 1, &xsplit);
-        size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
+        // rows [row0, row1) only: a sharded rank computes its row block; the running product enters each block through the
+        // all-gathered per-rank block products, and the 20 value columns are completed by a row all-gather
+        const size_t rows = C->row1 - C->row0;
+        const size_t nt = (rows + SCAN_CH - 1) / SCAN_CH, t0 = C->row0 / SCAN_CH;
         u64* q = ensure(C->ws.q, (size_t)NC * nchunk * n);
-        u64* totals = ensure(C->ws.totals, 4 * nt);
-        dim3 g1((unsigned)((n + 127) / 128), NC);
+        u64* totals = ensure(C->ws.totals, 4 * ((n + SCAN_CH - 1) / SCAN_CH));
+        u64* rank_totals = ensure(C->ws.rank_totals, (size_t)C->world * NC);
+        dim3 g1((unsigned)((rows + 127) / 128), NC);
         if (C->up.active && C->up.routed) CUDA_CHECK(cudaStreamWaitEvent(st, C->up.routed, 0));
-        k_zpp_chunks<<<g1, 128, 0, st>>>(zp, d_wires, n, C->sigma_values.p, xtab, xsplit, q);
+        k_zpp_chunks<<<g1, 128, 0, st>>>(zp, d_wires, n, C->sigma_values.p, xtab, xsplit, q, C->row0, C->row1);
         dim3 g2((unsigned)((nt + 127) / 128), NC);
-        k_zscan_totals<<<g2, 128, 0, st>>>(zp, q, totals, nt);
-        k_scan_mul_excl<<<NC, 1024, 0, st>>>(totals, nt);
-        k_zscan_apply<<<g2, 128, 0, st>>>(zp, q, totals, nt, C->zpp_values.p);
+        k_zscan_totals<<<g2, 128, 0, st>>>(zp, q, totals, nt, t0);
+        k_scan_mul_excl<<<NC, 1024, 0, st>>>(totals, nt, rank_totals + (size_t)C->rank * NC);
+        if (C->row_shard) shard_allgather(C, rank_totals + (size_t)C->rank * NC, rank_totals, (size_t)NC * 8, true);
+        k_zscan_apply<<<g2, 128, 0, st>>>(zp, q, totals, nt, C->zpp_values.p, t0, rank_totals, C->row_shard ? C->rank : 0);
         count_launch(c, 4);
         CUDA_CHECK(cudaGetLastError());
+        if (C->row_shard) shard_allgather_cols(C, C->zpp_values.p, nzp, n, rows);
         tr.mark("zpp launches");
         commit_from_values(C, C->zpp, C->zpp_values.p, n);
         tr.mark("zpp commit launched");
@@ -1270,31 +1342,44 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
     const int total = P + W + nzp + nq;
     u64* ztab0 = ensure(C->ws.ztab0, 2 * n);
     u64* ztab1 = ensure(C->ws.ztab1, 2 * n);
-    k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0, n, zeta);
-    k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1, n, zeta_next);
+    k_e2_powers<<<(unsigned)((n / POW_RUN + 128) / 128), 128, 0, st>>>(ztab0, n, zeta);
+    k_e2_powers<<<(unsigned)((n / POW_RUN + 128) / 128), 128, 0, st>>>(ztab1, n, zeta_next);
     count_launch(c, 2);
     const int nsplit = (int)((n + EVAL_SPLIT - 1) / EVAL_SPLIT);
     std::vector<e2> op(total), zs_next(NC);
     {
-        e2* partial = ensure(C->ws.partial, (size_t)(total + NC) * nsplit);
+        // evaluation g of the opening set: polynomial g of the four oracles at zeta (g < total), Z_{g - total} at g zeta.  A sharded
+        // rank evaluates the slice [g0, g1) -- every rank holds every coefficient -- and the values are all-gathered.
+        const int nev = total + NC;
+        const bool split_evals = C->row_shard;
+        const int per = split_evals ? (nev + C->world - 1) / C->world : nev;
+        const int g0 = split_evals ? std::min(nev, C->rank * per) : 0, g1 = std::min(nev, g0 + per);
+        e2* partial = ensure(C->ws.partial, (size_t)nev * nsplit);
         int off = 0;
-        for (int o = 0; o < 4; o++) {
-            dim3 grid(widths[o], nsplit);
-            k_eval_polys<<<grid, 256, 0, st>>>(oracles[o]->coeffs.p, n, n, ztab0, partial + (size_t)off * nsplit, nsplit);
-            off += widths[o];
+        for (int o = 0; o < 5; o++) {
+            const int width = o < 4 ? widths[o] : NC;
+            const int lo = std::max(g0, off), hi = std::min(g1, off + width);
+            if (hi > lo) {
+                const u64* cf = (o < 4 ? oracles[o]->coeffs.p : C->zpp.coeffs.p) + (size_t)(lo - off) * n;
+                dim3 grid(hi - lo, nsplit);
+                k_eval_polys<<<grid, 256, 0, st>>>(cf, n, n, o < 4 ? ztab0 : ztab1, partial + (size_t)lo * nsplit, nsplit);
+                count_launch(c);
+            }
+            off += width;
         }
-        dim3 grid(NC, nsplit);
-        k_eval_polys<<<grid, 256, 0, st>>>(C->zpp.coeffs.p, n, n, ztab1, partial + (size_t)total * nsplit, nsplit);
-        count_launch(c, 5);
         CUDA_CHECK(cudaGetLastError());
-        std::vector<e2> hp((size_t)(total + NC) * nsplit);
-        CUDA_CHECK(cudaMemcpyAsync(hp.data(), partial, hp.size() * sizeof(e2), cudaMemcpyDeviceToHost, st));
+        std::vector<e2> hp((size_t)std::max(per, 1) * nsplit), vals((size_t)per * (split_evals ? C->world : 1));
+        if (g1 > g0) CUDA_CHECK(cudaMemcpyAsync(hp.data(), partial + (size_t)g0 * nsplit, (size_t)(g1 - g0) * nsplit * sizeof(e2), cudaMemcpyDeviceToHost, st));
         stream_sync(C);
-        for (int i = 0; i < total + NC; i++) {
-            e2 s = e2_make(0, 0);
-            for (int k = 0; k < nsplit; k++) s = e2_add(s, hp[(size_t)i * nsplit + k]);
-            if (i < total) op[i] = s;
-            else zs_next[i - total] = s;
+        for (int i = 0; i < g1 - g0; i++) {
+            e2 sacc = e2_make(0, 0);
+            for (int k = 0; k < nsplit; k++) sacc = e2_add(sacc, hp[(size_t)i * nsplit + k]);
+            vals[(size_t)(split_evals ? C->rank * per : 0) + i] = sacc;
+        }
+        if (split_evals) shard_allgather(C, vals.data() + (size_t)C->rank * per, vals.data(), (size_t)per * sizeof(e2), false);
+        for (int i = 0; i < nev; i++) {
+            if (i < total) op[i] = vals[i];
+            else zs_next[i - total] = vals[i];
         }
     }
     for (int i = 0; i < total; i++) ch.observe_e2(op[i]);
@@ -1324,7 +1409,8 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         ca.num_challenges = NC;
         ca.logn = logn;
         u64* u = ensure(C->ws.u, 4 * n);
-        k_fri_combine<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ca, d_apow, ztab0, ztab1, u);
+        k_fri_combine<<<(unsigned)((C->row1 - C->row0 + 127) / 128), 128, 0, st>>>(ca, d_apow, ztab0, ztab1, u, C->row0, C->row1);
+        if (C->row_shard) shard_allgather_cols(C, u, 4, n, C->row1 - C->row0);
         // tables of inverse powers (reuse the forward tables' storage after the combine)
         e2 zi0, zi1;  // inverse in F_{p^2}: z^-1 = conj(z) / norm(z)
         {
@@ -1336,8 +1422,8 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
             zi0 = inv2(zeta);
             zi1 = inv2(zeta_next);
         }
-        k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab0, n, zi0);
-        k_e2_powers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ztab1, n, zi1);
+        k_e2_powers<<<(unsigned)((n / POW_RUN + 128) / 128), 128, 0, st>>>(ztab0, n, zi0);
+        k_e2_powers<<<(unsigned)((n / POW_RUN + 128) / 128), 128, 0, st>>>(ztab1, n, zi1);
         size_t nt = (n + SCAN_CH - 1) / SCAN_CH;
         u64* totals = ensure(C->ws.totals, 4 * nt);
         dim3 g2((unsigned)((nt + 127) / 128), 4);
@@ -1740,12 +1826,16 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
             auto col_ptr = [&](int col) { return cols ? cols[col] : wires + (size_t)col * n; };
             int slot = 0;
             int step = std::max(1, std::min(32, (int)(((size_t)64 << 20) / (n * 8)) + 1));   // >= 64 MB per chunk ...
-            std::function<void(int, int)> copy_cols = [&](int a, int e) {
-                if (e - a > step && !pinned) {   // staging buffers hold one chunk: split longer runs
-                    for (int x = a; x < e; x += step) copy_cols(x, std::min(e, x + step));
+            // rows [r0, r1) of columns [a, e) -> the same place of the device staging matrix
+            std::function<void(int, int, size_t, size_t)> copy_block = [&](int a, int e, size_t r0, size_t r1) {
+                const size_t nr = r1 - r0;
+                const int fit = (int)std::max<size_t>(1, ((size_t)step * n) / nr);   // columns of nr rows per staging buffer
+                if (e - a > fit && !pinned) {   // staging buffers hold one chunk: split longer runs
+                    for (int x = a; x < e; x += fit) copy_block(x, std::min(e, x + fit), r0, r1);
                     return;
                 }
-                const size_t words = (size_t)(e - a) * n;
+                const size_t words = (size_t)(e - a) * nr;
+                u64* d_dst = C->wires_values.p + (size_t)a * n + r0;
                 if (!pinned && words * 8 >= ((size_t)1 << 20)) {
                     // stage through pinned memory: wait for the slot's previous DMA, fill it with 8 threads, DMA from it
                     if (up.stage_words < words) {
@@ -1768,24 +1858,27 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
                         size_t lo = words * t / T, hi = words * (t + 1) / T;
                         th[t] = std::thread([=] {
                             for (size_t x = lo; x < hi;) {
-                                const size_t col = x / n, r = x % n, run = std::min(n - r, hi - x);
-                                memcpy(dst + x, col_ptr(a + (int)col) + r, run * 8);
+                                const size_t col = x / nr, r = x % nr, run = std::min(nr - r, hi - x);
+                                memcpy(dst + x, col_ptr(a + (int)col) + r0 + r, run * 8);
                                 x += run;
                             }
                         });
                     }
                     for (int t = 0; t < T; t++) th[t].join();
-                    CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)a * n, dst, words * 8, cudaMemcpyHostToDevice, up.copy));
+                    if (nr == n) CUDA_CHECK(cudaMemcpyAsync(d_dst, dst, words * 8, cudaMemcpyHostToDevice, up.copy));
+                    else CUDA_CHECK(cudaMemcpy2DAsync(d_dst, n * 8, dst, nr * 8, nr * 8, e - a, cudaMemcpyHostToDevice, up.copy));
                     CUDA_CHECK(cudaEventRecord(up.stage_free[slot], up.copy));
                     slot = (slot + 1) % p2g_circuit::Upload::NSTAGE;
                 } else if (!cols) {
-                    CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)a * n, col_ptr(a), words * 8, cudaMemcpyHostToDevice, up.copy));
+                    if (nr == n) CUDA_CHECK(cudaMemcpyAsync(d_dst, col_ptr(a), words * 8, cudaMemcpyHostToDevice, up.copy));
+                    else CUDA_CHECK(cudaMemcpy2DAsync(d_dst, n * 8, col_ptr(a) + r0, n * 8, nr * 8, e - a, cudaMemcpyHostToDevice, up.copy));
                 } else {
                     for (int x = a; x < e; x++)
-                        CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)x * n, col_ptr(x), n * 8, cudaMemcpyHostToDevice, up.copy));
+                        CUDA_CHECK(cudaMemcpyAsync(C->wires_values.p + (size_t)x * n + r0, col_ptr(x) + r0, nr * 8, cudaMemcpyHostToDevice, up.copy));
                 }
                 up.bytes += (double)words * 8;
             };
+            auto copy_cols = [&](int a, int e) { copy_block(a, e, 0, n); };
             up.chunks.clear();
             up.canon = cols != nullptr;
             up.bytes = 0;
@@ -1808,9 +1901,9 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
                 up.chunks.emplace_back(a, e, ev);
                 up.last = ev;
             }
-            if (c0 > 0 || c1 < R) {   // sharded: routed columns outside the block
-                if (c0 > 0) copy_cols(0, std::min(c0, R));
-                if (c1 < R) copy_cols(c1, R);
+            if (c0 > 0 || c1 < R) {   // sharded: routed columns outside the block -- only the rows of this rank's Z / partial products
+                if (c0 > 0) copy_block(0, std::min(c0, R), C->row0, C->row1);
+                if (c1 < R) copy_block(c1, R, C->row0, C->row1);
                 up.routed = next_event();
                 CUDA_CHECK(cudaEventRecord(up.routed, up.copy));
                 up.last = up.routed;
