@@ -1,0 +1,201 @@
+"""ACIR circuits -> the payload of include/p2g.h, without the Rust layers.
+
+Mirror of the reference's `CircuitBuilderFromAcirToPlonky2` (plonky2-backend/src/circuit_translation/mod.rs:55-190): the same
+names -- `translate_circuit`, `unpack`, `witness_target_map` semantics -- over libp2acir.so (C++: the translator, the slice of
+plonky2's CircuitBuilder it drives, and the witness generators).  ACIR values are the ones the reference's test factories build by
+hand (circuit_translation/tests/factories/circuit_factory.rs): `Expression(mul_terms, linear_combinations, q_c)`, `AssertZero`,
+`BlackBoxFuncCall::{RANGE, AND, XOR}`, `MemoryInit`, `MemoryOp` (read).  Field elements are Goldilocks (mod.rs:43-45).
+"""
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import lib as _lib
+from .circuit import CircuitConfig, CircuitData, CommonCircuitData, Gate, P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libp2acir.so")
+    src = os.path.join(_HERE, "acir", "p2acir.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "acir"), "-s"])
+    return so
+
+
+def _acir_lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.p2a_last_error.restype = C.c_char_p
+        L.p2a_translate.restype = C.c_void_p
+        L.p2a_translate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.p2a_destroy.argtypes = [C.c_void_p]
+        L.p2a_shape.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.p2a_gate_types.argtypes = [C.c_void_p, C.c_void_p]
+        L.p2a_constants_sigmas.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.p2a_witness.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+class TranslationError(Exception):
+    """Where the reference panics (unsupported opcode, RANGE over 33 bits, unsatisfiable witness)."""
+
+
+# ---- ACIR values (acir::native_types / acir::circuit, the subset the translators accept) -----------------------------------
+@dataclass
+class Expression:
+    mul_terms: list = field(default_factory=list)            # [(coefficient, witness, witness)]
+    linear_combinations: list = field(default_factory=list)  # [(coefficient, witness)]
+    q_c: int = 0
+
+
+@dataclass
+class AssertZero:
+    expr: Expression
+
+
+@dataclass
+class Range:          # BlackBoxFuncCall::RANGE { input: FunctionInput { witness, num_bits } }
+    witness: int
+    num_bits: int
+
+
+@dataclass
+class And:            # BlackBoxFuncCall::AND { lhs, rhs, output }
+    lhs: int
+    rhs: int
+    num_bits: int
+    output: int
+
+
+@dataclass
+class Xor:
+    lhs: int
+    rhs: int
+    num_bits: int
+    output: int
+
+
+@dataclass
+class MemoryInit:
+    block_id: int
+    init: list
+
+
+@dataclass
+class MemoryRead:     # MemoryOp { operation = 0, index, value }
+    block_id: int
+    index: int
+    value: int
+
+
+@dataclass
+class Circuit:
+    opcodes: list
+    public_parameters: list = field(default_factory=list)
+    private_parameters: list = field(default_factory=list)
+
+
+def _encode(circuit):
+    words = []
+    for op in circuit.opcodes:
+        if isinstance(op, AssertZero):
+            e = op.expr
+            words += [1, len(e.mul_terms), len(e.linear_combinations), e.q_c % P]
+            for c, a, b in e.mul_terms:
+                words += [c % P, a, b]
+            for c, w in e.linear_combinations:
+                words += [c % P, w]
+        elif isinstance(op, Range):
+            words += [2, op.witness, op.num_bits]
+        elif isinstance(op, And):
+            words += [3, op.lhs, op.rhs, op.num_bits, op.output]
+        elif isinstance(op, Xor):
+            words += [4, op.lhs, op.rhs, op.num_bits, op.output]
+        elif isinstance(op, MemoryInit):
+            words += [5, op.block_id, len(op.init)] + list(op.init)
+        elif isinstance(op, MemoryRead):
+            words += [6, op.block_id, op.index, op.value]
+        else:
+            raise TranslationError(f"Opcode not supported yet: {op!r}")
+    return np.array(words, dtype=np.uint64)
+
+
+_ARITY = {0: 0, 1: 1, 2: 0, 3: 1, 4: 2, 5: 0, 6: 3}
+
+
+class CircuitBuilderFromAcirToPlonky2:
+    """translate_circuit(circuit) then unpack() -> (CircuitData inputs, witness generator), like mod.rs:72-83."""
+
+    def __init__(self, config=None):
+        self.config = config or CircuitConfig.wide_ecc_config()
+        if (self.config.num_wires, self.config.num_routed_wires, self.config.num_constants) != (234, 80, 2):
+            raise ValueError("the translator builds with CircuitConfig::wide_ecc_config() (circuit_translation/mod.rs:69)")
+        self._h = None
+
+    def translate_circuit(self, circuit):
+        L = _acir_lib()
+        pub = np.array(sorted(circuit.public_parameters), dtype=np.uint64)       # BTreeSet order (mod.rs:291-296)
+        priv = np.array(sorted(circuit.private_parameters), dtype=np.uint64)
+        ops = _encode(circuit)
+        h = L.p2a_translate(pub.ctypes.data_as(C.c_void_p), len(pub), priv.ctypes.data_as(C.c_void_p), len(priv),
+                            ops.ctypes.data_as(C.c_void_p), len(ops))
+        if not h:
+            raise TranslationError(L.p2a_last_error().decode())
+        self._h = C.c_void_p(h)
+        db, ng, npub = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        L.p2a_shape(self._h, C.byref(db), C.byref(ng), C.byref(npub))
+        raw = np.zeros(5 * ng.value, dtype=np.uint32)
+        L.p2a_gate_types(self._h, raw.ctypes.data_as(C.c_void_p))
+        types = [Gate(int(raw[5 * i]), tuple(int(x) for x in raw[5 * i + 1:5 * i + 5])) for i in range(ng.value)]
+        self.common = CommonCircuitData(self.config, db.value, types, npub.value)
+        com = self.common
+        # preprocessed polynomials for the sorted gate table
+        table = (_lib.GateS * len(com.gates))()
+        for i, g in enumerate(com.gates):
+            table[i].kind = g.kind
+            for k in range(4):
+                table[i].params[k] = g.params[k]
+            table[i].selector_index = com.selector_indices[i]
+            table[i].group_lo, table[i].group_hi = com.groups[com.selector_indices[i]]
+            table[i].num_constraints = g.num_constraints
+        t2g = np.array([com.gate_index(t) for t in types], dtype=np.uint32)
+        k_is = np.array(com.k_is, dtype=np.uint64)
+        self.constants_sigmas = np.zeros((com.num_preprocessed, com.degree()), dtype=np.uint64)
+        rc = L.p2a_constants_sigmas(self._h, table, len(com.gates), t2g.ctypes.data_as(C.c_void_p), com.num_selectors, com.num_constants,
+                                    k_is.ctypes.data_as(C.c_void_p), self.constants_sigmas.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise TranslationError(L.p2a_last_error().decode())
+        return self
+
+    def generate_witness(self, witness_map):
+        """plonky2 `generate_partial_witness(..).full_witness()` for an ACIR witness map {witness index: value} (what
+        prove_action.rs:99-117 feeds in): returns (wires [234, N], public_inputs)."""
+        L = _acir_lib()
+        ids = np.array(list(witness_map.keys()), dtype=np.uint64)
+        vals = np.array([int(v) % P for v in witness_map.values()], dtype=np.uint64)
+        wires = np.zeros((self.config.num_wires, self.common.degree()), dtype=np.uint64)
+        pis = np.zeros(max(1, self.common.num_public_inputs), dtype=np.uint64)
+        rc = L.p2a_witness(self._h, ids.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p), len(ids),
+                           wires.ctypes.data_as(C.c_void_p), pis.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise TranslationError(L.p2a_last_error().decode())
+        return wires, [int(x) for x in pis[:self.common.num_public_inputs]]
+
+    def unpack(self, device=0):
+        """(CircuitData on the GPU, self): the analogue of `translator.unpack()` -> (circuit_data, witness_target_map)."""
+        return CircuitData(self.common, self.constants_sigmas, device=device), self
+
+    def close(self):
+        if self._h:
+            _acir_lib().p2a_destroy(self._h)
+            self._h = None
+
+    __del__ = close

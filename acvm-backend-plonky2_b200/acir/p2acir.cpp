@@ -1,0 +1,682 @@
+// ACIR -> gate table + witness, outside Rust.
+//
+// Host-side C++ mirror of the two reference layers that sit above the prover:
+//   * the translator  plonky2-backend/src/circuit_translation/mod.rs:72-190 (CircuitBuilderFromAcirToPlonky2::translate_circuit)
+//     with assert_zero_translator.rs:30-116 (AssertZero), mod.rs:131-137 (RANGE -> builder.range_check), mod.rs:213-232 +
+//     binary_digits_target.rs:120-186 (AND / XOR on bit decompositions), memory_translator.rs:145-171 (MemoryInit) and :125-137
+//     (memory read -> RandomAccessGate);
+//   * the part of plonky2's CircuitBuilder those translators drive (arithmetic / add / mul / mul_const / sub, constant, connect,
+//     assert_zero, split_le, le_sum, random_access, register_public_input, build()) and its witness generators
+//     (generate_partial_witness: ArithmeticBaseGenerator, BaseSplitGenerator / BaseSumGenerator, WireSplitGenerator,
+//     RandomAccessGenerator, PoseidonGenerator).
+// It emits exactly what crosses the C ABI of include/p2g.h: the gate list, the per-row gate assignment + gate constants, the
+// sigma permutation of the copy constraints, and -- from the ACIR witness map -- the full wire matrix and the public inputs.
+//
+// What it is NOT: plonky2's builder bit for bit.  Gate packing (which op lands in which row) follows the same rules
+// (operations with equal constants share a row, 20 ops per ArithmeticGate, ConstantGate rows of 2, BaseSumGate<2> of 63 limbs
+// for split_le, public-input hash through PoseidonGate rows connected to a PublicInputGate) but is not guaranteed to coincide
+// with the fork's, so its circuit_digest differs from the Rust one; every circuit it builds is a valid plonky2 circuit in the
+// reference's configuration, and proofs of it verify.  Host tooling, not on the hot path.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "../csrc/hash.cuh"
+#include "../../include/p2g.h"
+
+namespace {
+
+typedef int32_t Target;   // >= 0: index into the target table (virtual targets and wires alike)
+
+struct GateType {
+    u32 kind;
+    u32 params[4];
+    bool operator<(const GateType& o) const { return std::tie(kind, params[0], params[1], params[2], params[3]) < std::tie(o.kind, o.params[0], o.params[1], o.params[2], o.params[3]); }
+    bool operator==(const GateType& o) const { return !(*this < o) && !(o < *this); }
+};
+
+struct Row {
+    int gate;                 // index into Builder::gate_types
+    std::vector<u64> consts;  // gate-local constants
+};
+
+enum GenKind { GEN_ARITH, GEN_CONST, GEN_SPLIT, GEN_BASE_SPLIT, GEN_BASE_SUM, GEN_RANDOM_ACCESS, GEN_POSEIDON };
+struct Gen {
+    GenKind kind;
+    int row, i;         // gate row, op / copy index
+    u64 c0, c1;         // arithmetic constants / constant value
+    Target t;           // GEN_SPLIT: the integer
+    std::vector<int> rows;   // GEN_SPLIT: the BaseSum rows
+    int n;              // limbs / bits
+    bool done = false;
+};
+
+struct Error {
+    std::string msg;
+};
+
+const int NUM_WIRES = 234, NUM_ROUTED = 80, ARITH_OPS = 20, CONSTS_PER_GATE = 2, SPLIT_LIMBS = 63;
+
+struct Builder {
+    // targets: wires are created lazily as (row, col) -> id
+    std::vector<std::pair<int, int>> target_wire;   // (row, col) or (-1, -1) for virtual targets
+    std::map<std::pair<int, int>, Target> wire_target;
+    std::vector<Target> parent;                      // union-find over targets (copy constraints)
+    std::vector<Row> rows;
+    std::vector<GateType> gate_types;
+    std::map<u64, Target> constants;                 // value -> target
+    std::vector<u64> constant_order;
+    std::map<std::tuple<u64, u64>, std::pair<int, int>> free_arith;   // (c0, c1) -> (row, next op)
+    std::map<std::tuple<u64, u64, Target, Target, Target>, Target> arith_cache;
+    std::map<int, std::pair<int, int>> free_ra;      // bits -> (row, next copy)
+    std::vector<Target> public_inputs;
+    std::vector<Gen> gens;
+    bool built = false;
+    int degree_bits = 0;
+    Target pi_hash[4];
+
+    Target new_target(int row = -1, int col = -1) {
+        target_wire.emplace_back(row, col);
+        parent.push_back((Target)parent.size());
+        return (Target)parent.size() - 1;
+    }
+    Target add_virtual_target() { return new_target(); }
+    Target wire(int row, int col) {
+        auto it = wire_target.find({row, col});
+        if (it != wire_target.end()) return it->second;
+        Target t = new_target(row, col);
+        wire_target[{row, col}] = t;
+        return t;
+    }
+    Target find(Target t) {
+        while (parent[t] != t) {
+            parent[t] = parent[parent[t]];
+            t = parent[t];
+        }
+        return t;
+    }
+    void connect(Target a, Target b) {
+        for (Target t : {a, b})
+            if (target_wire[t].first >= 0 && target_wire[t].second >= NUM_ROUTED) throw Error{"connect: wire is not routable"};
+        a = find(a);
+        b = find(b);
+        if (a != b) parent[b] = a;
+    }
+    int gate_type(u32 kind, u32 p0 = 0, u32 p1 = 0, u32 p2 = 0) {
+        GateType g = {kind, {p0, p1, p2, 0}};
+        for (size_t i = 0; i < gate_types.size(); i++)
+            if (gate_types[i] == g) return (int)i;
+        gate_types.push_back(g);
+        return (int)gate_types.size() - 1;
+    }
+    int add_gate(int gt, std::vector<u64> consts = {}) {
+        rows.push_back({gt, std::move(consts)});
+        return (int)rows.size() - 1;
+    }
+
+    // ---- constants (plonky2 CircuitBuilder::constant: one virtual target per distinct value, placed in ConstantGate rows by build())
+    Target constant(u64 c) {
+        auto it = constants.find(c);
+        if (it != constants.end()) return it->second;
+        Target t = add_virtual_target();
+        constants[c] = t;
+        constant_order.push_back(c);
+        return t;
+    }
+    Target zero() { return constant(0); }
+    Target one() { return constant(1); }
+    bool is_const(Target t, u64* v) {
+        Target r = find(t);
+        for (auto& kv : constants)
+            if (find(kv.second) == r) {
+                *v = kv.first;
+                return true;
+            }
+        return false;
+    }
+
+    // ---- arithmetic: c0 * x * y + c1 * z   (gadgets/arithmetic.rs arithmetic / add_base_arithmetic_operation)
+    Target arithmetic(u64 c0, u64 c1, Target x, Target y, Target z) {
+        auto key = std::make_tuple(c0, c1, find(x), find(y), find(z));
+        auto key2 = std::make_tuple(c0, c1, find(y), find(x), find(z));
+        auto hit = arith_cache.find(key);
+        if (hit == arith_cache.end()) hit = arith_cache.find(key2);
+        if (hit != arith_cache.end()) return hit->second;
+        auto& slot = free_arith[std::make_tuple(c0, c1)];
+        if (slot.second == 0 || slot.second >= ARITH_OPS) {   // no open row for these constants
+            slot.first = add_gate(gate_type(P2G_GATE_ARITHMETIC, ARITH_OPS), {c0, c1});
+            slot.second = 0;
+        }
+        const int row = slot.first, i = slot.second++;
+        connect(x, wire(row, 4 * i));
+        connect(y, wire(row, 4 * i + 1));
+        connect(z, wire(row, 4 * i + 2));
+        Target out = wire(row, 4 * i + 3);
+        Gen g = {};
+        g.kind = GEN_ARITH;
+        g.row = row;
+        g.i = i;
+        g.c0 = c0;
+        g.c1 = c1;
+        gens.push_back(g);
+        arith_cache[key] = out;
+        return out;
+    }
+    Target mul(Target x, Target y) { return arithmetic(1, 0, x, y, x); }
+    Target add(Target x, Target y) { return arithmetic(1, 1, x, one(), y); }
+    Target sub(Target x, Target y) { return arithmetic(1, GL_P - 1, x, one(), y); }
+    Target mul_const(u64 c, Target x) { return mul(constant(c), x); }
+    Target mul_const_add(u64 c, Target x, Target y) { return arithmetic(c, 1, x, one(), y); }
+    void assert_zero(Target x) { connect(x, zero()); }
+    // bool gadgets (gadgets/arithmetic.rs and / or / not)
+    Target b_and(Target a, Target b) { return mul(a, b); }
+    Target b_or(Target a, Target b) { return add(arithmetic(GL_P - 1, 1, a, b, a), b); }
+    Target b_not(Target a) { return sub(one(), a); }
+    Target b_xor(Target a, Target b) {   // binary_digits_target.rs:169-175: (a or b) and not (a and b)
+        return b_and(b_or(a, b), b_not(b_and(a, b)));
+    }
+
+    // ---- split_le (gadgets/split_base.rs / split_join.rs): BaseSumGate<2> rows of 63 limbs, unused limbs tied to zero
+    std::vector<Target> split_le(Target x, int nbits) {
+        std::vector<Target> bits;
+        if (nbits == 0) return bits;
+        const int k = (nbits + SPLIT_LIMBS - 1) / SPLIT_LIMBS;
+        std::vector<int> grows;
+        for (int g = 0; g < k; g++) grows.push_back(add_gate(gate_type(P2G_GATE_BASE_SUM, 2, SPLIT_LIMBS)));
+        for (int g : grows)
+            for (int l = 0; l < SPLIT_LIMBS; l++) bits.push_back(wire(g, 1 + l));
+        for (size_t b = nbits; b < bits.size(); b++) assert_zero(bits[b]);
+        bits.resize(nbits);
+        u64 base = gl_pow(2, SPLIT_LIMBS);
+        Target acc = zero();
+        for (int g = k - 1; g >= 0; g--) acc = mul_const_add(base, acc, wire(grows[g], 0));
+        connect(acc, x);
+        Gen sg = {};
+        sg.kind = GEN_SPLIT;
+        sg.t = x;
+        sg.rows = grows;
+        sg.n = SPLIT_LIMBS;
+        gens.push_back(sg);
+        for (int g : grows) {
+            Gen bg = {};
+            bg.kind = GEN_BASE_SPLIT;
+            bg.row = g;
+            bg.n = SPLIT_LIMBS;
+            gens.push_back(bg);
+        }
+        return bits;
+    }
+    void range_check(Target x, int nbits) { split_le(x, nbits); }
+    // le_sum (gadgets/split_base.rs): one BaseSumGate<2> with exactly bits.size() limbs
+    Target le_sum(const std::vector<Target>& bits) {
+        if (bits.empty()) return zero();
+        if ((int)bits.size() > SPLIT_LIMBS) throw Error{"le_sum: more than 63 bits"};
+        const int row = add_gate(gate_type(P2G_GATE_BASE_SUM, 2, (u32)bits.size()));
+        for (size_t i = 0; i < bits.size(); i++) connect(bits[i], wire(row, 1 + (int)i));
+        Gen g = {};
+        g.kind = GEN_BASE_SUM;
+        g.row = row;
+        g.n = (int)bits.size();
+        gens.push_back(g);
+        return wire(row, 0);
+    }
+    // random_access (gadgets/random_access.rs): RandomAccessGate::new_from_config(bits): copies = min(routed / (2 + 2^bits), ...)
+    static int ra_copies(int bits) {
+        const int vec = 1 << bits;
+        int by_routed = NUM_ROUTED / (2 + vec), by_wires = NUM_WIRES / (2 + vec + bits);
+        return std::max(1, std::min(by_routed, by_wires));
+    }
+    Target random_access(Target index, const std::vector<Target>& v) {
+        int bits = 0;
+        while ((1 << bits) < (int)v.size()) bits++;
+        if ((size_t)(1 << bits) != v.size()) throw Error{"random_access: length must be a power of two"};
+        if (bits == 0) return v[0];
+        if (bits > 6 || 2 + (1 << bits) > NUM_ROUTED) throw Error{"random_access: vector too long for one gate"};
+        const int copies = ra_copies(bits), vec = 1 << bits;
+        auto& slot = free_ra[bits];
+        if (slot.second == 0 || slot.second >= copies) {
+            slot.first = add_gate(gate_type(P2G_GATE_RANDOM_ACCESS, bits, copies, 0));
+            slot.second = 0;
+        }
+        const int row = slot.first, cp = slot.second++;
+        const int base = (2 + vec) * cp;
+        connect(index, wire(row, base));
+        for (int i = 0; i < vec; i++) connect(v[i], wire(row, base + 2 + i));
+        Gen g = {};
+        g.kind = GEN_RANDOM_ACCESS;
+        g.row = row;
+        g.i = cp;
+        g.n = bits;
+        gens.push_back(g);
+        return wire(row, base + 1);
+    }
+    void register_public_input(Target t) { public_inputs.push_back(t); }
+
+    // ---- build(): public-input hash, constants, unused gate slots, padding (plonk/circuit_builder.rs build)
+    void build() {
+        if (built) return;
+        // hash_n_to_hash_no_pad::<PoseidonHash>(public_inputs): sponge of rate 8, overwrite mode, one PoseidonGate row per permutation
+        Target state[12];
+        for (auto& s : state) s = zero();
+        for (size_t off = 0; off < public_inputs.size(); off += 8) {
+            const size_t len = std::min<size_t>(8, public_inputs.size() - off);
+            for (size_t i = 0; i < len; i++) state[i] = public_inputs[off + i];
+            const int row = add_gate(gate_type(P2G_GATE_POSEIDON));
+            for (int i = 0; i < 12; i++) connect(state[i], wire(row, i));
+            connect(zero(), wire(row, 24));   // swap = 0
+            Gen g = {};
+            g.kind = GEN_POSEIDON;
+            g.row = row;
+            gens.push_back(g);
+            for (int i = 0; i < 12; i++) state[i] = wire(row, 12 + i);
+        }
+        const int pi_row = add_gate(gate_type(P2G_GATE_PUBLIC_INPUT));
+        for (int i = 0; i < 4; i++) {
+            pi_hash[i] = state[i];
+            connect(state[i], wire(pi_row, i));
+        }
+        // unused arithmetic / random-access slots compute on zeros (their output wires are simply 0 * 0 * c0 + 0 * c1 = 0)
+        // constants -> ConstantGate rows
+        for (size_t off = 0; off < constant_order.size(); off += CONSTS_PER_GATE) {
+            std::vector<u64> cs;
+            for (size_t i = off; i < std::min(constant_order.size(), off + CONSTS_PER_GATE); i++) cs.push_back(constant_order[i]);
+            while ((int)cs.size() < CONSTS_PER_GATE) cs.push_back(0);
+            const int row = add_gate(gate_type(P2G_GATE_CONSTANT, CONSTS_PER_GATE), cs);
+            for (size_t i = off; i < std::min(constant_order.size(), off + CONSTS_PER_GATE); i++) {
+                connect(constants[constant_order[i]], wire(row, (int)(i - off)));
+                Gen g = {};
+                g.kind = GEN_CONST;
+                g.row = row;
+                g.i = (int)(i - off);
+                g.c0 = constant_order[i];
+                gens.push_back(g);
+            }
+        }
+        // pad with NoopGate to a power of two (at least 2^2 rows so that the LDE has 2^cap_height leaves)
+        size_t n = 4;
+        while (n < rows.size()) n <<= 1;
+        const int noop = gate_type(P2G_GATE_NOOP);
+        while (rows.size() < n) add_gate(noop);
+        degree_bits = 0;
+        while (((size_t)1 << degree_bits) < n) degree_bits++;
+        built = true;
+    }
+
+    // ---- witness generation: plonky2 iop/generator.rs generate_partial_witness restricted to the generators above.
+    // values are kept per copy-constraint class (PartitionWitness); a class set twice with different values is an unsatisfied
+    // copy constraint -- plonky2 panics there, this returns an error.
+    std::vector<u64> val;
+    std::vector<char> has;
+    void grow() {   // generators touch wires nobody referenced before (Poseidon's internal columns): they become targets now
+        if (val.size() < parent.size()) {
+            val.resize(parent.size(), 0);
+            has.resize(parent.size(), 0);
+        }
+    }
+    void set(Target t, u64 v) {
+        grow();
+        Target r = find(t);
+        if (has[r]) {
+            if (val[r] != v) throw Error{"witness generation: a copy-constrained target was set twice with different values (unsatisfiable witness)"};
+            return;
+        }
+        has[r] = 1;
+        val[r] = v;
+    }
+    bool get(Target t, u64* v) {
+        grow();
+        Target r = find(t);
+        if (!has[r]) return false;
+        *v = val[r];
+        return true;
+    }
+    bool run(Gen& g) {
+        switch (g.kind) {
+        case GEN_CONST:
+            set(wire(g.row, g.i), g.c0);
+            return true;
+        case GEN_ARITH: {
+            u64 x, y, z;
+            if (!get(wire(g.row, 4 * g.i), &x) || !get(wire(g.row, 4 * g.i + 1), &y) || !get(wire(g.row, 4 * g.i + 2), &z)) return false;
+            set(wire(g.row, 4 * g.i + 3), gl_add(gl_mul(gl_mul(x, y), g.c0), gl_mul(z, g.c1)));
+            return true;
+        }
+        case GEN_SPLIT: {   // WireSplitGenerator: integer -> the sum wire of each BaseSum row, 63 bits at a time
+            u64 x;
+            if (!get(g.t, &x)) return false;
+            for (size_t k = 0; k < g.rows.size(); k++) {
+                u64 chunk = (k * g.n >= 64) ? 0 : (x >> (k * g.n)) & (g.n >= 64 ? ~0ULL : (((u64)1 << g.n) - 1));
+                set(wire(g.rows[k], 0), chunk);
+            }
+            return true;
+        }
+        case GEN_BASE_SPLIT: {   // BaseSplitGenerator: sum -> limbs
+            u64 s;
+            if (!get(wire(g.row, 0), &s)) return false;
+            for (int l = 0; l < g.n; l++) set(wire(g.row, 1 + l), l < 64 ? (s >> l) & 1 : 0);
+            return true;
+        }
+        case GEN_BASE_SUM: {   // BaseSumGenerator: limbs -> sum
+            u64 s = 0, pw = 1;
+            for (int l = 0; l < g.n; l++) {
+                u64 b;
+                if (!get(wire(g.row, 1 + l), &b)) return false;
+                s = gl_add(s, gl_mul(b, pw));
+                pw = gl_add(pw, pw);
+            }
+            set(wire(g.row, 0), s);
+            return true;
+        }
+        case GEN_RANDOM_ACCESS: {
+            const GateType& gt = gate_types[rows[g.row].gate];
+            const int bits = gt.params[0], copies = gt.params[1], vec = 1 << bits, base = (2 + vec) * g.i;
+            u64 idx;
+            if (!get(wire(g.row, base), &idx)) return false;
+            if (idx >= (u64)vec) throw Error{"random_access: index out of range"};
+            u64 item;
+            if (!get(wire(g.row, base + 2 + (int)idx), &item)) return false;
+            set(wire(g.row, base + 1), item);
+            const int routed_used = (2 + vec) * copies + (int)gt.params[2];
+            for (int b = 0; b < bits; b++) set(wire(g.row, routed_used + g.i * bits + b), (idx >> b) & 1);
+            return true;
+        }
+        case GEN_POSEIDON: {
+            u64 st[12];
+            for (int i = 0; i < 12; i++)
+                if (!get(wire(g.row, i), &st[i])) return false;
+            u64 swap;
+            if (!get(wire(g.row, 24), &swap)) return false;
+            for (int i = 0; i < 4; i++) {
+                u64 delta = gl_mul(swap, gl_sub(st[i + 4], st[i]));
+                set(wire(g.row, 25 + i), delta);
+                st[i] = gl_add(st[i], delta);
+                st[i + 4] = gl_sub(st[i + 4], delta);
+            }
+            int rnd = 0;
+            for (int r = 0; r < 4; r++, rnd++) {
+                for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC(12 * rnd + i));
+                if (r != 0)
+                    for (int i = 0; i < 12; i++) set(wire(g.row, 29 + 12 * (r - 1) + i), st[i]);
+                for (int i = 0; i < 12; i++) st[i] = poseidon_sbox(st[i]);
+                poseidon_mds(st);
+            }
+            for (int r = 0; r < 22; r++, rnd++) {
+                for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC(12 * rnd + i));
+                set(wire(g.row, 65 + r), st[0]);
+                st[0] = poseidon_sbox(st[0]);
+                poseidon_mds(st);
+            }
+            for (int r = 0; r < 4; r++, rnd++) {
+                for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC(12 * rnd + i));
+                for (int i = 0; i < 12; i++) set(wire(g.row, 87 + 12 * r + i), st[i]);
+                for (int i = 0; i < 12; i++) st[i] = poseidon_sbox(st[i]);
+                poseidon_mds(st);
+            }
+            for (int i = 0; i < 12; i++) set(wire(g.row, 12 + i), gl_canon(st[i]));
+            return true;
+        }
+        }
+        return false;
+    }
+};
+
+// ---- the translator (circuit_translation/mod.rs) -----------------------------------------------------------------------------
+struct Translator {
+    Builder b;
+    std::map<u32, Target> witness_target_map;
+    std::map<u32, std::pair<std::vector<Target>, size_t>> memory_blocks;
+    Target target_for_witness(u32 w) {
+        auto it = witness_target_map.find(w);
+        if (it != witness_target_map.end()) return it->second;
+        Target t = b.add_virtual_target();
+        witness_target_map[w] = t;
+        return t;
+    }
+    std::vector<Target> binary_number_target_for_witness(u32 w, int digits) {   // most significant bit first (mod.rs:262-274)
+        std::vector<Target> bits = b.split_le(target_for_witness(w), digits);
+        std::reverse(bits.begin(), bits.end());
+        return bits;
+    }
+    Target convert_binary_number_to_number(std::vector<Target> bits) {
+        std::reverse(bits.begin(), bits.end());
+        return b.le_sum(bits);
+    }
+};
+
+// flat opcode stream (what acir.py writes): u64 words
+//   1 AssertZero: n_mul, n_lin, q_c, then n_mul x (coef, w1, w2), n_lin x (coef, w)          assert_zero_translator.rs:30-116
+//   2 RANGE: witness, num_bits                                                                  mod.rs:131-137
+//   3 AND / 4 XOR: lhs, rhs, num_bits, output                                                   mod.rs:139-155, 213-232
+//   5 MemoryInit: block_id, n, then n witnesses                                                 memory_translator.rs:145-156
+//   6 MemoryRead: block_id, index witness, value witness                                        memory_translator.rs:125-137
+enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6 };
+
+void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size_t npriv, const u64* ops, size_t nwords) {
+    Builder& b = T.b;
+    for (size_t i = 0; i < npub; i++) {   // _register_witnesses_from_acir_circuit (mod.rs:289-316)
+        Target t = b.add_virtual_target();
+        b.register_public_input(t);
+        T.witness_target_map[(u32)pub[i]] = t;
+    }
+    for (size_t i = 0; i < npriv; i++) T.target_for_witness((u32)priv[i]);
+    size_t p = 0;
+    auto next = [&]() {
+        if (p >= nwords) throw Error{"opcode stream truncated"};
+        return ops[p++];
+    };
+    while (p < nwords) {
+        const u64 op = next();
+        switch (op) {
+        case OP_ASSERT_ZERO: {
+            const u64 n_mul = next(), n_lin = next(), q_c = next();
+            if (q_c >= GL_P) throw Error{"AssertZero: non-canonical constant"};
+            std::vector<std::tuple<u64, u32, u32>> muls;
+            std::vector<std::pair<u64, u32>> lins;
+            for (u64 i = 0; i < n_mul; i++) {
+                u64 c = next(), w1 = next(), w2 = next();
+                muls.emplace_back(c, (u32)w1, (u32)w2);
+            }
+            for (u64 i = 0; i < n_lin; i++) {
+                u64 c = next(), w = next();
+                lins.emplace_back(c, (u32)w);
+            }
+            for (auto& m : muls) {   // _register_intermediate_witnesses_for_assert_zero
+                T.target_for_witness(std::get<1>(m));
+                T.target_for_witness(std::get<2>(m));
+            }
+            for (auto& l : lins) T.target_for_witness(l.second);
+            Target acc = b.constant(q_c);
+            for (auto& l : lins) acc = b.add(b.mul_const(l.first, T.target_for_witness(l.second)), acc);
+            for (auto& m : muls) {
+                Target q = b.mul(T.target_for_witness(std::get<1>(m)), T.target_for_witness(std::get<2>(m)));
+                acc = b.add(b.mul_const(std::get<0>(m), q), acc);
+            }
+            b.assert_zero(acc);
+            break;
+        }
+        case OP_RANGE: {
+            const u64 w = next(), bits = next();
+            if (bits > 33) throw Error{"Range checks with more than 33 bits are not allowed yet while using Plonky2 prover"};
+            b.range_check(T.target_for_witness((u32)w), (int)bits);
+            break;
+        }
+        case OP_AND:
+        case OP_XOR: {
+            const u64 lhs = next(), rhs = next(), bits = next(), out = next();
+            std::vector<Target> l = T.binary_number_target_for_witness((u32)lhs, (int)bits);
+            std::vector<Target> r = T.binary_number_target_for_witness((u32)rhs, (int)bits);
+            std::vector<Target> o(l.size());
+            for (size_t i = 0; i < l.size(); i++) o[i] = op == OP_AND ? b.b_and(l[i], r[i]) : b.b_xor(l[i], r[i]);
+            T.witness_target_map[(u32)out] = T.convert_binary_number_to_number(o);
+            break;
+        }
+        case OP_MEM_INIT: {
+            const u64 id = next(), n = next();
+            std::vector<Target> v;
+            for (u64 i = 0; i < n; i++) v.push_back(T.target_for_witness((u32)next()));
+            size_t real = v.size(), len = 1;
+            while (len < real) len <<= 1;
+            while (v.size() < len) v.push_back(b.zero());
+            T.memory_blocks[(u32)id] = {v, real};
+            break;
+        }
+        case OP_MEM_READ: {
+            const u64 id = next(), iw = next(), vw = next();
+            auto it = T.memory_blocks.find((u32)id);
+            if (it == T.memory_blocks.end()) throw Error{"MemoryOp on an uninitialised block"};
+            Target res = b.random_access(T.target_for_witness((u32)iw), it->second.first);
+            T.witness_target_map[(u32)vw] = res;
+            break;
+        }
+        default: throw Error{"Opcode not supported yet: " + std::to_string(op)};
+        }
+    }
+    b.build();
+}
+
+thread_local std::string g_err;
+
+}  // namespace
+
+extern "C" {
+
+const char* p2a_last_error(void) { return g_err.c_str(); }
+
+// translate an ACIR circuit; returns a handle or NULL
+void* p2a_translate(const u64* pub, size_t npub, const u64* priv, size_t npriv, const u64* ops, size_t nwords) {
+    Translator* T = new Translator();
+    try {
+        translate(*T, pub, npub, priv, npriv, ops, nwords);
+        return T;
+    } catch (const Error& e) {
+        g_err = e.msg;
+        delete T;
+        return nullptr;
+    }
+}
+void p2a_destroy(void* h) { delete (Translator*)h; }
+
+// degree_bits, number of distinct gate types, number of public inputs, rows used before padding
+void p2a_shape(void* h, u32* degree_bits, u32* ngates, u32* npub) {
+    Translator* T = (Translator*)h;
+    *degree_bits = T->b.degree_bits;
+    *ngates = (u32)T->b.gate_types.size();
+    *npub = (u32)T->b.public_inputs.size();
+}
+// distinct gate types in creation order: kind + params[4] each
+void p2a_gate_types(void* h, u32* out) {
+    Translator* T = (Translator*)h;
+    for (size_t i = 0; i < T->b.gate_types.size(); i++) {
+        out[5 * i] = T->b.gate_types[i].kind;
+        for (int k = 0; k < 4; k++) out[5 * i + 1 + k] = T->b.gate_types[i].params[k];
+    }
+}
+
+// The preprocessed polynomials for the SORTED gate table `gates` (common.gates order with selector data, from the host-side
+// CommonCircuitData): constants_sigmas [num_constants + 80][N] values; `type_to_gate[i]` = position of creation-order type i in it.
+int p2a_constants_sigmas(void* h, const p2g_gate* gates, u32 ngates, const u32* type_to_gate, u32 num_selectors, u32 num_constants,
+                         const u64* k_is, u64* out) {
+    Translator* T = (Translator*)h;
+    Builder& b = T->b;
+    try {
+        const size_t n = (size_t)1 << b.degree_bits;
+        const u64 UNUSED = 0xFFFFFFFFULL;
+        // selectors + gate constants
+        for (size_t r = 0; r < n; r++) {
+            const u32 g = type_to_gate[b.rows[r].gate];
+            if (g >= ngates) throw Error{"bad gate mapping"};
+            for (u32 s = 0; s < num_selectors; s++) out[(size_t)s * n + r] = (s == gates[g].selector_index) ? g : UNUSED;
+            for (u32 c = num_selectors; c < num_constants; c++) {
+                const size_t k = c - num_selectors;
+                out[(size_t)c * n + r] = k < b.rows[r].consts.size() ? b.rows[r].consts[k] : 0;
+            }
+        }
+        // sigmas: plonky2 plonk/permutation_argument.rs WirePartition::get_sigma_polys -- the routed wires of a copy class, in
+        // row-major order, form one cycle; sigma(row, col) = k_is[col'] * omega^row' of the next wire of the cycle
+        const u64 w = gl_root_of_unity(b.degree_bits);
+        std::vector<u64> subgroup(n);
+        u64 x = 1;
+        for (size_t r = 0; r < n; r++) {
+            subgroup[r] = x;
+            x = gl_mul(x, w);
+        }
+        std::unordered_map<Target, std::vector<u32>> classes;   // representative -> wires (row * 80 + col) in row-major order
+        for (size_t r = 0; r < n; r++)
+            for (int c = 0; c < NUM_ROUTED; c++) {
+                auto it = b.wire_target.find({(int)r, c});
+                if (it == b.wire_target.end()) continue;   // never connected: fixed point
+                classes[b.find(it->second)].push_back((u32)(r * NUM_ROUTED + c));
+            }
+        u64* sig = out + (size_t)num_constants * n;
+        for (size_t r = 0; r < n; r++)
+            for (int c = 0; c < NUM_ROUTED; c++) sig[(size_t)c * n + r] = gl_mul(k_is[c], subgroup[r]);
+        for (auto& kv : classes) {
+            const std::vector<u32>& ws = kv.second;
+            for (size_t i = 0; i < ws.size(); i++) {
+                const u32 from = ws[i], to = ws[(i + 1) % ws.size()];
+                sig[(size_t)(from % NUM_ROUTED) * n + from / NUM_ROUTED] = gl_mul(k_is[to % NUM_ROUTED], subgroup[to / NUM_ROUTED]);
+            }
+        }
+        return 0;
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return -1;
+    }
+}
+
+// Witness generation: ACIR witness map (ids + canonical values) -> wires [234][N] (unset wires are zero, as
+// in plonky2's full_witness) and the public inputs in registration order.  Returns 0, or -1 (message in p2a_last_error) when a
+// copy constraint is contradicted -- where the reference panics inside witness generation, before the prover.
+int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wires, u64* public_inputs) {
+    Translator* T = (Translator*)h;
+    Builder& b = T->b;
+    try {
+        const size_t n = (size_t)1 << b.degree_bits;
+        b.val.assign(b.parent.size(), 0);
+        b.has.assign(b.parent.size(), 0);
+        for (auto& g : b.gens) g.done = false;
+        for (size_t i = 0; i < nw; i++) {
+            if (values[i] >= GL_P) throw Error{"witness value is not canonical"};
+            auto it = T->witness_target_map.find((u32)ids[i]);
+            if (it == T->witness_target_map.end()) continue;   // a witness the circuit never mentions (Brillig intermediates)
+            b.set(it->second, values[i]);
+        }
+        // run the generators to a fixed point (plonky2 keeps watch lists; a handful of sweeps suffice for forward-built circuits)
+        for (int sweep = 0; sweep < 64; sweep++) {
+            bool progress = false, pending = false;
+            for (auto& g : b.gens) {
+                if (g.done) continue;
+                if (b.run(g)) {
+                    g.done = true;
+                    progress = true;
+                } else {
+                    pending = true;
+                }
+            }
+            if (!pending || !progress) break;
+        }
+        memset(wires, 0, (size_t)NUM_WIRES * n * 8);
+        for (auto& kv : b.wire_target) {
+            u64 v;
+            if (b.get(kv.second, &v)) wires[(size_t)kv.first.second * n + kv.first.first] = v;
+        }
+        for (size_t i = 0; i < b.public_inputs.size(); i++) {
+            u64 v;
+            if (!b.get(b.public_inputs[i], &v)) throw Error{"public input has no value"};
+            public_inputs[i] = v;
+        }
+        return 0;
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return -1;
+    }
+}
+
+}  // extern "C"

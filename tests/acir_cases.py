@@ -1,0 +1,52 @@
+"""ACIR circuits of the reference's translator tests, built by hand like circuit_translation/tests/factories/circuit_factory.rs
+(no nargo): (name, circuit, witness assignment, expected public inputs)."""
+P = 0xFFFFFFFF00000001
+
+
+def cases(acir):
+    E, AZ, C = acir.Expression, acir.AssertZero, acir.Circuit
+    out = []
+    # test_assert_zero.rs:6-273
+    out.append(("x_equals_0", C([AZ(E([], [(1, 0)], 0))], [0]), {0: 0}, [0]))
+    out.append(("x_equals_4", C([AZ(E([], [(1, 0)], -4))], [0]), {0: 4}, [4]))
+    out.append(("x_times_3_equals_12", C([AZ(E([], [(3, 0)], -12))], [0]), {0: 4}, [4]))
+    out.append(("3x_plus_9y_equals_12", C([AZ(E([], [(3, 0), (9, 1)], -12))], [0, 1]), {0: 1, 1: 1}, [1, 1]))
+    out.append(("multiple_linear_combinations", C([AZ(E([], [(3, w) for w in reversed(range(4))], -12))], [0, 1, 2, 3]),
+                {0: 1, 1: 1, 2: 1, 3: 1}, [1, 1, 1, 1]))
+    out.append(("two_x_x_equals_32", C([AZ(E([(2, 0, 0)], [], -32))], [0]), {0: 4}, [4]))
+    out.append(("two_x_y_equals_40", C([AZ(E([(2, 0, 1)], [], -40))], [0, 1]), {0: 5, 1: 4}, [5, 4]))
+    out.append(("multiple_cuadratic_terms", C([AZ(E([(2, 0, 0), (3, 0, 1), (4, 1, 1)], [], -(2 * 4 + 3 * 6 + 4 * 9)))], [0, 1]),
+                {0: 2, 1: 3}, [2, 3]))
+    out.append(("cuadratic_and_linear", C([AZ(E([(2, 0, 0), (3, 0, 1)], [(5, 0), (7, 1)], -(8 + 18 + 10 + 21)))], [0, 1]),
+                {0: 2, 1: 3}, [2, 3]))
+    out.append(("two_assert_zero_opcodes", C([AZ(E([], [(1, 0)], -4)), AZ(E([], [(3, 1)], -12))], [0, 1]), {0: 4, 1: 4}, [4, 4]))
+    # private inputs, an intermediate witness shared by two opcodes (w2 = x * y ; w2 + x = 26)
+    out.append(("private_and_intermediate", C([AZ(E([(1, 0, 1)], [(P - 1, 2)], 0)), AZ(E([], [(1, 2), (1, 0)], -25))], [0], [1]),
+                {0: 5, 1: 4, 2: 20}, [5]))
+    # test_blackbox.rs:8-82 (RANGE), :112-218 (AND / XOR; the output witness is computed by the generators, not provided)
+    for bits, v in ((8, 255), (16, 65535), (32, (1 << 32) - 1), (33, (1 << 33) - 1)):
+        out.append((f"range_u{bits}", C([acir.Range(0, bits)], [0]), {0: v}, [v]))
+    for bits, a, b in ((8, 0b10101010, 0b11001100), (16, 0xBEEF, 0x0FF0), (32, 0xDEADBEEF, 0x12345678)):
+        out.append((f"and_{bits}", C([acir.And(0, 1, bits, 2)], [0, 1]), {0: a, 1: b}, [a, b]))
+        out.append((f"xor_{bits}", C([acir.Xor(0, 1, bits, 2)], [0, 1]), {0: a, 1: b}, [a, b]))
+    # AND output fed to an AssertZero: out - expected = 0
+    out.append(("and_output_is_constrained", C([acir.And(0, 1, 8, 2), AZ(E([], [(1, 2)], -(0b10101010 & 0b11001100)))], [0, 1]),
+                {0: 0b10101010, 1: 0b11001100}, [0b10101010, 0b11001100]))
+    # test_memory_operations.rs:10-37 (read), :82-121 (irregular block size)
+    out.append(("memory_read", C([acir.MemoryInit(0, [0, 1, 2, 3]), acir.MemoryRead(0, 4, 5)], [0, 1, 2, 3, 4]),
+                {0: 10, 1: 11, 2: 12, 3: 13, 4: 2}, [10, 11, 12, 13, 2]))
+    out.append(("memory_read_irregular_block", C([acir.MemoryInit(0, [0, 1, 2]), acir.MemoryRead(0, 3, 4),
+                                                  AZ(E([], [(1, 4)], -21))], [0, 1, 2, 3]),
+                {0: 20, 1: 21, 2: 22, 3: 1}, [20, 21, 22, 1]))
+    return out
+
+
+def chain(acir, n_ops, seed=1):
+    """A longer AssertZero chain (BASELINE configs[1] shape from real opcodes): w_{i+1} = w_i * w_i + 3 w_i + i."""
+    ops, wit, x = [], {0: seed}, seed
+    for i in range(n_ops):
+        y = (x * x + 3 * x + i) % P
+        ops.append(acir.AssertZero(acir.Expression([(1, i, i)], [(3, i), (P - 1, i + 1)], i)))
+        wit[i + 1] = y
+        x = y
+    return acir.Circuit(ops, [0]), wit

@@ -1,0 +1,109 @@
+"""CPU: the ACIR translator + mini CircuitBuilder + witness generators on the reference's own
+translator tests (circuit_translation/tests/test_assert_zero.rs, test_blackbox.rs, test_memory_operations.rs): the generated
+trace satisfies every gate constraint and every copy constraint, the ORACLE prover proves it and the ORACLE verifier accepts --
+the reference's `assert!(circuit_data.verify(proof).is_ok())` (tests/factories/utils.rs:16-27) -- and bad witnesses are refused
+where the reference panics."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import acir_cases  # noqa: E402
+
+P = 0xFFFFFFFF00000001
+
+
+def _check_trace(p2g, corc, tr, wires, pis):
+    from helpers import oracle_cd
+    from oracle.pyref.hashing import PoseidonHash
+    com = tr.common
+    cd = oracle_cd(com)
+    n = com.degree()
+    # 1. gate constraints vanish on every row (gate_testing.rs property, through the oracle's evaluators)
+    pi_hash = PoseidonHash.hash_no_pad_elems(pis) if pis else [0, 0, 0, 0]
+    out = corc.eval_gate_constraints(cd, tr.constants_sigmas[:com.num_constants], wires, pi_hash)
+    assert not out.any(), f"gate constraint {np.argwhere(out)[0]} does not vanish"
+    # 2. copy constraints: the value on a routed wire equals the value on the wire sigma sends it to
+    w = pow(7277203076849721926, 1 << (32 - com.degree_bits()), P)
+    sub = {}
+    x = 1
+    for r in range(n):
+        sub[x] = r
+        x = x * w % P
+    kinv = {k: i for i, k in enumerate(com.k_is)}
+    sig = tr.constants_sigmas[com.num_constants:]
+    moved = 0
+    for c in range(80):
+        for r in range(n):
+            s = int(sig[c, r])
+            # s = k_is[c'] * omega^r'
+            for kc, ci in kinv.items():
+                t = s * pow(kc, P - 2, P) % P
+                if t in sub:
+                    assert wires[c, r] == wires[ci, sub[t]], (c, r, ci, sub[t])
+                    moved += (ci, sub[t]) != (c, r)
+                    break
+            else:
+                raise AssertionError("sigma value is not a routed wire position")
+    return cd, moved
+
+
+NUM_CASES = 24
+
+
+@pytest.mark.parametrize("case", range(NUM_CASES))
+def test_reference_translator_cases(p2g, corc, case):
+    all_cases = acir_cases.cases(p2g.acir)
+    assert len(all_cases) == NUM_CASES
+    name, circuit, witness, want_pis = all_cases[case]
+    tr = p2g.acir.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    wires, pis = tr.generate_witness(witness)
+    if want_pis is not None:
+        assert pis == want_pis, name
+    cd, moved = _check_trace(p2g, corc, tr, wires, pis)
+    assert moved > 0, "the circuit has copy constraints"
+    # the oracle proves and verifies (the reference test's acceptance criterion)
+    from oracle.pyref import proof, verifier
+    op = corc.OracleProver(cd, tr.constants_sigmas)
+    pb = op.prove(wires, pis)
+    cap, dg = op.cap_and_digest()
+    pr = proof.parse_uncompressed(pb, cd)
+    verifier.verify(pr, cd, cap, dg)
+    assert [int(x) for x in pr.public_inputs] == pis
+
+
+def test_bad_witnesses_are_refused_like_the_reference_panics(p2g):
+    A = p2g.acir
+    tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(A.Circuit([A.AssertZero(A.Expression([], [(1, 0)], -4))], [0]))
+    with pytest.raises(A.TranslationError):        # x = 5 where x - 4 = 0 is asserted
+        tr.generate_witness({0: 5})
+    for bits in (8, 16, 32):                       # test_blackbox.rs:17-25, 36-44, 55-63
+        tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(A.Circuit([A.Range(0, bits)], [0]))
+        with pytest.raises(A.TranslationError):
+            tr.generate_witness({0: 1 << bits})
+    with pytest.raises(A.TranslationError, match="33 bits"):     # test_blackbox.rs:75-82
+        A.CircuitBuilderFromAcirToPlonky2().translate_circuit(A.Circuit([A.Range(0, 64)], [0]))
+    # a provided output that disagrees with the computed one
+    tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(A.Circuit([A.And(0, 1, 8, 2)], [0, 1]))
+    tr.generate_witness({0: 3, 1: 5, 2: 1})
+    with pytest.raises(A.TranslationError):
+        tr.generate_witness({0: 3, 1: 5, 2: 7})
+    with pytest.raises(A.TranslationError):        # memory read past the block
+        tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(A.Circuit([A.MemoryInit(0, [0, 1]), A.MemoryRead(0, 2, 3)], [0, 1, 2]))
+        tr.generate_witness({0: 1, 1: 2, 2: 5})
+
+
+def test_assert_zero_chain_packs_rows_like_the_builder(p2g, corc):
+    """A 300-opcode AssertZero chain: ArithmeticGate rows hold 20 operations with equal constants, constants live in
+    ConstantGate rows, one PublicInputGate + one PoseidonGate row hash the public input; the trace is valid."""
+    circuit, wit = acir_cases.chain(p2g.acir, 300)
+    tr = p2g.acir.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    kinds = sorted(g.kind for g in tr.common.gates)
+    C = p2g.circuit
+    assert kinds == sorted([C.NOOP, C.CONSTANT, C.PUBLIC_INPUT, C.ARITHMETIC, C.POSEIDON])
+    assert tr.common.degree_bits() == 9          # 7 builder operations per opcode at 20 per row + 300 distinct constants at 2 per row
+    wires, pis = tr.generate_witness(wit)
+    assert pis == [1]
+    _check_trace(p2g, corc, tr, wires, pis)

@@ -1,0 +1,44 @@
+"""GPU: circuits translated from ACIR opcodes (not synthetic gate mixes) through the whole product path: translate -> witness ->
+p2g_prove, compared byte for byte with the oracle prover on the same payload and accepted by the oracle verifier -- the
+reference's translator tests (circuit_translation/tests/*.rs, `assert!(circuit_data.verify(proof).is_ok())`) on the CUDA prover."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import acir_cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", [0, 4, 8, 10, 14, 16, 19, 21, 23])
+def test_translated_circuits_prove_on_the_gpu(p2g, corc, case):
+    from helpers import oracle_cd
+    from oracle.pyref import proof, verifier
+    name, circuit, witness, want_pis = acir_cases.cases(p2g.acir)[case]
+    tr = p2g.acir.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    wires, pis = tr.generate_witness(witness)
+    cd = oracle_cd(tr.common)
+    data, _ = tr.unpack()
+    with data:
+        pw = data.prove(wires, pis)
+        pr = proof.parse_uncompressed(pw.to_bytes(), cd)
+        verifier.verify(pr, cd, data.constants_sigmas_cap, data.circuit_digest)
+        assert [int(x) for x in pr.public_inputs] == pis
+        op = corc.OracleProver(cd, tr.constants_sigmas)
+        assert pw.to_bytes() == op.prove(wires, pis), name
+
+
+def test_assert_zero_chain_from_real_opcodes(p2g, corc):
+    """BASELINE configs[1] shape from real AssertZero opcodes (2^14 rows): translated, witnessed, proved, byte-compared."""
+    from helpers import oracle_cd
+    circuit, wit = acir_cases.chain(p2g.acir, 20000)
+    tr = p2g.acir.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    assert tr.common.degree_bits() >= 14
+    wires, pis = tr.generate_witness(wit)
+    cd = oracle_cd(tr.common)
+    data, _ = tr.unpack()
+    with data:
+        got = data.prove(wires, pis).to_bytes()
+    assert got == corc.OracleProver(cd, tr.constants_sigmas).prove(wires, pis)
