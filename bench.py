@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--inflight", type=int, default=2,
                     help="proofs in flight per GPU (one circuit handle + stream + host thread each); a step is still one proof")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-columns e2e measurement")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-proof-across-N-GPUs measurement")
     ap.add_argument("--sharded-callback", action="store_true",
                     help="N > 1: exchange through the host callback bound to torch.distributed instead of the library's own NCCL communicator")
@@ -288,18 +289,22 @@ def main():
             ms = float(t.item())
         return ms, outs
 
-    def prove_steps(w):
-        """steps -> list of proofs: `steps` proofs in total, spread over the F handles, each driven by its own host thread."""
+    def prove_steps(w, columns=False):
+        """steps -> list of proofs: `steps` proofs in total, spread over the F handles, each driven by its own host thread.
+        columns: w is a list of separately allocated pageable wire columns (p2g_prove_columns)."""
+        def one(h):
+            return h.prove_columns(w, sc.public_inputs) if columns else h.prove(w, sc.public_inputs)
+
         def run(steps):
             if F == 1:
-                return [data.prove(w, sc.public_inputs) for _ in range(steps)]
+                return [one(data) for _ in range(steps)]
             outs, errs = [[] for _ in range(F)], []
 
             def work(i):
                 try:
                     torch.cuda.set_device(local_rank)
                     for _ in range(steps // F + (1 if i < steps % F else 0)):
-                        outs[i].append(handles[i].prove(w, sc.public_inputs))
+                        outs[i].append(one(handles[i]))
                 except BaseException as e:  # noqa: BLE001
                     errs.append(e)
             ts = [threading.Thread(target=work, args=(i,)) for i in range(F)]
@@ -319,6 +324,16 @@ def main():
     ms_dev, outs = timed(prove_steps(wires_dev), args.steps)
     prove_steps(wires_host)(min(args.warmup, 2) * F)
     ms_e2e, outs_e2e = timed(prove_steps(wires_host), args.steps)
+    # the same call from ordinary (pageable) memory laid out as plonky2 holds the witness -- one heap allocation per wire column
+    # (MatrixWitness.wire_values), handed over as column pointers: what the Rust shim does, with no flat copy and no pinning
+    ms_pageable = None
+    if world == 1 and not args.no_pageable:
+        cols = [sc.wires[i].copy() for i in range(sc.wires.shape[0])]
+        prove_steps(cols, True)(F)
+        ms_pageable, outs_pg = timed(prove_steps(cols, True), max(2, args.steps // 2))
+        ms_pageable /= max(2, args.steps // 2)
+        assert outs_pg[0].to_bytes() == outs_e2e[0].to_bytes()
+        del cols
     # per-kernel / per-stage device timings (CUDA events on the library's stream): with several proofs in flight the stage
     # events of one proof span kernels of the others, so they are taken from two proofs run alone right after the timed region
     solo = [data.prove(wires_dev, sc.public_inputs) for _ in range(2)] if F > 1 else outs
@@ -383,7 +398,10 @@ def main():
             "execution": {"parallelism": f"{world} GPU(s) x {F} proofs in flight per GPU (independent witnesses per GPU)",
                           "inflight_per_gpu": F, "proof_bytes": proof_bytes},
             "e2e": {"value": world * K / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": proof_bytes},
+                    "d2h_bytes_per_step": proof_bytes, "host_memory": "pinned (p2g_host_alloc), one [wires][rows] block",
+                    "pageable_columns_ms_per_step": ms_pageable,
+                    "pageable_columns_note": "p2g_prove_columns from ordinary memory, one allocation per wire column (MatrixWitness.wire_values "
+                                             "as the Rust shim passes it), staged through the library's pinned ring; measured at N = 1"},
             "gpu_launches": int(launches),
             # dominant stage of the step and the north-star's headline: the coset-LDE passes (NTT stage).  achieved = algorithmic
             # bytes (8N read + 64N written per column) / device time of those launches (CUDA events on the
