@@ -182,6 +182,15 @@ struct Builder {
     Target b_xor(Target a, Target b) {   // binary_digits_target.rs:169-175: (a or b) and not (a and b)
         return b_and(b_or(a, b), b_not(b_and(a, b)));
     }
+    Target mul_sub(Target x, Target y, Target z) { return arithmetic(1, GL_P - 1, x, y, z); }
+    Target select(Target b, Target x, Target y) {   // gadgets/select.rs: b x - (b y - y)
+        return mul_sub(b, x, mul_sub(b, y, y));
+    }
+    Target add_virtual_bool_target_safe() {   // a fresh target constrained to {0, 1}: b b - b = 0
+        Target t = add_virtual_target();
+        connect(mul_sub(t, t, t), zero());
+        return t;
+    }
 
     // ---- split_le (gadgets/split_base.rs / split_join.rs): BaseSumGate<2> rows of 63 limbs, unused limbs tied to zero
     std::vector<Target> split_le(Target x, int nbits) {
@@ -450,13 +459,133 @@ struct Translator {
     }
 };
 
+// ---- BinaryDigitsTarget (plonky2-backend/src/binary_digits_target.rs): bit vectors, most significant bit first ---------------
+typedef std::vector<Target> Bits;
+Bits rotate_right(Builder& b, const Bits& t, size_t times) {   // :21-41
+    Bits out;
+    const size_t n = t.size();
+    for (size_t i = n - times; i < n; i++) {
+        Target nb = b.add_virtual_bool_target_safe();
+        b.connect(t[i], nb);
+        out.push_back(nb);
+    }
+    for (size_t i = 0; i < n - times; i++) {
+        Target nb = b.add_virtual_bool_target_safe();
+        b.connect(t[i], nb);
+        out.push_back(nb);
+    }
+    return out;
+}
+Bits shift_right(Builder& b, const Bits& t, size_t times) {   // :43-63
+    Bits out;
+    for (size_t i = 0; i < times; i++) out.push_back(b.constant(0));
+    for (size_t i = 0; i < t.size() - times; i++) {
+        Target nb = b.add_virtual_bool_target_safe();
+        b.connect(t[i], nb);
+        out.push_back(nb);
+    }
+    return out;
+}
+Bits bits_xor(Builder& b, const Bits& x, const Bits& y) {
+    Bits o(x.size());
+    for (size_t i = 0; i < x.size(); i++) o[i] = b.b_xor(x[i], y[i]);
+    return o;
+}
+Bits choose(Builder& b, const Bits& c, const Bits& t, const Bits& f) {   // :65-82
+    Bits o(c.size());
+    for (size_t i = 0; i < c.size(); i++) o[i] = b.select(c[i], t[i], f[i]);
+    return o;
+}
+Bits majority(Builder& b, const Bits& x, const Bits& y, const Bits& z) {   // :84-106: select(z, x or y, x and y)
+    Bits o(x.size());
+    for (size_t i = 0; i < x.size(); i++) o[i] = b.select(z[i], b.b_or(x[i], y[i]), b.b_and(x[i], y[i]));
+    return o;
+}
+Bits add_module_32_bits(Builder& b, const Bits& x, const Bits& y) {   // :188-221: ripple-carry adder, carry out dropped
+    const size_t n = x.size();
+    Bits ps(n), pc(n), sum;
+    for (size_t i = 0; i < n; i++) ps[i] = b.b_xor(x[i], y[i]);
+    for (size_t i = 0; i < n; i++) pc[i] = b.b_and(x[i], y[i]);
+    Target carry = b.constant(0);
+    for (size_t k = n; k-- > 0;) {
+        Target s = b.b_xor(ps[k], carry);
+        Target pair = b.b_and(carry, ps[k]);
+        carry = b.b_or(pc[k], pair);
+        sum.push_back(s);
+    }
+    std::reverse(sum.begin(), sum.end());
+    return sum;
+}
+Bits bits_for_constant(Builder& b, u32 c, int digits) {   // mod.rs:243-253
+    Bits o;
+    for (int pos = digits - 1; pos >= 0; pos--) o.push_back(b.constant((c >> pos) & 1));
+    return o;
+}
+
+// Sha256Compression (circuit_translation/sha256_translator.rs:60-273): 16 message words, 8 state words -> 8 state words
+void sha256_compression(Translator& T, const u32* in_w, const u32* hv_w, const u32* out_w) {
+    static const u32 K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+        0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+        0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+        0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+        0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+        0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+        0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    Builder& b = T.b;
+    auto x3 = [&](const Bits& t, int r1, int r2, int r3, bool shift3) {   // sigma / big sigma: rot ^ rot ^ (rot | shift)
+        Bits a = rotate_right(b, t, r1), c = rotate_right(b, t, r2), d = shift3 ? shift_right(b, t, r3) : rotate_right(b, t, r3);
+        return bits_xor(b, bits_xor(b, a, c), d);
+    };
+    std::vector<Bits> w;
+    for (int i = 0; i < 16; i++) w.push_back(T.binary_number_target_for_witness(in_w[i], 32));
+    for (int t = 16; t < 64; t++) {   // calculate_w_t
+        Bits s1 = x3(w[t - 2], 17, 19, 10, true);
+        Bits a1 = add_module_32_bits(b, s1, w[t - 7]);
+        Bits s0 = x3(w[t - 15], 7, 18, 3, true);
+        Bits a2 = add_module_32_bits(b, s0, w[t - 16]);
+        w.push_back(add_module_32_bits(b, a1, a2));
+    }
+    std::vector<Bits> k;
+    for (int t = 0; t < 64; t++) k.push_back(bits_for_constant(b, K[t], 32));
+    std::vector<Bits> h0;
+    for (int i = 0; i < 8; i++) h0.push_back(T.binary_number_target_for_witness(hv_w[i], 32));
+    std::vector<Bits> st = h0;   // a b c d e f g h
+    for (int t = 0; t < 64; t++) {   // compression_function_iteration
+        Bits S1 = x3(st[4], 6, 11, 25, false);
+        Bits ch = choose(b, st[4], st[5], st[6]);
+        Bits s0 = add_module_32_bits(b, k[t], w[t]);
+        Bits s1 = add_module_32_bits(b, st[7], S1);
+        Bits s2 = add_module_32_bits(b, ch, s0);
+        Bits t1 = add_module_32_bits(b, s1, s2);
+        Bits S0 = x3(st[0], 2, 13, 22, false);
+        Bits mj = majority(b, st[0], st[1], st[2]);
+        Bits t2 = add_module_32_bits(b, S0, mj);
+        std::vector<Bits> nx(8);
+        nx[0] = add_module_32_bits(b, t1, t2);
+        nx[1] = st[0];
+        nx[2] = st[1];
+        nx[3] = st[2];
+        nx[4] = add_module_32_bits(b, st[3], t1);
+        nx[5] = st[4];
+        nx[6] = st[5];
+        nx[7] = st[6];
+        st = nx;
+    }
+    for (int i = 0; i < 8; i++) {
+        Bits fin = add_module_32_bits(b, h0[i], st[i]);
+        T.witness_target_map[out_w[i]] = T.convert_binary_number_to_number(fin);
+    }
+}
+
 // flat opcode stream (what acir.py writes): u64 words
 //   1 AssertZero: n_mul, n_lin, q_c, then n_mul x (coef, w1, w2), n_lin x (coef, w)          assert_zero_translator.rs:30-116
 //   2 RANGE: witness, num_bits                                                                  mod.rs:131-137
 //   3 AND / 4 XOR: lhs, rhs, num_bits, output                                                   mod.rs:139-155, 213-232
 //   5 MemoryInit: block_id, n, then n witnesses                                                 memory_translator.rs:145-156
 //   6 MemoryRead: block_id, index witness, value witness                                        memory_translator.rs:125-137
-enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6 };
+//   7 Sha256Compression: 16 input witnesses, 8 hash-value witnesses, 8 output witnesses         sha256_translator.rs:60-111
+enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6, OP_SHA256_COMPRESSION = 7 };
 
 void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size_t npriv, const u64* ops, size_t nwords) {
     Builder& b = T.b;
@@ -533,6 +662,12 @@ void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size
             if (it == T.memory_blocks.end()) throw Error{"MemoryOp on an uninitialised block"};
             Target res = b.random_access(T.target_for_witness((u32)iw), it->second.first);
             T.witness_target_map[(u32)vw] = res;
+            break;
+        }
+        case OP_SHA256_COMPRESSION: {
+            u32 ws[32];
+            for (int i = 0; i < 32; i++) ws[i] = (u32)next();
+            sha256_compression(T, ws, ws + 16, ws + 24);
             break;
         }
         default: throw Error{"Opcode not supported yet: " + std::to_string(op)};

@@ -50,3 +50,30 @@ def chain(acir, n_ops, seed=1):
         wit[i + 1] = y
         x = y
     return acir.Circuit(ops, [0]), wit
+
+
+SHA256_IV = [0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19]
+
+
+def sha256_circuit(acir, message):
+    """SHA-256 of `message` as chained Sha256Compression opcodes (one per 64-byte block of the padded message), the way the
+    reference's sha256 tests drive the translator (circuit_translation/tests/test_sha256_internal.rs:481-549).  Public parameters:
+    the message words and the IV; the final state words are the last 8 witnesses.  Returns (circuit, witness map without outputs,
+    output witness ids, expected digest words)."""
+    import hashlib
+    import struct
+    padded = message + b"\x80" + b"\0" * ((55 - len(message)) % 64) + struct.pack(">Q", 8 * len(message))
+    nblocks = len(padded) // 64
+    words = list(struct.unpack(f">{16 * nblocks}I", padded))
+    wit = {i: w for i, w in enumerate(words)}
+    iv_ids = list(range(16 * nblocks, 16 * nblocks + 8))
+    wit.update({iv_ids[i]: SHA256_IV[i] for i in range(8)})
+    nxt = iv_ids[-1] + 1
+    ops, state = [], iv_ids
+    for blk in range(nblocks):
+        outs = list(range(nxt, nxt + 8))
+        nxt += 8
+        ops.append(acir.Sha256Compression(list(range(16 * blk, 16 * blk + 16)), state, outs))
+        state = outs
+    circuit = acir.Circuit(ops, list(range(16 * nblocks + 8)))
+    return circuit, wit, state, list(struct.unpack(">8I", hashlib.sha256(message).digest()))

@@ -25,28 +25,24 @@ def _check_trace(p2g, corc, tr, wires, pis):
     pi_hash = PoseidonHash.hash_no_pad_elems(pis) if pis else [0, 0, 0, 0]
     out = corc.eval_gate_constraints(cd, tr.constants_sigmas[:com.num_constants], wires, pi_hash)
     assert not out.any(), f"gate constraint {np.argwhere(out)[0]} does not vanish"
-    # 2. copy constraints: the value on a routed wire equals the value on the wire sigma sends it to
+    # 2. copy constraints: the value on a routed wire equals the value on the wire sigma sends it to (sigma values are
+    #    k_is[col'] * omega^row'; every one of them must name a routed wire position)
     w = pow(7277203076849721926, 1 << (32 - com.degree_bits()), P)
-    sub = {}
-    x = 1
+    sub, x = [], 1
     for r in range(n):
-        sub[x] = r
+        sub.append(x)
         x = x * w % P
-    kinv = {k: i for i, k in enumerate(com.k_is)}
-    sig = tr.constants_sigmas[com.num_constants:]
-    moved = 0
-    for c in range(80):
-        for r in range(n):
-            s = int(sig[c, r])
-            # s = k_is[c'] * omega^r'
-            for kc, ci in kinv.items():
-                t = s * pow(kc, P - 2, P) % P
-                if t in sub:
-                    assert wires[c, r] == wires[ci, sub[t]], (c, r, ci, sub[t])
-                    moved += (ci, sub[t]) != (c, r)
-                    break
-            else:
-                raise AssertionError("sigma value is not a routed wire position")
+    ids = np.array([k * s % P for k in com.k_is for s in sub], dtype=np.uint64)          # position c * n + r
+    order = np.argsort(ids, kind="stable")
+    sorted_ids = ids[order]
+    sig = np.ascontiguousarray(tr.constants_sigmas[com.num_constants:]).reshape(-1)
+    at = np.searchsorted(sorted_ids, sig)
+    assert (at < len(sorted_ids)).all() and (sorted_ids[np.minimum(at, len(sorted_ids) - 1)] == sig).all(), "sigma value is not a routed wire position"
+    dest = order[at]
+    routed = np.ascontiguousarray(wires[:80]).reshape(-1)
+    assert (routed[dest] == routed).all(), "a copy constraint is violated"
+    assert len(np.unique(dest)) == len(dest), "sigma is not a permutation"
+    moved = int((dest != np.arange(len(dest))).sum())
     return cd, moved
 
 
@@ -106,4 +102,19 @@ def test_assert_zero_chain_packs_rows_like_the_builder(p2g, corc):
     assert tr.common.degree_bits() == 9          # 7 builder operations per opcode at 20 per row + 300 distinct constants at 2 per row
     wires, pis = tr.generate_witness(wit)
     assert pis == [1]
+    _check_trace(p2g, corc, tr, wires, pis)
+
+
+def test_sha256_compression_known_answer(p2g, corc):
+    """Sha256Compression translated like sha256_translator.rs:60-273 (bit decompositions, rotations as re-wired fresh bool targets,
+    xor / choose / majority / ripple-carry adders): SHA-256("abc") comes out of the witness generators (test_sha256_internal.rs:481-549
+    pins the same digest), a wrong digest contradicts a copy constraint, and the trace satisfies the circuit."""
+    A = p2g.acir
+    circuit, wit, out_ids, digest = acir_cases.sha256_circuit(A, b"abc")
+    tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    assert tr.common.degree_bits() == 15
+    wires, pis = tr.generate_witness({**wit, **{out_ids[i]: digest[i] for i in range(8)}})
+    with pytest.raises(A.TranslationError):
+        tr.generate_witness({**wit, out_ids[0]: digest[0] ^ 1})
+    assert pis[:16] == [wit[i] for i in range(16)]
     _check_trace(p2g, corc, tr, wires, pis)

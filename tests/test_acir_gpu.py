@@ -42,3 +42,24 @@ def test_assert_zero_chain_from_real_opcodes(p2g, corc):
     with data:
         got = data.prove(wires, pis).to_bytes()
     assert got == corc.OracleProver(cd, tr.constants_sigmas).prove(wires, pis)
+
+
+def test_config2_real_sha256_circuit_2_18(p2g, corc):
+    """BASELINE configs[2] from real opcodes: SHA-256 of a 448-byte message = 8 chained Sha256Compression opcodes translated like
+    sha256_translator.rs -> 2^18 rows (not the "SHA-256-shaped" synthetic mix).  The witness generators produce the digest hashlib
+    computes; the CUDA prover's bytes equal the oracle prover's on the same payload, and the oracle verifier accepts them."""
+    from helpers import oracle_cd
+    from oracle.pyref import proof, verifier
+    A = p2g.acir
+    message = bytes((7 * i + 3) & 0xFF for i in range(448))
+    circuit, wit, out_ids, digest = acir_cases.sha256_circuit(A, message)
+    assert len(circuit.opcodes) == 8
+    tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    assert tr.common.degree_bits() == 18
+    wires, pis = tr.generate_witness({**wit, **{out_ids[i]: digest[i] for i in range(8)}})
+    cd = oracle_cd(tr.common)
+    data, _ = tr.unpack()
+    with data:
+        got = data.prove(wires, pis).to_bytes()
+        verifier.verify(proof.parse_uncompressed(got, cd), cd, data.constants_sigmas_cap, data.circuit_digest)
+    assert got == corc.OracleProver(cd, tr.constants_sigmas).prove(wires, pis)
