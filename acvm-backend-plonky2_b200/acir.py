@@ -4,7 +4,7 @@ Mirror of the reference's `CircuitBuilderFromAcirToPlonky2` (plonky2-backend/src
 names -- `translate_circuit`, `unpack`, `witness_target_map` semantics -- over libp2acir.so (C++: the translator, the slice of
 plonky2's CircuitBuilder it drives, and the witness generators).  ACIR values are the ones the reference's test factories build by
 hand (circuit_translation/tests/factories/circuit_factory.rs): `Expression(mul_terms, linear_combinations, q_c)`, `AssertZero`,
-`BlackBoxFuncCall::{RANGE, AND, XOR, Sha256Compression}`, `MemoryInit`, `MemoryOp` (read).  Field elements are Goldilocks (mod.rs:43-45).
+`BlackBoxFuncCall::{RANGE, AND, XOR, Sha256Compression}`, `MemoryInit`, `MemoryOp` (read and write).  Field elements are Goldilocks (mod.rs:43-45).
 """
 import ctypes as C
 import os
@@ -97,6 +97,13 @@ class MemoryRead:     # MemoryOp { operation = 0, index, value }
 
 
 @dataclass
+class MemoryWrite:    # MemoryOp { operation = 1, index, value }
+    block_id: int
+    index: int
+    value: int
+
+
+@dataclass
 class Sha256Compression:   # BlackBoxFuncCall::Sha256Compression { inputs: [_; 16], hash_values: [_; 8], outputs: [_; 8] }
     inputs: list
     hash_values: list
@@ -130,6 +137,8 @@ def _encode(circuit):
             words += [5, op.block_id, len(op.init)] + list(op.init)
         elif isinstance(op, MemoryRead):
             words += [6, op.block_id, op.index, op.value]
+        elif isinstance(op, MemoryWrite):
+            words += [8, op.block_id, op.index, op.value]
         elif isinstance(op, Sha256Compression):
             if (len(op.inputs), len(op.hash_values), len(op.outputs)) != (16, 8, 8):
                 raise TranslationError("Sha256Compression takes 16 inputs, 8 hash values and 8 outputs")

@@ -47,12 +47,13 @@ struct Row {
     std::vector<u64> consts;  // gate-local constants
 };
 
-enum GenKind { GEN_ARITH, GEN_CONST, GEN_SPLIT, GEN_BASE_SPLIT, GEN_BASE_SUM, GEN_RANDOM_ACCESS, GEN_POSEIDON };
+enum GenKind { GEN_ARITH, GEN_CONST, GEN_SPLIT, GEN_BASE_SPLIT, GEN_BASE_SUM, GEN_RANDOM_ACCESS, GEN_POSEIDON, GEN_EQUAL };
 struct Gen {
     GenKind kind;
     int row, i;         // gate row, op / copy index
     u64 c0, c1;         // arithmetic constants / constant value
-    Target t;           // GEN_SPLIT: the integer
+    Target t;           // GEN_SPLIT: the integer; GEN_EQUAL: x
+    Target t2, t3, t4;  // GEN_EQUAL: y, equal, inv
     std::vector<int> rows;   // GEN_SPLIT: the BaseSum rows
     int n;              // limbs / bits
     bool done = false;
@@ -185,6 +186,23 @@ struct Builder {
     Target mul_sub(Target x, Target y, Target z) { return arithmetic(1, GL_P - 1, x, y, z); }
     Target select(Target b, Target x, Target y) {   // gadgets/select.rs: b x - (b y - y)
         return mul_sub(b, x, mul_sub(b, y, y));
+    }
+    // is_equal (gadgets/arithmetic.rs): equal * (x - y) = 0 and 1 - equal = (x - y) * inv, with EqualityGenerator filling equal / inv
+    Target is_equal(Target x, Target y) {
+        Target equal = add_virtual_target(), not_equal = b_not(equal), inv = add_virtual_target();
+        Gen g = {};
+        g.kind = GEN_EQUAL;
+        g.t = x;
+        g.t2 = y;
+        g.t3 = equal;
+        g.t4 = inv;
+        gens.push_back(g);
+        Target diff = sub(x, y);
+        Target not_equal_check = mul(equal, diff);
+        Target diff_normalized = mul(diff, inv);
+        connect(not_equal, diff_normalized);
+        connect(not_equal_check, zero());
+        return equal;
     }
     Target add_virtual_bool_target_safe() {   // a fresh target constrained to {0, 1}: b b - b = 0
         Target t = add_virtual_target();
@@ -396,6 +414,13 @@ struct Builder {
             for (int b = 0; b < bits; b++) set(wire(g.row, routed_used + g.i * bits + b), (idx >> b) & 1);
             return true;
         }
+        case GEN_EQUAL: {
+            u64 x, y;
+            if (!get(g.t, &x) || !get(g.t2, &y)) return false;
+            set(g.t3, x == y ? 1 : 0);
+            set(g.t4, x == y ? 0 : gl_inv(gl_sub(x, y)));
+            return true;
+        }
         case GEN_POSEIDON: {
             u64 st[12];
             for (int i = 0; i < 12; i++)
@@ -578,6 +603,20 @@ void sha256_compression(Translator& T, const u32* in_w, const u32* hv_w, const u
     }
 }
 
+// memory_translator.rs:55-85: index <= max_allowed_value, bit by bit from the most significant one
+void assert_less_or_equal(Builder& b, size_t max_allowed, Target index) {
+    int nbits = 1;
+    while ((max_allowed >> nbits) != 0) nbits++;
+    Bits bits = b.split_le(index, nbits);
+    std::reverse(bits.begin(), bits.end());
+    Target acc = b.one();
+    for (int i = 0; i < nbits; i++) {
+        const int bit = (int)((max_allowed >> (nbits - 1 - i)) & 1);
+        if (bit == 0) b.assert_zero(b.mul(bits[i], acc));
+        else acc = b.mul(acc, bits[i]);
+    }
+}
+
 // flat opcode stream (what acir.py writes): u64 words
 //   1 AssertZero: n_mul, n_lin, q_c, then n_mul x (coef, w1, w2), n_lin x (coef, w)          assert_zero_translator.rs:30-116
 //   2 RANGE: witness, num_bits                                                                  mod.rs:131-137
@@ -585,7 +624,8 @@ void sha256_compression(Translator& T, const u32* in_w, const u32* hv_w, const u
 //   5 MemoryInit: block_id, n, then n witnesses                                                 memory_translator.rs:145-156
 //   6 MemoryRead: block_id, index witness, value witness                                        memory_translator.rs:125-137
 //   7 Sha256Compression: 16 input witnesses, 8 hash-value witnesses, 8 output witnesses         sha256_translator.rs:60-111
-enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6, OP_SHA256_COMPRESSION = 7 };
+//   8 MemoryWrite: block_id, index witness, value witness                                       memory_translator.rs:87-113
+enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6, OP_SHA256_COMPRESSION = 7, OP_MEM_WRITE = 8 };
 
 void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size_t npriv, const u64* ops, size_t nwords) {
     Builder& b = T.b;
@@ -660,8 +700,22 @@ void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size
             const u64 id = next(), iw = next(), vw = next();
             auto it = T.memory_blocks.find((u32)id);
             if (it == T.memory_blocks.end()) throw Error{"MemoryOp on an uninitialised block"};
+            assert_less_or_equal(b, it->second.second - 1, T.target_for_witness((u32)iw));
             Target res = b.random_access(T.target_for_witness((u32)iw), it->second.first);
             T.witness_target_map[(u32)vw] = res;
+            break;
+        }
+        case OP_MEM_WRITE: {   // memory_translator.rs:87-113: every cell becomes  index == position ? new value : old value
+            const u64 id = next(), iw = next(), vw = next();
+            auto it = T.memory_blocks.find((u32)id);
+            if (it == T.memory_blocks.end()) throw Error{"MemoryOp on an uninitialised block"};
+            Target idx = T.target_for_witness((u32)iw), val = T.target_for_witness((u32)vw);
+            assert_less_or_equal(b, it->second.second - 1, idx);
+            std::vector<Target>& cells = it->second.first;
+            for (size_t pos = 0; pos < cells.size(); pos++) {
+                Target eq = b.is_equal(idx, b.constant(pos));
+                cells[pos] = b.select(eq, val, cells[pos]);
+            }
             break;
         }
         case OP_SHA256_COMPRESSION: {

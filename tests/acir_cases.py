@@ -38,6 +38,14 @@ def cases(acir):
     out.append(("memory_read_irregular_block", C([acir.MemoryInit(0, [0, 1, 2]), acir.MemoryRead(0, 3, 4),
                                                   AZ(E([], [(1, 4)], -21))], [0, 1, 2, 3]),
                 {0: 20, 1: 21, 2: 22, 3: 1}, [20, 21, 22, 1]))
+    # test_memory_operations.rs:39-79: x[y] = v; assert(x[0] == 1); assert(x[1] == 11)
+    out.append(("memory_write", C([acir.MemoryInit(0, [0, 1]), acir.MemoryWrite(0, 2, 3), acir.MemoryRead(0, 4, 6),
+                                   acir.MemoryRead(0, 5, 7), AZ(E([], [(1, 6)], -1)), AZ(E([], [(1, 7)], -11))], [0, 1, 2, 3]),
+                {0: 10, 1: 11, 2: 0, 3: 1, 4: 0, 5: 1, 6: 1, 7: 11}, [10, 11, 0, 1]))
+    # a write into a block of irregular size, read back through a computed index
+    out.append(("memory_write_irregular", C([acir.MemoryInit(1, [0, 1, 2]), acir.MemoryWrite(1, 3, 4), acir.MemoryRead(1, 3, 5),
+                                             AZ(E([], [(1, 5), (P - 1, 4)], 0))], [0, 1, 2, 3, 4]),
+                {0: 7, 1: 8, 2: 9, 3: 2, 4: 55}, [7, 8, 9, 2, 55]))
     return out
 
 

@@ -46,7 +46,7 @@ def _check_trace(p2g, corc, tr, wires, pis):
     return cd, moved
 
 
-NUM_CASES = 24
+NUM_CASES = 26
 
 
 @pytest.mark.parametrize("case", range(NUM_CASES))
@@ -86,6 +86,9 @@ def test_bad_witnesses_are_refused_like_the_reference_panics(p2g):
     tr.generate_witness({0: 3, 1: 5, 2: 1})
     with pytest.raises(A.TranslationError):
         tr.generate_witness({0: 3, 1: 5, 2: 7})
+    with pytest.raises(A.TranslationError):        # index beyond the real block length (3 cells padded to 4): memory_translator.rs:55-85
+        tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(A.Circuit([A.MemoryInit(0, [0, 1, 2]), A.MemoryRead(0, 3, 4)], [0, 1, 2, 3]))
+        tr.generate_witness({0: 1, 1: 2, 2: 3, 3: 3})
     with pytest.raises(A.TranslationError):        # memory read past the block
         tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(A.Circuit([A.MemoryInit(0, [0, 1]), A.MemoryRead(0, 2, 3)], [0, 1, 2]))
         tr.generate_witness({0: 1, 1: 2, 2: 5})

@@ -12,7 +12,7 @@ import acir_cases  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("case", [0, 4, 8, 10, 14, 16, 19, 21, 23])
+@pytest.mark.parametrize("case", [0, 4, 8, 10, 14, 16, 19, 21, 23, 24, 25])
 def test_translated_circuits_prove_on_the_gpu(p2g, corc, case):
     from helpers import oracle_cd
     from oracle.pyref import proof, verifier
