@@ -1497,7 +1497,9 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
         pow_witness = *forced_pow;
     } else {
         unsigned long long* best = ensure(C->ws.best, 1);
-        const u64 batch = (u64)1 << 20;
+        // 2^(pow_bits + 2) candidates per launch: the smallest witness is in the first batch with probability 1 - e^-4 (98 %);
+        // a 2^20 batch hashed 16 x more candidates than needed at pow_bits = 16 (0.8 ms per proof)
+        const u64 batch = (u64)1 << std::min<u32>(20, std::max<u32>(12, d.pow_bits + 2));
         for (u64 start = 0;; start += batch) {
             CUDA_CHECK(cudaMemsetAsync(best, 0xff, 8, st));
             k_pow_search<<<(unsigned)(batch / 128), 128, 0, st>>>(ch, start, batch, d.pow_bits, best);

@@ -27,7 +27,9 @@ UNIT = "proofs/s"
 NCU = {"lde_traffic_over_algorithmic": 6.26 / 2.265, "keccak_traffic_over_algorithmic": 15.98 / 15.70,
        "lde_limiter": "integer ALU pipe 64-67% active, FMA pipe 21-22%, DRAM 1.08 TB/s: issue-bound 64-bit modular arithmetic, not HBM-bound",
        "keccak_limiter": "integer ALU pipe 99.7% active (LOP3/SHF): at the hardware floor for Keccak-f",
-       "files": ["profiles/r1k_ntt_ncu_raw.csv", "profiles/r1k_keccak_ncu_raw.csv", "profiles/r1k_launches_bench.csv"]}
+       "quotient_dram_bytes": 65.5e9,
+       "quotient_limiter": "integer issue: 84 k instructions per point in the limb sweep (8.1 k IMAD.WIDE), issue slots 55 % busy, DRAM 0.6-2.8 TB/s",
+       "files": ["profiles/r2_ntt_ncu_raw.csv", "profiles/r2_keccak_ncu_raw.csv", "profiles/r2_quotient_ncu_raw.csv", "profiles/r2_launches_bench.csv"]}
 
 
 def parse():
@@ -388,6 +390,7 @@ def main():
         stages = {k: round(mean(k), 3) for k in ["wires_commit_ms", "zs_pp_ms", "quotient_ms", "openings_ms", "fri_ms", "d2h_ms",
                                                  "total_ms", "ntt_ms", "merkle_ms", "leaf_hash_ms", "lde_ms",
                                                  "quotient_kernel_ms"]}
+        q_alg = 8.0 * (sc.common.degree() << cfg.rate_bits) * (sc.common.num_preprocessed + cfg.num_wires + 20 + 2 + 2)
         launches = sum(o.timings["kernel_launches"] for o in outs) + sum(o.timings["kernel_launches"] for o in outs_e2e)
         proof_bytes = len(outs[0].to_bytes())
         line = {
@@ -422,6 +425,13 @@ def main():
                                 "traffic_unit": "bytes per step", "launches_per_step": tms[0]["leaf_hash_launches"],
                                 "avg_launch_ms": sum(t["leaf_hash_ms"] for t in tms) / sum(t["leaf_hash_launches"] for t in tms),
                                 "limiter": NCU["keccak_limiter"]},
+            # constraint evaluation (quotient.cu): bounded by integer issue, reported against HBM like the other two; algorithmic bytes =
+            # every preprocessed / wire / Z column of the LDE read once + the two quotient columns written (64N (P + W + 22))
+            "quotient_roofline": {"kernel": "k_quotient_perm + k_quotient_limb + k_quotient_gate<kind> (vanishing-polynomial evaluation on the 8N coset)",
+                                  "bound": "hbm", "achieved": q_alg / 1e9 / (mean("quotient_kernel_ms") / 1e3), "peak": hbm, "unit": "GB/s",
+                                  "frac": q_alg / 1e9 / (mean("quotient_kernel_ms") / 1e3) / hbm, "algorithmic_bytes_per_step": q_alg,
+                                  "traffic": NCU["quotient_dram_bytes"], "traffic_unit": "bytes per step (ncu dram__bytes_read + write, 2^20-row proof)",
+                                  "avg_stage_ms": mean("quotient_kernel_ms"), "limiter": NCU["quotient_limiter"]},
             "stages_ms": dict(stages, measured_on="one proof at a time (no overlap)" if F > 1 else "the timed region"),
             "clocks": clocks,
         }

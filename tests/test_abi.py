@@ -62,3 +62,48 @@ def test_header_is_plain_c99(tmp_path):
     hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "p2g.h")).read(), flags=re.S)   # declarations only
     assert "torch" not in hdr and "cudaStream" not in hdr and "std::" not in hdr
     assert subprocess.run([str(exe)]).returncode == 0        # p2g_version / p2g_last_error need no GPU
+
+
+def _desc(p2g, workload="all_gates", bits=6):
+    sc = p2g.synth.SyntheticCircuit(bits, workload, num_public_inputs=2, seed=5)
+    d, keep = sc.common.fill_desc(sc.constants_sigmas)
+    return sc, d, keep
+
+
+def test_malformed_descriptors_are_refused_before_any_cuda_call(p2g):
+    """include/p2g.h promises P2G_EBADARG for malformed descriptors: gate parameters are checked against the circuit
+    shape, so a bad table can never drive the kernels out of bounds.  No GPU needed: validation precedes device work."""
+    L = p2g.lib.lib()
+    h = C.c_void_p()
+
+    def refused(mutate, needle):
+        sc, d, keep = _desc(p2g)
+        mutate(d, sc)
+        rc = L.p2g_circuit_create(C.byref(d), 0, C.byref(h))
+        assert rc == p2g.lib.P2G_EBADARG, (needle, rc, L.p2g_last_error())
+        assert needle.encode() in L.p2g_last_error(), L.p2g_last_error()
+        del keep
+
+    def gate_of(d, kind):
+        return next(i for i in range(d.num_gates) if d.gates[i].kind == kind)
+    K = p2g.circuit
+    refused(lambda d, sc: setattr(d, "num_wires", 100), "more wires than num_wires")                    # U32 gates need > 200 wires
+    refused(lambda d, sc: setattr(d.gates[gate_of(d, K.ARITHMETIC)], "num_constraints", 19), "num_constraints does not match")
+    refused(lambda d, sc: setattr(d, "num_selectors", d.num_constants + 1), "num_selectors > num_constants")
+    refused(lambda d, sc: setattr(d, "pow_bits", 65), "pow_bits")
+    refused(lambda d, sc: setattr(d, "cap_height", 12), "cap_height")
+    refused(lambda d, sc: d.gates[gate_of(d, K.COMPARISON)].params.__setitem__(1, 0), "ComparisonGate")  # num_chunks = 0 would divide by zero
+    refused(lambda d, sc: d.gates[gate_of(d, K.RANDOM_ACCESS)].params.__setitem__(0, 7), "RandomAccessGate bits")
+    refused(lambda d, sc: setattr(d, "num_constants", d.num_selectors + 1), "more constants than")       # ArithmeticGate reads 2 constants
+
+    def deep_fri(d, sc):
+        d.num_fri_layers = 1
+        d.reduction_arity_bits[0] = 6          # 2^(6 + 3 - 6) = 8 leaves < 2^cap_height
+    refused(deep_fri, "fewer than 2^cap_height leaves")
+    # and the untouched descriptor passes validation: the only failure left on a machine without a GPU is the device itself
+    sc, d, keep = _desc(p2g)
+    rc = L.p2g_circuit_create(C.byref(d), 0, C.byref(h))
+    if rc == 0:
+        L.p2g_circuit_destroy(h)
+    else:
+        assert rc == p2g.lib.P2G_ECUDA, L.p2g_last_error()
