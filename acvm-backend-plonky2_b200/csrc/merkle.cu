@@ -98,6 +98,29 @@ __global__ void __launch_bounds__(128) k_nodes(int h, const digest_t* __restrict
     out[i] = h == P2G_H_KECCAK25 ? keccak25_two_to_one(l, r) : poseidon_two_to_one(l, r);
 }
 
+// The last levels of a tree (<= 1024 nodes) in ONE launch: a level per __syncthreads instead of a launch per level (each of
+// those launches ran below one wave and cost its launch latency: ~10 per tree, 7 trees per proof).
+#define TAIL_MAX 12
+struct TailArgs {
+    const digest_t* in;          // the level below the first tail level
+    digest_t* out[TAIL_MAX];     // the tail levels, bottom up
+    int nlev;
+    unsigned cnt0;               // nodes of the first tail level
+};
+__global__ void __launch_bounds__(1024) k_nodes_tail(int h, TailArgs a) {
+    const unsigned t = threadIdx.x;
+    const digest_t* in = a.in;
+    unsigned cnt = a.cnt0;
+    for (int k = 0; k < a.nlev; k++, cnt >>= 1) {
+        if (t < cnt) {
+            digest_t l = in[2 * t], r = in[2 * t + 1];
+            a.out[k][t] = h == P2G_H_KECCAK25 ? keccak25_two_to_one(l, r) : poseidon_two_to_one(l, r);
+        }
+        __syncthreads();   // block-wide: the level just written is read by the same block
+        in = a.out[k];
+    }
+}
+
 }  // namespace
 
 void merkle_build(DevCtx* c, MerkleTree* t, const u64* d_leaves, size_t col_stride, int log_leaves, int ncols, int cap_height,
@@ -136,6 +159,16 @@ void merkle_build(DevCtx* c, MerkleTree* t, const u64* d_leaves, size_t col_stri
     count_launch(c);
     for (int k = 1; k < nlevels; k++) {
         size_t cnt = nl >> k;
+        if (cnt <= 1024 && nlevels - k <= TAIL_MAX) {   // the rest of the tree in one block
+            TailArgs a = {};
+            a.in = t->levels[k - 1].p;
+            a.nlev = nlevels - k;
+            a.cnt0 = (unsigned)cnt;
+            for (int q = 0; q < a.nlev; q++) a.out[q] = t->levels[k + q].p;
+            k_nodes_tail<<<1, (unsigned)std::max<size_t>(32, cnt), 0, c->stream>>>(hasher, a);
+            count_launch(c);
+            break;
+        }
         k_nodes<<<(unsigned)((cnt + TH - 1) / TH), TH, 0, c->stream>>>(hasher, t->levels[k - 1].p, t->levels[k].p, cnt);
         count_launch(c);
     }

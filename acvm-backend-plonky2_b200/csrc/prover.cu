@@ -1781,6 +1781,7 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
         std::lock_guard<std::mutex> lk(C->mu);
         DevCtx* c = C->ctx;
         CUDA_CHECK(cudaSetDevice(c->device));
+        resolve_timers(c);   // stage events left behind by a proof that failed half way must not leak into this one's totals
         c->launches = 0;
         c->ntt_bytes = c->merkle_bytes = c->leaf_bytes = c->lde_bytes = 0;
         c->ntt_ms = c->merkle_ms = c->leaf_ms = c->lde_ms = c->quot_ms = 0;

@@ -189,6 +189,10 @@ __global__ void __launch_bounds__(256, MINB) k_quotient_limb(const __grid_consta
             u64 v[SWEEP_B];
 #pragma unroll
             for (int i = 0; i < SWEEP_B; i++) v[i] = (w0 + i < w_end && LP.need[w0 + i]) ? wire(w0 + i) : 0;
+            // the SWEEP_B checks are independent of each other and of the event bookkeeping below: computing them up front gives
+            // the scheduler four multiply chains to interleave
+#pragma unroll
+            for (int i = 0; i < SWEEP_B; i++) v[i] = limb4_check(v[i]);
 #pragma unroll
             for (int i = 0; i < SWEEP_B; i++) {
                 const int w = w0 + i;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(256, MINB) k_quotient_limb(const __grid_consta
                 events_at(w);
                 const unsigned need = LP.need[w];
                 if (need) {
-                    const u64 ck = limb4_check(v[i]);
+                    const u64 ck = v[i];
                     if (need & 1) {
                         A0.mac(ck, P.apow[0][w]);
                         A1.mac(ck, P.apow[1][w]);
