@@ -1854,8 +1854,13 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
                     }
                     CUDA_CHECK(cudaEventSynchronize(up.stage_free[slot]));
                     u64* dst = up.stage[slot];
-                    const int T = 8;
-                    std::thread th[T];
+                    // gather threads: up to 16 (P2G_STAGE_THREADS overrides); the copy is bound by host memory bandwidth
+                    static const int T = [] {
+                        const char* e = getenv("P2G_STAGE_THREADS");
+                        int t = e ? atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+                        return std::max(1, std::min(t, 64));
+                    }();
+                    std::vector<std::thread> th(T);
                     for (int t = 0; t < T; t++) {
                         // words [lo, hi) of the chunk, column by column (the columns need not be adjacent in host memory)
                         size_t lo = words * t / T, hi = words * (t + 1) / T;
