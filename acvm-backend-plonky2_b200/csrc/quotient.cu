@@ -143,11 +143,11 @@ __global__ void __launch_bounds__(256) k_quotient_gate(const __grid_constant__ Q
 // four multiply-accumulates into the running prefixes, and at every window boundary one `filter * prefix * coef` term.  The
 // gates' remaining constraints (recombinations, carries) follow in the same kernel while the block's columns are L2-resident.
 #define SWEEP_B 4
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) k_quotient_limb(const __grid_constant__ QuotientParams P, const __grid_constant__ LimbPlan LP,
+template <int MINB, int NTH>
+__global__ void __launch_bounds__(NTH, MINB) k_quotient_limb(const __grid_constant__ QuotientParams P, const __grid_constant__ LimbPlan LP,
                                                        const u64* __restrict__ cs, const u64* __restrict__ wires,
                                                        u64* __restrict__ out_, int scale_now, size_t L, size_t j0, size_t OL) {
-    __shared__ u64 fsh[P2G_MAX_LIMB_GATES][256];
+    __shared__ u64 fsh[P2G_MAX_LIMB_GATES][NTH];
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= L) return;
     u64* __restrict__ out = out_ + j0;
@@ -432,10 +432,11 @@ void quotient_eval(DevCtx* c, const QuotientParams& qp, const LimbPlan* lp, cons
         count_launch(c);
     }
     if (sweep) {
-        // two blocks per SM (126 registers): the three-block build spills and measured 50 ms against 34 ms (tools/limb_sweep.sh)
         static const int minb = getenv("P2G_LIMB_MINB") ? atoi(getenv("P2G_LIMB_MINB")) : 2;
-        if (minb == 2) k_quotient_limb<2><<<grid, TH, 0, c->stream>>>(qp, *lp, d_cs, d_wires, d_out, 1, npts, j0, out_stride);
-        else k_quotient_limb<3><<<grid, TH, 0, c->stream>>>(qp, *lp, d_cs, d_wires, d_out, 1, npts, j0, out_stride);
+        // two blocks of 256 threads per SM at 126 registers.  Measured alternatives on B200 (tools/limb_sweep.sh): 3 x 256 at 80
+        // registers spills (50 ms), 3 x 192 and 5 x 128 at 96 registers re-materialise (48 / 45 ms) against 34.5 ms here
+        if (minb == 3) k_quotient_limb<3, 256><<<grid, TH, 0, c->stream>>>(qp, *lp, d_cs, d_wires, d_out, 1, npts, j0, out_stride);
+        else k_quotient_limb<2, 256><<<grid, TH, 0, c->stream>>>(qp, *lp, d_cs, d_wires, d_out, 1, npts, j0, out_stride);
         count_launch(c);
     }
     CUDA_CHECK(cudaGetLastError());
