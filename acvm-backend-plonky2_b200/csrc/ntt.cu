@@ -124,18 +124,29 @@ __device__ __forceinline__ u64 shl_by_index(u64 v, int, int h, int kk, bool inv)
 // stage.  Forward = decimation in frequency (stage order s0 .. s0+R-1), inverse = decimation in time (reverse order).
 // LAST: the round that ends the sub-transform (s0 + R == a).  Its twiddles are omega_{2h}^kk with 2h <= 2^R <= 16, i.e. the
 // compile-time powers of two 2^(96 kk / h): multiplication-free butterflies, no twiddle loads.
-template <int R, bool INV, bool LAST>
-__device__ __forceinline__ void reg_round(u64* __restrict__ sm, const u64* __restrict__ s_tw, int a, int s0, int logq, int log_tasks) {
+// CA / CS0 / CQ / CLE / CTH: the sub-transform length, first stage, run width, tile size and block size as compile-time constants (the hot
+// plans of the 2^20-row LDE are instantiated that way: every shift, mask and padded address below folds; ncu showed a third of a
+// round's instructions going into them).  A thread's 2^R elements sit `stride` apart in the tile; when stride is a multiple of 16
+// their padded addresses are phys(first) + k * (stride + stride / 16).
+template <int R, bool INV, bool LAST, int CA = 0, int CS0 = -1, int CQ = -1, int CLE = 0, int CTH = 0>
+__device__ __forceinline__ void reg_round(u64* __restrict__ sm, const u64* __restrict__ s_tw, int a_, int s0_, int logq_, int log_tasks_) {
+    const int a = CA > 0 ? CA : a_, s0 = CS0 >= 0 ? CS0 : s0_, logq = CQ >= 0 ? CQ : logq_;
+    const int log_tasks = CLE > 0 ? CLE - R : log_tasks_;   // CLE: log2 of the tile's element count
+    const int nthreads = CTH > 0 ? CTH : (int)blockDim.x;
     const int lo_bits = LAST ? 0 : a - s0 - R;
     const int A = 1 << a;
     const int lo_mask = (1 << lo_bits) - 1, q_mask = (1 << logq) - 1;
-    for (int task = threadIdx.x; task < (1 << log_tasks); task += blockDim.x) {
+    const int stride = 1 << (lo_bits + logq);
+    const bool linear = (stride & 15) == 0;
+    const int pstride = stride + (stride >> 4);
+    for (int task = threadIdx.x; task < (1 << log_tasks); task += nthreads) {
         const int qq = task & q_mask, t = task >> logq;
         const int lo = t & lo_mask;
         const int base_m = ((t >> lo_bits) << (lo_bits + R)) | lo;
+        const int e0 = (base_m << logq) | qq, p0 = phys(e0);
         u64 x[1 << R];
 #pragma unroll
-        for (int k = 0; k < (1 << R); k++) x[k] = sm[phys(((base_m + (k << lo_bits)) << logq) | qq)];
+        for (int k = 0; k < (1 << R); k++) x[k] = sm[linear ? p0 + k * pstride : phys(e0 + k * stride)];
 #pragma unroll
         for (int ii = 0; ii < R; ii++) {
             const int i = INV ? R - 1 - ii : ii;
@@ -173,7 +184,7 @@ __device__ __forceinline__ void reg_round(u64* __restrict__ sm, const u64* __res
             }
         }
 #pragma unroll
-        for (int k = 0; k < (1 << R); k++) sm[phys(((base_m + (k << lo_bits)) << logq) | qq)] = x[k];
+        for (int k = 0; k < (1 << R); k++) sm[linear ? p0 + k * pstride : phys(e0 + k * stride)] = x[k];
     }
     __syncthreads();
 }
@@ -214,6 +225,19 @@ __device__ __forceinline__ void tile_butterflies(u64* sm, const u64* s_tw, int a
         else if (rem == 2) reg_round<2, true, false>(sm, s_tw, a, 0, logq, log_elems - 2);
         else if (rem == 1) reg_round<1, true, false>(sm, s_tw, a, 0, logq, log_elems - 1);
     }
+}
+
+// The same for a compile-time shape (forward only, RMAX = 3): the round sequence of tile_butterflies unrolled with constant stages.
+template <int CA, int CQ, int CLE, int CTH>
+__device__ __forceinline__ void tile_butterflies_fixed(u64* sm, const u64* s_tw) {
+    constexpr int rem = CA % 3, full = CA / 3;
+    static_assert(full >= 1, "fixed shapes have at least one full round");
+    if (rem == 2) reg_round<2, false, false, CA, 0, CQ, CLE, CTH>(sm, s_tw, CA, 0, CQ, CLE - 2);
+    else if (rem == 1) reg_round<1, false, false, CA, 0, CQ, CLE, CTH>(sm, s_tw, CA, 0, CQ, CLE - 1);
+    if (full >= 2) reg_round<3, false, false, CA, rem, CQ, CLE, CTH>(sm, s_tw, CA, rem, CQ, CLE - 3);
+    if (full >= 3) reg_round<3, false, false, CA, rem + 3, CQ, CLE, CTH>(sm, s_tw, CA, rem + 3, CQ, CLE - 3);
+    static_assert(full <= 3, "add a round");
+    reg_round<3, false, true, CA, CA - 3, CQ, CLE, CTH>(sm, s_tw, CA, CA - 3, CQ, CLE - 3);
 }
 
 // Strided pass: tile [A][Q], element (m, qq) at column index blk*B + m*S + q0 + qq.  grid.x = tile * nz + coset: the cosets
@@ -307,6 +331,97 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_contig(PassArgs
     }
 }
 
+// ---- forward passes with compile-time shapes (the plans of the hot LDE sizes) ---------------------------------------------------
+// Same data movement and arithmetic as k_pass_strided<false> / k_pass_contig<false>; tile size, sub-transform length, run width and
+// block size are template constants, so the fill / drain loops are fully unrolled with constant strides and the register rounds'
+// index arithmetic folds (ncu source page of the generic kernels: ~35 % of a round's instructions were address arithmetic).
+template <int CA, int CQ, int CTH>
+__global__ void __launch_bounds__(CTH, 1024 / CTH) k_pass_strided_fwd(PassArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    constexpr int A = 1 << CA, Q = 1 << CQ, total = A << CQ, EPT = total / CTH, MSTEP = CTH >> CQ, PSTEP = CTH + (CTH >> 4);
+    static_assert(CTH % Q == 0 && CTH % 16 == 0 && total % CTH == 0 && EPT % 4 == 0, "shape");
+    const int logS = a.logB - CA;
+    u64* s_tw = sm + tile_words(total);
+    u64* mbar = s_tw + A;
+    const u32 col = a.col_fast ? blockIdx.x : blockIdx.y, tz = a.col_fast ? blockIdx.y : blockIdx.x;
+    const u32 z = tz % a.nz, tile = tz / a.nz;
+    const u32 tiles_per_blk = 1u << (logS - CQ);
+    const u32 blk = tile / tiles_per_blk;
+    const u32 q0 = (tile % tiles_per_blk) << CQ;
+    const u64* in = a.in + (size_t)col * a.in_cs + (size_t)z * a.in_zs;
+    u64* out = a.out + (size_t)col * a.out_cs + (size_t)z * a.out_zs;
+    const u64* stab = a.stab ? a.stab + (size_t)z * a.stab_zs : nullptr;
+    const int tid = threadIdx.x, qq = tid & (Q - 1), m0 = tid >> CQ, p0 = phys(tid);
+    // element i of this thread: tile index e = tid + i CTH -> (m0 + i MSTEP, qq); column index idx0 + i * istep
+    const size_t idx0 = ((size_t)blk << a.logB) + q0 + ((size_t)m0 << logS) + qq, istep = (size_t)MSTEP << logS;
+
+    stage_tw_begin(s_tw, a.tw, A, mbar);
+#pragma unroll
+    for (int i0 = 0; i0 < EPT; i0 += 4) {
+        u64 v[4], sc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            v[i] = in[idx0 + (i0 + i) * istep];
+            sc[i] = stab ? __ldg(stab + idx0 + (i0 + i) * istep) : 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) sm[p0 + (i0 + i) * PSTEP] = stab ? glf_mul(v[i], sc[i]) : v[i];
+    }
+    stage_tw_end(A, mbar);
+    tile_butterflies_fixed<CA, CQ, CA + CQ, CTH>(sm, s_tw);
+    const u64* twist = a.twist ? a.twist + ((size_t)m0 << logS) + q0 + qq : nullptr;
+#pragma unroll
+    for (int i0 = 0; i0 < EPT; i0 += 4) {
+        u64 v[4], tw[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            v[i] = sm[p0 + (i0 + i) * PSTEP];
+            tw[i] = twist ? __ldg(twist + (i0 + i) * istep) : 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[idx0 + (i0 + i) * istep] = twist ? glf_mul(v[i], tw[i]) : v[i];
+    }
+}
+
+template <int CA, int CNB, int CTH>
+__global__ void __launch_bounds__(CTH, 1024 / CTH) k_pass_contig_fwd(PassArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    constexpr int A = 1 << CA, total = A << CNB, EPT = total / CTH, PSTEP = CTH + (CTH >> 4);
+    static_assert(CTH % 16 == 0 && total % CTH == 0 && EPT % 4 == 0, "shape");
+    u64* s_tw = sm + tile_words(total);
+    u64* mbar = s_tw + A;
+    const u32 col = a.col_fast ? blockIdx.x : blockIdx.y, tz = a.col_fast ? blockIdx.y : blockIdx.x;
+    const u32 z = tz % a.nz, tile = tz / a.nz;
+    const u64* in = a.in + (size_t)col * a.in_cs + (size_t)z * a.in_zs;
+    u64* out = a.out + (size_t)col * a.out_cs + (size_t)z * a.out_zs;
+    const u64* stab = a.stab ? a.stab + (size_t)z * a.stab_zs : nullptr;
+    const int tid = threadIdx.x, p0 = phys(tid);
+    const size_t idx0 = ((size_t)tile << (CA + CNB)) + tid;
+
+    stage_tw_begin(s_tw, a.tw, A, mbar);
+#pragma unroll
+    for (int i0 = 0; i0 < EPT; i0 += 4) {
+        u64 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = in[idx0 + (size_t)(i0 + i) * CTH];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (stab) v[i] = glf_mul(v[i], __ldg(stab + idx0 + (size_t)(i0 + i) * CTH));   // single-pass plans only
+            sm[p0 + (i0 + i) * PSTEP] = v[i];
+        }
+    }
+    stage_tw_end(A, mbar);
+    tile_butterflies_fixed<CA, 0, CA + CNB, CTH>(sm, s_tw);
+#pragma unroll
+    for (int i0 = 0; i0 < EPT; i0 += 4) {
+        u64 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = sm[p0 + (i0 + i) * PSTEP];
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[idx0 + (size_t)(i0 + i) * CTH] = v[i];
+    }
+}
+
 // out[i] = premul * base^(i * step) for i < n
 __global__ void k_fill_pow(u64* out, u32 n, u64 base, u64 step, u64 premul) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -345,6 +460,7 @@ int env_int(const char* name, int dflt) {
 int ntt_tile_log() { static int v = env_int("P2G_NTT_TILE", 12); return v; }
 int ntt_last_log() { static int v = env_int("P2G_NTT_LAST", 11); return v; }
 int ntt_threads() { static int v = env_int("P2G_NTT_TH", 0); return v; }
+int ntt_fixed() { static int v = env_int("P2G_NTT_FIXED", 1); return v; }   // 0: generic kernels only (A/B)
 int ntt_rmax() {
     static int r = 0;
     if (!r) {
@@ -389,6 +505,10 @@ void set_smem_attrs() {
     if (std::find(devs.begin(), devs.end(), dev) != devs.end()) return;
     devs.push_back(dev);
     const int lim = 160 * 1024;
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<9, 3, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<7, 5, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<5, 7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig_fwd<11, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -460,7 +580,11 @@ void run_forward(DevCtx* c, const XformDesc& d) {
             a.nz = d.nz;
             dim3 grid = make_grid(a, tiles * d.nz, d.ncols);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
-            if (ntt_rmax() == 4) k_pass_strided<false, 4><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
+            const bool fixed = ntt_fixed() && ntt_rmax() == 3 && th == 256 && a.scale == 1;
+            if (fixed && a.loga == 9 && a.logq == 3) k_pass_strided_fwd<9, 3, 256><<<grid, 256, strided_smem(9, 3), c->stream>>>(a);
+            else if (fixed && a.loga == 7 && a.logq == 5) k_pass_strided_fwd<7, 5, 256><<<grid, 256, strided_smem(7, 5), c->stream>>>(a);
+            else if (fixed && a.loga == 5 && a.logq == 7) k_pass_strided_fwd<5, 7, 256><<<grid, 256, strided_smem(5, 7), c->stream>>>(a);
+            else if (ntt_rmax() == 4) k_pass_strided<false, 4><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
             else k_pass_strided<false, 3><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
         } else {
             int lognb = d.logn - a.loga;
@@ -469,7 +593,9 @@ void run_forward(DevCtx* c, const XformDesc& d) {
             a.nz = d.nz;
             dim3 grid = make_grid(a, tiles * d.nz, d.ncols);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
-            if (ntt_rmax() == 4) k_pass_contig<false, 4><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
+            const bool fixed = ntt_fixed() && ntt_rmax() == 3 && th == 256 && a.scale == 1;
+            if (fixed && a.loga == 11 && a.logq == 1) k_pass_contig_fwd<11, 1, 256><<<grid, 256, contig_smem(11, 1), c->stream>>>(a);
+            else if (ntt_rmax() == 4) k_pass_contig<false, 4><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
             else k_pass_contig<false, 3><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
         }
         count_launch(c);
