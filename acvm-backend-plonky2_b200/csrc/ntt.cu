@@ -508,6 +508,8 @@ void set_smem_attrs() {
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<9, 3, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<7, 5, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<5, 7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<6, 6, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<8, 4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig_fwd<11, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -584,6 +586,8 @@ void run_forward(DevCtx* c, const XformDesc& d) {
             if (fixed && a.loga == 9 && a.logq == 3) k_pass_strided_fwd<9, 3, 256><<<grid, 256, strided_smem(9, 3), c->stream>>>(a);
             else if (fixed && a.loga == 7 && a.logq == 5) k_pass_strided_fwd<7, 5, 256><<<grid, 256, strided_smem(7, 5), c->stream>>>(a);
             else if (fixed && a.loga == 5 && a.logq == 7) k_pass_strided_fwd<5, 7, 256><<<grid, 256, strided_smem(5, 7), c->stream>>>(a);
+            else if (fixed && a.loga == 6 && a.logq == 6) k_pass_strided_fwd<6, 6, 256><<<grid, 256, strided_smem(6, 6), c->stream>>>(a);
+            else if (fixed && a.loga == 8 && a.logq == 4) k_pass_strided_fwd<8, 4, 256><<<grid, 256, strided_smem(8, 4), c->stream>>>(a);
             else if (ntt_rmax() == 4) k_pass_strided<false, 4><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
             else k_pass_strided<false, 3><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
         } else {

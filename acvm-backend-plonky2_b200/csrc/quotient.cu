@@ -38,6 +38,9 @@ struct WeightedSink {  // folds constraint k into sum_c += v * alpha_c^(off + k)
 // warp time stalled on instruction fetch and 38% on a load-imbalance barrier; see profiles/.)
 // Sharding: a rank evaluates the `npts` leaves [j0, j0 + npts) (whole cosets).  Input columns are local (stride L = npts,
 // index j); xs / l0s are the full per-circuit tables (index j0 + j); `out` is the full-size [NC][OL] quotient-value buffer.
+// CNC / CR / CCH > 0: num_challenges, num_routed and the chunk size as compile-time constants (2 / 80 / 8 = the reference's
+// configuration): loop bounds fold, the boundary predicates of the 4-wide load batches disappear.
+template <int CNC, int CR, int CCH>
 __global__ void __launch_bounds__(256) k_quotient_perm(const __grid_constant__ QuotientParams P, const u64* __restrict__ cs,
                                                        const u64* __restrict__ wires,
                                                        const u64* __restrict__ zpp, const u64* __restrict__ xs,
@@ -48,13 +51,14 @@ __global__ void __launch_bounds__(256) k_quotient_perm(const __grid_constant__ Q
     u64* __restrict__ out = out_ + j0;
     xs += j0;
     l0s += j0;
-    const int NC = P.num_challenges, NPP = P.num_partial_products, R = P.num_routed, C = P.num_constants;
+    const int NC = CNC ? CNC : P.num_challenges, R = CR ? CR : P.num_routed, C = P.num_constants;
+    const int NPP = (CR && CCH) ? (CR + CCH - 1) / CCH - 1 : P.num_partial_products;
     // next row of Z: natural index + 2^rate_bits  <=>  same coset, k -> k + 1 (k = bitrev_n(j mod N))
     const u32 nmask = (1u << P.logn) - 1;
     const u32 k = bitrev32((u32)j & nmask, P.logn);
     const size_t jn = (j & ~(size_t)nmask) | bitrev32((k + 1) & nmask, P.logn);
     const u64 x = xs[j], l0 = l0s[j];
-    const int chunk = P.qdf;
+    const int chunk = CCH ? CCH : P.qdf;
     gl_acc acc0, acc1;   // the two alpha-weighted sums, one reduction each at the end
     acc0.clear();
     acc1.clear();
@@ -413,7 +417,10 @@ void quotient_eval(DevCtx* c, const QuotientParams& qp, const LimbPlan* lp, cons
         solo.push_back(g);
     }
     const bool sweep = lp != nullptr;
-    k_quotient_perm<<<grid, TH, 0, c->stream>>>(qp, d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, solo.empty() && !sweep, npts, j0, out_stride);
+    if (qp.num_challenges == 2 && qp.num_routed == 80 && qp.qdf == 8 && qp.num_partial_products == 9)
+        k_quotient_perm<2, 80, 8><<<grid, TH, 0, c->stream>>>(qp, d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, solo.empty() && !sweep, npts, j0, out_stride);
+    else
+        k_quotient_perm<0, 0, 0><<<grid, TH, 0, c->stream>>>(qp, d_cs, d_wires, d_zpp, d_xs, d_l0s, d_out, solo.empty() && !sweep, npts, j0, out_stride);
     count_launch(c);
     for (size_t i = 0; i < solo.size(); i++) {
         const int g = solo[i];
