@@ -240,9 +240,22 @@ __device__ __forceinline__ void tile_butterflies_fixed(u64* sm, const u64* s_tw)
     reg_round<3, false, true, CA, CA - 3, CQ, CLE, CTH>(sm, s_tw, CA, CA - 3, CQ, CLE - 3);
 }
 
+// inverse order: the multiplication-free round first, then the generic rounds with descending stages, then the remainder round
+template <int CA, int CQ, int CLE, int CTH>
+__device__ __forceinline__ void tile_butterflies_fixed_inv(u64* sm, const u64* s_tw) {
+    constexpr int rem = CA % 3, full = CA / 3;
+    static_assert(full >= 1 && full <= 3, "shape");
+    reg_round<3, true, true, CA, CA - 3, CQ, CLE, CTH>(sm, s_tw, CA, CA - 3, CQ, CLE - 3);
+    if (full >= 2) reg_round<3, true, false, CA, CA - 6, CQ, CLE, CTH>(sm, s_tw, CA, CA - 6, CQ, CLE - 3);
+    if (full >= 3) reg_round<3, true, false, CA, CA - 9, CQ, CLE, CTH>(sm, s_tw, CA, CA - 9, CQ, CLE - 3);
+    if (rem == 2) reg_round<2, true, false, CA, 0, CQ, CLE, CTH>(sm, s_tw, CA, 0, CQ, CLE - 2);
+    else if (rem == 1) reg_round<1, true, false, CA, 0, CQ, CLE, CTH>(sm, s_tw, CA, 0, CQ, CLE - 1);
+}
+
 // Strided pass: tile [A][Q], element (m, qq) at column index blk*B + m*S + q0 + qq.  grid.x = tile * nz + coset: the cosets
 // of one coefficient tile are adjacent in launch order, so the tile is read from HBM once and from L2 seven times.
-template <bool INV, int RMAX>
+// CA / CQ / CTH > 0 (inverse passes of the hot plans): the butterflies run with compile-time shapes; fill and drain stay generic
+template <bool INV, int RMAX, int CA = 0, int CQ = 0, int CTH = 0>
 __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_strided(PassArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const int A = 1 << a.loga, Q = 1 << a.logq;
@@ -270,7 +283,8 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_strided(PassArg
         sm[phys(e)] = v;
     }
     stage_tw_end(A, mbar);
-    tile_butterflies<INV, RMAX>(sm, s_tw, a.loga, a.logq, a.loga + a.logq);
+    if (CA > 0 && INV) tile_butterflies_fixed_inv<CA ? CA : 3, CQ, CA + CQ, CTH>(sm, s_tw);
+    else tile_butterflies<INV, RMAX>(sm, s_tw, a.loga, a.logq, a.loga + a.logq);
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
         int qq = e & (Q - 1), m = e >> a.logq;
         size_t idx = base + ((size_t)m << logS) + qq;
@@ -285,7 +299,7 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_strided(PassArg
 }
 
 // Contiguous pass: tile = 2^logq consecutive blocks of A elements.
-template <bool INV, int RMAX>
+template <bool INV, int RMAX, int CA = 0, int CNB = 0, int CTH = 0>
 __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_contig(PassArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const int A = 1 << a.loga, NB = 1 << a.logq;
@@ -317,7 +331,8 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_contig(PassArgs
         }
     }
     stage_tw_end(A, mbar);
-    tile_butterflies<INV, RMAX>(sm, s_tw, a.loga, 0, a.loga + a.logq);
+    if (CA > 0 && INV) tile_butterflies_fixed_inv<CA ? CA : 3, 0, CA + CNB, CTH>(sm, s_tw);
+    else tile_butterflies<INV, RMAX>(sm, s_tw, a.loga, 0, a.loga + a.logq);
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
         int bb = e >> a.loga, m = e & (A - 1);
         u32 blk = (INV && a.gather) ? bitrev32(c0 + bb, lognb) : (c0 + bb);
@@ -511,6 +526,8 @@ void set_smem_attrs() {
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<6, 6, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<8, 4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig_fwd<11, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true, 3, 10, 3, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<true, 3, 10, 3, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_contig<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -643,7 +660,9 @@ void run_inverse(DevCtx* c, const XformDesc& d) {
             a.nz = d.nz;
             dim3 grid = make_grid(a, tiles * d.nz, d.ncols);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
-            if (ntt_rmax() == 4) k_pass_contig<true, 4><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
+            const bool fixed = ntt_fixed() && ntt_rmax() == 3 && th == 512;
+            if (fixed && a.loga == 10 && a.logq == 3) k_pass_contig<true, 3, 10, 3, 512><<<grid, 512, contig_smem(10, 3), c->stream>>>(a);
+            else if (ntt_rmax() == 4) k_pass_contig<true, 4><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
             else k_pass_contig<true, 3><<<grid, th, contig_smem(a.loga, a.logq), c->stream>>>(a);
         } else {
             a.logB = done + a.loga;
@@ -654,7 +673,9 @@ void run_inverse(DevCtx* c, const XformDesc& d) {
             a.nz = d.nz;
             dim3 grid = make_grid(a, tiles * d.nz, d.ncols);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
-            if (ntt_rmax() == 4) k_pass_strided<true, 4><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
+            const bool fixed = ntt_fixed() && ntt_rmax() == 3 && th == 512;
+            if (fixed && a.loga == 10 && a.logq == 3) k_pass_strided<true, 3, 10, 3, 512><<<grid, 512, strided_smem(10, 3), c->stream>>>(a);
+            else if (ntt_rmax() == 4) k_pass_strided<true, 4><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
             else k_pass_strided<true, 3><<<grid, th, strided_smem(a.loga, a.logq), c->stream>>>(a);
         }
         count_launch(c);
