@@ -112,9 +112,10 @@ def test_coset_ifft_leaforder_large_matches_oracle(p2g, corc, log_n):
     assert np.array_equal(p2g.lib.coset_ifft_leaforder(v), corc.coset_ifft_leaforder(v))
 
 
-@pytest.mark.parametrize("log_n,ncols", [(18, 2), (20, 2), (21, 1), (22, 1)])
+@pytest.mark.parametrize("log_n,ncols", [(17, 2), (18, 2), (19, 2), (20, 2), (21, 1), (22, 1)])
 def test_ifft_and_lde_large_match_oracle(p2g, corc, log_n, ncols):
-    """Inverse NTT + rate-8 coset LDE at the BASELINE row counts: every pass plan the prover uses."""
+    """Inverse NTT + rate-8 coset LDE at the BASELINE row counts and between them: every pass plan the prover uses, including every
+    compile-time-shaped kernel of ntt.cu (strided <5,7> <6,6> <7,5> <8,4> <9,3>, contiguous <11,1>, the inverse <10,3> pair)."""
     rng = np.random.default_rng(950 + log_n)
     v = rng.integers(0, P, size=(ncols, 1 << log_n), dtype=np.uint64)
     c = p2g.lib.ifft(v)
