@@ -25,7 +25,8 @@ METRIC = "proofs/sec on a 2^20-row ACIR circuit (ECDSA-shaped, 234 wires, Keccak
 UNIT = "proofs/s"
 # constants read off the committed ncu --set full captures (profiles/r1_summary.md section 3)
 NCU = {"lde_traffic_over_algorithmic": 6.26 / 2.265, "keccak_traffic_over_algorithmic": 15.98 / 15.70,
-       "lde_limiter": "integer ALU pipe 64-67% active, FMA pipe 21-22%, DRAM 1.08 TB/s: issue-bound 64-bit modular arithmetic, not HBM-bound",
+       "lde_limiter": "integer issue: 413 thread instructions per output element, issue slots 59-60% busy (ALU pipe 58-62%, FMA pipe 22-25%), DRAM 1.3 TB/s: "
+                      "64-bit modular arithmetic on 32-bit pipes, 59% of the issue roofline, not HBM-bound",
        "keccak_limiter": "integer ALU pipe 99.7% active (LOP3/SHF): at the hardware floor for Keccak-f",
        "quotient_dram_bytes": 65.5e9,
        "quotient_limiter": "integer issue: 84 k instructions per point in the limb sweep (8.1 k IMAD.WIDE), issue slots 55 % busy, DRAM 0.6-2.8 TB/s",
@@ -409,7 +410,7 @@ def main():
             # dominant stage of the step and the north-star's headline: the coset-LDE passes (NTT stage).  achieved = algorithmic
             # bytes (8N read + 64N written per column) / device time of those launches (CUDA events on the
             # library's stream); traffic = DRAM bytes actually moved, from the committed ncu --set full capture (2.73 x: two passes)
-            "roofline": {"kernel": "k_pass_strided + k_pass_contig (rate-8 coset LDE of the trace / Z / quotient columns: the NTT stage)",
+            "roofline": {"kernel": "k_pass_strided_fwd + k_pass_contig_fwd (rate-8 coset LDE of the trace / Z / quotient columns: the NTT stage)",
                          "bound": "hbm", "achieved": lde_gbs, "peak": hbm, "unit": "GB/s", "frac": lde_gbs / hbm,
                          "traffic": tms[0]["lde_bytes"] * NCU["lde_traffic_over_algorithmic"], "traffic_unit": "bytes per step",
                          "algorithmic_bytes_per_step": tms[0]["lde_bytes"], "peak_source": src,
