@@ -124,6 +124,48 @@ __device__ __forceinline__ u64 shl_by_index(u64 v, int, int h, int kk, bool inv)
 // stage.  Forward = decimation in frequency (stage order s0 .. s0+R-1), inverse = decimation in time (reverse order).
 // LAST: the round that ends the sub-transform (s0 + R == a).  Its twiddles are omega_{2h}^kk with 2h <= 2^R <= 16, i.e. the
 // compile-time powers of two 2^(96 kk / h): multiplication-free butterflies, no twiddle loads.
+// The R butterfly stages [s0, s0 + R) on the 2^R registers of one task (`lo` = the task's position inside the half-blocks of the
+// round's last stage, lo_bits its width): forward = decimation in frequency, inverse = decimation in time.
+template <int R, bool INV, bool LAST>
+__device__ __forceinline__ void reg_butterflies(u64 (&x)[1 << R], const u64* __restrict__ s_tw, int A, int s0, int lo_bits, int lo) {
+#pragma unroll
+    for (int ii = 0; ii < R; ii++) {
+        const int i = INV ? R - 1 - ii : ii;
+        const int h = 1 << (R - 1 - i);
+        const u64* tw = s_tw + (A - (A >> (s0 + i)));
+#pragma unroll
+        for (int kk = 0; kk < h; kk++) {
+            u64 w = 0;
+            if (!LAST) w = tw[(kk << lo_bits) | lo];
+#pragma unroll
+            for (int g = 0; g < (1 << R); g += 2 * h) {
+                u64 u = x[g + kk], v = x[g + kk + h];
+                if (LAST) {
+                    // forward: (u + v, (u - v) 2^S), S = 96 kk / h;  inverse: v 2^-S = -v 2^(96 - S)
+                    if (kk == 0) {
+                        x[g] = glf_add(u, v);
+                        x[g + h] = gl_sub(u, v);
+                    } else if (INV) {
+                        v = shl_by_index<R>(v, 0, h, kk, true);
+                        x[g + kk] = gl_sub(u, v);
+                        x[g + kk + h] = glf_add(u, v);
+                    } else {
+                        x[g + kk] = glf_add(u, v);
+                        x[g + kk + h] = shl_by_index<R>(gl_sub(u, v), 0, h, kk, false);
+                    }
+                } else if (INV) {
+                    v = glf_mul(v, w);
+                    x[g + kk] = glf_add(u, v);
+                    x[g + kk + h] = gl_sub(u, v);
+                } else {
+                    x[g + kk] = glf_add(u, v);
+                    x[g + kk + h] = glf_mul(gl_sub(u, v), w);
+                }
+            }
+        }
+    }
+}
+
 // CA / CS0 / CQ / CLE / CTH: the sub-transform length, first stage, run width, tile size and block size as compile-time constants (the hot
 // plans of the 2^20-row LDE are instantiated that way: every shift, mask and padded address below folds; ncu showed a third of a
 // round's instructions going into them).  A thread's 2^R elements sit `stride` apart in the tile; when stride is a multiple of 16
@@ -147,42 +189,7 @@ __device__ __forceinline__ void reg_round(u64* __restrict__ sm, const u64* __res
         u64 x[1 << R];
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) x[k] = sm[linear ? p0 + k * pstride : phys(e0 + k * stride)];
-#pragma unroll
-        for (int ii = 0; ii < R; ii++) {
-            const int i = INV ? R - 1 - ii : ii;
-            const int h = 1 << (R - 1 - i);
-            const u64* tw = s_tw + (A - (A >> (s0 + i)));
-#pragma unroll
-            for (int kk = 0; kk < h; kk++) {
-                u64 w = 0;
-                if (!LAST) w = tw[(kk << lo_bits) | lo];
-#pragma unroll
-                for (int g = 0; g < (1 << R); g += 2 * h) {
-                    u64 u = x[g + kk], v = x[g + kk + h];
-                    if (LAST) {
-                        // forward: (u + v, (u - v) 2^S), S = 96 kk / h;  inverse: v 2^-S = -v 2^(96 - S)
-                        if (kk == 0) {
-                            x[g] = glf_add(u, v);
-                            x[g + h] = gl_sub(u, v);
-                        } else if (INV) {
-                            v = shl_by_index<R>(v, 0, h, kk, true);
-                            x[g + kk] = gl_sub(u, v);
-                            x[g + kk + h] = glf_add(u, v);
-                        } else {
-                            x[g + kk] = glf_add(u, v);
-                            x[g + kk + h] = shl_by_index<R>(gl_sub(u, v), 0, h, kk, false);
-                        }
-                    } else if (INV) {
-                        v = glf_mul(v, w);
-                        x[g + kk] = glf_add(u, v);
-                        x[g + kk + h] = gl_sub(u, v);
-                    } else {
-                        x[g + kk] = glf_add(u, v);
-                        x[g + kk + h] = glf_mul(gl_sub(u, v), w);
-                    }
-                }
-            }
-        }
+        reg_butterflies<R, INV, LAST>(x, s_tw, A, s0, lo_bits, lo);
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) sm[linear ? p0 + k * pstride : phys(e0 + k * stride)] = x[k];
     }
@@ -350,11 +357,14 @@ __global__ void __launch_bounds__(512, RMAX == 4 ? 1 : 2) k_pass_contig(PassArgs
 // Same data movement and arithmetic as k_pass_strided<false> / k_pass_contig<false>; tile size, sub-transform length, run width and
 // block size are template constants, so the fill / drain loops are fully unrolled with constant strides and the register rounds'
 // index arithmetic folds (ncu source page of the generic kernels: ~35 % of a round's instructions were address arithmetic).
+// The first register round runs on the elements a thread has just loaded (its EPT fill elements ARE whole tasks of that round) and
+// the last one on the elements it is about to store: two of the tile's shared-memory round trips and their barriers disappear.
 template <int CA, int CQ, int CTH>
 __global__ void __launch_bounds__(CTH, 1024 / CTH) k_pass_strided_fwd(PassArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int A = 1 << CA, Q = 1 << CQ, total = A << CQ, EPT = total / CTH, MSTEP = CTH >> CQ, PSTEP = CTH + (CTH >> 4);
-    static_assert(CTH % Q == 0 && CTH % 16 == 0 && total % CTH == 0 && EPT % 4 == 0, "shape");
+    constexpr int R0 = (CA % 3 == 0) ? 3 : CA % 3, NT = EPT >> R0, MID = (CA - R0 - 3) / 3;   // first round, its tasks per thread, middle rounds
+    static_assert(CTH % Q == 0 && CTH % 16 == 0 && total % CTH == 0 && EPT >= 8 && CA >= R0 + 3 && (CA - R0) % 3 == 0 && MID <= 1, "shape");
     const int logS = a.logB - CA;
     u64* s_tw = sm + tile_words(total);
     u64* mbar = s_tw + A;
@@ -367,42 +377,54 @@ __global__ void __launch_bounds__(CTH, 1024 / CTH) k_pass_strided_fwd(PassArgs a
     u64* out = a.out + (size_t)col * a.out_cs + (size_t)z * a.out_zs;
     const u64* stab = a.stab ? a.stab + (size_t)z * a.stab_zs : nullptr;
     const int tid = threadIdx.x, qq = tid & (Q - 1), m0 = tid >> CQ, p0 = phys(tid);
-    // element i of this thread: tile index e = tid + i CTH -> (m0 + i MSTEP, qq); column index idx0 + i * istep
+    // fill element i of this thread: tile index e = tid + i CTH -> (m0 + i MSTEP, qq); column index idx0 + i * istep
     const size_t idx0 = ((size_t)blk << a.logB) + q0 + ((size_t)m0 << logS) + qq, istep = (size_t)MSTEP << logS;
 
     stage_tw_begin(s_tw, a.tw, A, mbar);
+    // fill + first round: task t of this thread = elements i = t + k NT (m = m0 + t MSTEP + k A / 2^R0)
 #pragma unroll
-    for (int i0 = 0; i0 < EPT; i0 += 4) {
-        u64 v[4], sc[4];
+    for (int t = 0; t < NT; t++) {
+        u64 x[1 << R0], sc[1 << R0];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            v[i] = in[idx0 + (i0 + i) * istep];
-            sc[i] = stab ? __ldg(stab + idx0 + (i0 + i) * istep) : 1;
+        for (int k = 0; k < (1 << R0); k++) {
+            x[k] = in[idx0 + (t + k * NT) * istep];
+            sc[k] = stab ? __ldg(stab + idx0 + (t + k * NT) * istep) : 1;
         }
+        if (stab) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) sm[p0 + (i0 + i) * PSTEP] = stab ? glf_mul(v[i], sc[i]) : v[i];
+            for (int k = 0; k < (1 << R0); k++) x[k] = glf_mul(x[k], sc[k]);
+        }
+        if (t == 0) stage_tw_end(A, mbar);   // the twiddle tile (TMA) has landed; every thread passes here exactly once
+        reg_butterflies<R0, false, false>(x, s_tw, A, 0, CA - R0, m0 + t * MSTEP);
+#pragma unroll
+        for (int k = 0; k < (1 << R0); k++) sm[p0 + (t + k * NT) * PSTEP] = x[k];
     }
-    stage_tw_end(A, mbar);
-    tile_butterflies_fixed<CA, CQ, CA + CQ, CTH>(sm, s_tw);
-    const u64* twist = a.twist ? a.twist + ((size_t)m0 << logS) + q0 + qq : nullptr;
+    __syncthreads();
+    if (MID == 1) reg_round<3, false, false, CA, R0, CQ, CA + CQ, CTH>(sm, s_tw, CA, R0, CQ, CA + CQ - 3);
+    // last round (multiplication-free twiddles) + twist + drain: task = 8 consecutive m at one qq
+    const u64* twist = a.twist ? a.twist + q0 + qq : nullptr;
+    u64* o = out + ((size_t)blk << a.logB) + q0 + qq;
 #pragma unroll
-    for (int i0 = 0; i0 < EPT; i0 += 4) {
-        u64 v[4], tw[4];
+    for (int j = 0; j < EPT / 8; j++) {
+        const int base_m = (m0 + j * MSTEP) << 3;
+        u64 x[8], tw[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            v[i] = sm[p0 + (i0 + i) * PSTEP];
-            tw[i] = twist ? __ldg(twist + (i0 + i) * istep) : 1;
+        for (int k = 0; k < 8; k++) {
+            x[k] = sm[phys(((base_m + k) << CQ) | qq)];
+            tw[k] = twist ? __ldg(twist + ((size_t)(base_m + k) << logS)) : 1;
         }
+        reg_butterflies<3, false, true>(x, s_tw, A, CA - 3, 0, 0);
 #pragma unroll
-        for (int i = 0; i < 4; i++) out[idx0 + (i0 + i) * istep] = twist ? glf_mul(v[i], tw[i]) : v[i];
+        for (int k = 0; k < 8; k++) o[(size_t)(base_m + k) << logS] = twist ? glf_mul(x[k], tw[k]) : x[k];
     }
 }
 
 template <int CA, int CNB, int CTH>
 __global__ void __launch_bounds__(CTH, 1024 / CTH) k_pass_contig_fwd(PassArgs a) {
     extern __shared__ __align__(16) u64 sm[];
-    constexpr int A = 1 << CA, total = A << CNB, EPT = total / CTH, PSTEP = CTH + (CTH >> 4);
-    static_assert(CTH % 16 == 0 && total % CTH == 0 && EPT % 4 == 0, "shape");
+    constexpr int A = 1 << CA, total = A << CNB, EPT = total / CTH, EPB = EPT >> CNB, PSTEP = CTH + (CTH >> 4);
+    constexpr int R0 = (CA % 3 == 0) ? 3 : CA % 3, NTB = EPB >> R0, MID = (CA - R0 - 3) / 3;
+    static_assert(CTH % 16 == 0 && total % CTH == 0 && A % CTH == 0 && EPB >= (1 << R0) && (CA - R0) % 3 == 0 && MID >= 0 && MID <= 2, "shape");
     u64* s_tw = sm + tile_words(total);
     u64* mbar = s_tw + A;
     const u32 col = a.col_fast ? blockIdx.x : blockIdx.y, tz = a.col_fast ? blockIdx.y : blockIdx.x;
@@ -414,26 +436,37 @@ __global__ void __launch_bounds__(CTH, 1024 / CTH) k_pass_contig_fwd(PassArgs a)
     const size_t idx0 = ((size_t)tile << (CA + CNB)) + tid;
 
     stage_tw_begin(s_tw, a.tw, A, mbar);
+    // fill + first round: fill element i = tid + i CTH lies in block bb = i / EPB at m = tid + (i % EPB) CTH; task (bb, t) = the
+    // elements i = bb EPB + t + k NTB, i.e. m = (tid + t CTH) + k A / 2^R0
 #pragma unroll
-    for (int i0 = 0; i0 < EPT; i0 += 4) {
-        u64 v[4];
+    for (int bt = 0; bt < (NTB << CNB); bt++) {
+        const int bb = bt / NTB, t = bt % NTB;
+        u64 x[1 << R0];
 #pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = in[idx0 + (size_t)(i0 + i) * CTH];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (stab) v[i] = glf_mul(v[i], __ldg(stab + idx0 + (size_t)(i0 + i) * CTH));   // single-pass plans only
-            sm[p0 + (i0 + i) * PSTEP] = v[i];
+        for (int k = 0; k < (1 << R0); k++) {
+            const int i = bb * EPB + t + k * NTB;
+            x[k] = in[idx0 + (size_t)i * CTH];
+            if (stab) x[k] = glf_mul(x[k], __ldg(stab + idx0 + (size_t)i * CTH));   // single-pass plans only
         }
+        if (bt == 0) stage_tw_end(A, mbar);
+        reg_butterflies<R0, false, false>(x, s_tw, A, 0, CA - R0, tid + t * CTH);
+#pragma unroll
+        for (int k = 0; k < (1 << R0); k++) sm[p0 + (bb * EPB + t + k * NTB) * PSTEP] = x[k];
     }
-    stage_tw_end(A, mbar);
-    tile_butterflies_fixed<CA, 0, CA + CNB, CTH>(sm, s_tw);
+    __syncthreads();
+    if (MID >= 1) reg_round<3, false, false, CA, R0, 0, CA + CNB, CTH>(sm, s_tw, CA, R0, 0, CA + CNB - 3);
+    if (MID >= 2) reg_round<3, false, false, CA, R0 + 3, 0, CA + CNB, CTH>(sm, s_tw, CA, R0 + 3, 0, CA + CNB - 3);
+    // last round + drain: task = 8 consecutive elements, written as one 64-byte run
 #pragma unroll
-    for (int i0 = 0; i0 < EPT; i0 += 4) {
-        u64 v[4];
+    for (int j = 0; j < EPT / 8; j++) {
+        const int e0 = (tid + j * CTH) << 3, pe = e0 + (e0 >> 4);
+        u64 x[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = sm[p0 + (i0 + i) * PSTEP];
+        for (int k = 0; k < 8; k++) x[k] = sm[pe + k];
+        reg_butterflies<3, false, true>(x, s_tw, A, CA - 3, 0, 0);
+        ulonglong2* o = reinterpret_cast<ulonglong2*>(out + ((size_t)tile << (CA + CNB)) + e0);
 #pragma unroll
-        for (int i = 0; i < 4; i++) out[idx0 + (size_t)(i0 + i) * CTH] = v[i];
+        for (int k = 0; k < 8; k += 2) o[k >> 1] = make_ulonglong2(x[k], x[k + 1]);
     }
 }
 
