@@ -40,6 +40,11 @@ def _synth_lib():
     return _SYNTH
 
 
+def set_threads(n):
+    """OpenMP threads of the generator (torchrun pins OMP_NUM_THREADS=1 for its workers)."""
+    _synth_lib().p2s_set_threads(int(n))
+
+
 def gate_mix(name, cfg):
     """[(Gate, weight)] for a named workload; weights are row fractions of the non-padding rows."""
     A = Gate.arithmetic(cfg)

@@ -311,6 +311,9 @@ void fill_outputs(Ctx& c, size_t row) {
 
 }  // namespace
 
+// torchrun pins OMP_NUM_THREADS=1 for its workers; the generator may use its share of the host cores anyway
+extern "C" void p2s_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
+
 extern "C" int p2s_synthesize(const p2s_spec* s, uint64_t* constants_sigmas, uint64_t* wires, uint64_t* public_inputs) {
     if (!s || !constants_sigmas || !wires || !s->gates || !s->row_gate) return -1;
     Ctx c;

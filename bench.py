@@ -264,6 +264,8 @@ def main():
         torch.cuda.synchronize()
 
     cfg = p2g.CircuitConfig.wide_ecc_config(hasher=args.hasher)
+    if world > 1:   # input generation (untimed): this rank's share of the host cores, not torchrun's OMP_NUM_THREADS=1
+        p2g.synth.set_threads(max(1, (os.cpu_count() or world) // world))
     sc = p2g.synth.SyntheticCircuit(args.degree_bits, args.workload, config=cfg, num_public_inputs=4,
                                     seed=0xAC1D + 3 + 1000 * rank, pinned=True)
     # circuit build: once, outside the timing.  `inflight` handles = proofs in flight on this GPU (own stream + host thread each)
