@@ -133,16 +133,6 @@ struct Builder {
     }
     Target zero() { return constant(0); }
     Target one() { return constant(1); }
-    bool is_const(Target t, u64* v) {
-        Target r = find(t);
-        for (auto& kv : constants)
-            if (find(kv.second) == r) {
-                *v = kv.first;
-                return true;
-            }
-        return false;
-    }
-
     // ---- arithmetic: c0 * x * y + c1 * z   (gadgets/arithmetic.rs arithmetic / add_base_arithmetic_operation)
     Target arithmetic(u64 c0, u64 c1, Target x, Target y, Target z) {
         auto key = std::make_tuple(c0, c1, find(x), find(y), find(z));

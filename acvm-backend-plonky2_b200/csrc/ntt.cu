@@ -234,19 +234,6 @@ __device__ __forceinline__ void tile_butterflies(u64* sm, const u64* s_tw, int a
     }
 }
 
-// The same for a compile-time shape (forward only, RMAX = 3): the round sequence of tile_butterflies unrolled with constant stages.
-template <int CA, int CQ, int CLE, int CTH>
-__device__ __forceinline__ void tile_butterflies_fixed(u64* sm, const u64* s_tw) {
-    constexpr int rem = CA % 3, full = CA / 3;
-    static_assert(full >= 1, "fixed shapes have at least one full round");
-    if (rem == 2) reg_round<2, false, false, CA, 0, CQ, CLE, CTH>(sm, s_tw, CA, 0, CQ, CLE - 2);
-    else if (rem == 1) reg_round<1, false, false, CA, 0, CQ, CLE, CTH>(sm, s_tw, CA, 0, CQ, CLE - 1);
-    if (full >= 2) reg_round<3, false, false, CA, rem, CQ, CLE, CTH>(sm, s_tw, CA, rem, CQ, CLE - 3);
-    if (full >= 3) reg_round<3, false, false, CA, rem + 3, CQ, CLE, CTH>(sm, s_tw, CA, rem + 3, CQ, CLE - 3);
-    static_assert(full <= 3, "add a round");
-    reg_round<3, false, true, CA, CA - 3, CQ, CLE, CTH>(sm, s_tw, CA, CA - 3, CQ, CLE - 3);
-}
-
 // inverse order: the multiplication-free round first, then the generic rounds with descending stages, then the remainder round
 template <int CA, int CQ, int CLE, int CTH>
 __device__ __forceinline__ void tile_butterflies_fixed_inv(u64* sm, const u64* s_tw) {

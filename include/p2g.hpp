@@ -247,7 +247,11 @@ class CircuitData {
     std::vector<uint8_t> circuit_digest;                       // verifier_only.circuit_digest
 
     // constants_sigmas: values on the subgroup, column-major [num_preprocessed][N]: selectors, gate constants, sigmas
-    CircuitData(const CommonCircuitData& c, const uint64_t* constants_sigmas, int device = 0) : common(c) {
+    // rank / world / nccl_id: this handle is one rank of a coset-sharded prover whose NCCL communicator lives inside the library
+    // (p2g_circuit_create_sharded_nccl; nccl_id = the P2G_NCCL_UNIQUE_ID_BYTES from p2g_nccl_unique_id() on rank 0); world = 1: one GPU.
+    CircuitData(const CommonCircuitData& c, const uint64_t* constants_sigmas, int device = 0, int rank = 0, int world = 1,
+                const uint8_t* nccl_id = nullptr)
+        : common(c) {
         std::vector<p2g_gate> table = common.gate_table();
         p2g_circuit_desc d{};
         d.struct_size = (uint32_t)sizeof d;
@@ -273,7 +277,7 @@ class CircuitData {
         d.constants_sigmas = constants_sigmas;
         d.k_is = common.k_is.data();
         d.circuit_digest = nullptr;
-        check(p2g_circuit_create(&d, device, &h_));
+        check(world > 1 ? p2g_circuit_create_sharded_nccl(&d, device, rank, world, nccl_id, &h_) : p2g_circuit_create(&d, device, &h_));
         const size_t hs = common.hash_size();
         const size_t ncap = (size_t)1 << std::min<uint32_t>(common.config.cap_height, common.degree_bits + common.config.rate_bits);
         std::vector<uint8_t> cap(ncap * hs);
