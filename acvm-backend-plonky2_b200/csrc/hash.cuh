@@ -246,30 +246,35 @@ GL_HD void poseidon_mds(u64 (&s)[12]) {
 
 GL_HD void poseidon_permute(u64 (&s)[12]) {
 #if defined(__CUDA_ARCH__)
+    // One loop body for all 30 rounds (a uniform branch skips the 11 extra S-boxes of the partial rounds): with three bodies -- full,
+    // partial, full, 31 + 16 + 31 KB of SASS -- ncu showed the leaf kernel stalled on instruction fetch (no_instruction 8.3 cycles per
+    // issue, issue slots 47 % busy): warps at different rounds thrash the instruction cache.  Same arithmetic, a third of the code.
 #pragma unroll 1
-#endif
-    for (int r = 0; r < 4; r++) {
+    for (int r = 0; r < 30; r++) {
 #pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_RC(12 * r + i));
+        s[0] = poseidon_sbox(s[0]);
+        if (r < 4 || r >= 26) {
+#pragma unroll
+            for (int i = 1; i < 12; i++) s[i] = poseidon_sbox(s[i]);
+        }
+        poseidon_mds(s);
+    }
+#else
+    for (int r = 0; r < 4; r++) {
         for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(gl_add(s[i], POSEIDON_RC(12 * r + i)));
         poseidon_mds(s);
     }
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
     for (int r = 4; r < 26; r++) {
-#pragma unroll
         for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_RC(12 * r + i));
         s[0] = poseidon_sbox(s[0]);
         poseidon_mds(s);
     }
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
     for (int r = 26; r < 30; r++) {
-#pragma unroll
         for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(gl_add(s[i], POSEIDON_RC(12 * r + i)));
         poseidon_mds(s);
     }
+#endif
 }
 
 GL_HD digest_t poseidon_two_to_one(const digest_t& l, const digest_t& r) {

@@ -73,17 +73,13 @@ __global__ void __launch_bounds__(128) k_leaf_poseidon(const u64* __restrict__ i
     u64 s[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = 0;
-    int base = 0;
-    for (; base + 8 <= ncols; base += 8) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = leaf_elem<FRI>(in, cs, ncols, j, base + i);
-        poseidon_permute(s);
-    }
-    int rem = ncols - base;
-    if (rem) {
+    // one instance of the permutation: the last (partial) chunk overwrites only the lanes it has (overwrite-mode sponge)
+#pragma unroll 1
+    for (int base = 0; base < ncols; base += 8) {
+        const int have = ncols - base;
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            if (i < rem) s[i] = leaf_elem<FRI>(in, cs, ncols, j, base + i);
+            if (i < have) s[i] = leaf_elem<FRI>(in, cs, ncols, j, base + i);
         poseidon_permute(s);
     }
 #pragma unroll
