@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(CTH, 1024 / CTH) k_pass_strided_fwd(PassArgs a
     extern __shared__ __align__(16) u64 sm[];
     constexpr int A = 1 << CA, Q = 1 << CQ, total = A << CQ, EPT = total / CTH, MSTEP = CTH >> CQ, PSTEP = CTH + (CTH >> 4);
     constexpr int R0 = (CA % 3 == 0) ? 3 : CA % 3, NT = EPT >> R0, MID = (CA - R0 - 3) / 3;   // first round, its tasks per thread, middle rounds
-    static_assert(CTH % Q == 0 && CTH % 16 == 0 && total % CTH == 0 && EPT >= 8 && CA >= R0 + 3 && (CA - R0) % 3 == 0 && MID <= 1, "shape");
+    static_assert(CTH % Q == 0 && CTH % 16 == 0 && total % CTH == 0 && EPT >= 8 && CA >= R0 + 3 && (CA - R0) % 3 == 0 && MID <= 2, "shape");
     const int logS = a.logB - CA;
     u64* s_tw = sm + tile_words(total);
     u64* mbar = s_tw + A;
@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(CTH, 1024 / CTH) k_pass_strided_fwd(PassArgs a
         for (int k = 0; k < (1 << R0); k++) sm[p0 + (t + k * NT) * PSTEP] = x[k];
     }
     __syncthreads();
-    if (MID == 1) reg_round<3, false, false, CA, R0, CQ, CA + CQ, CTH>(sm, s_tw, CA, R0, CQ, CA + CQ - 3);
+    if (MID >= 1) reg_round<3, false, false, CA, R0, CQ, CA + CQ, CTH>(sm, s_tw, CA, R0, CQ, CA + CQ - 3);
+    if (MID >= 2) reg_round<3, false, false, CA, R0 + 3, CQ, CA + CQ, CTH>(sm, s_tw, CA, R0 + 3, CQ, CA + CQ - 3);
     // last round (multiplication-free twiddles) + twist + drain: task = 8 consecutive m at one qq
     const u64* twist = a.twist ? a.twist + q0 + qq : nullptr;
     u64* o = out + ((size_t)blk << a.logB) + q0 + qq;
@@ -514,6 +515,13 @@ std::vector<int> make_plan(int logn, bool inverse = false) {
         plan.push_back(logn);
         return plan;
     }
+    // 2^22 forward (configs[4]): two passes 2^11 x 2^11 -- a 16 K-element strided tile (139 KB of shared memory, one 1024-thread block
+    // per SM) -- instead of three passes over HBM
+    if (!inverse && logn == 22 && ntt_fixed() && ntt_rmax() == 3 && !getenv("P2G_NTT_NO_BIG_TILE")) {
+        plan.push_back(11);
+        plan.push_back(11);
+        return plan;
+    }
     // the inverse transform's contiguous pass gathers 8 blocks per tile (64-byte runs of the natural-order input), so its
     // sub-transform is kept at 2^10 to stay at two resident tiles per SM
     int last = inverse ? std::min(10, ntt_last_log()) : std::min(ntt_last_log(), MAX_CONTIG_LOG);
@@ -541,6 +549,7 @@ void set_smem_attrs() {
     devs.push_back(dev);
     const int lim = 160 * 1024;
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<9, 3, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<11, 3, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<7, 5, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<5, 7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CUDA_CHECK(cudaFuncSetAttribute(k_pass_strided_fwd<6, 6, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -614,13 +623,15 @@ void run_forward(DevCtx* c, const XformDesc& d) {
             a.logB = d.logn - done;
             int logS = a.logB - a.loga;
             a.logq = std::min(logS, std::max(3, ntt_tile_log() - a.loga));
+            const bool big_tile = a.loga == 11 && a.logq == 3 && ntt_fixed() && ntt_rmax() == 3;
             a.twist = c->get_twist_full(a.logB, a.loga, false);
             size_t tiles = (size_t)1 << (d.logn - a.loga - a.logq);
             a.nz = d.nz;
             dim3 grid = make_grid(a, tiles * d.nz, d.ncols);
             int th = pick_threads((size_t)1 << (a.loga + a.logq));
             const bool fixed = ntt_fixed() && ntt_rmax() == 3 && th == 256 && a.scale == 1;
-            if (fixed && a.loga == 9 && a.logq == 3) k_pass_strided_fwd<9, 3, 256><<<grid, 256, strided_smem(9, 3), c->stream>>>(a);
+            if (big_tile) k_pass_strided_fwd<11, 3, 1024><<<grid, 1024, strided_smem(11, 3), c->stream>>>(a);
+            else if (fixed && a.loga == 9 && a.logq == 3) k_pass_strided_fwd<9, 3, 256><<<grid, 256, strided_smem(9, 3), c->stream>>>(a);
             else if (fixed && a.loga == 7 && a.logq == 5) k_pass_strided_fwd<7, 5, 256><<<grid, 256, strided_smem(7, 5), c->stream>>>(a);
             else if (fixed && a.loga == 5 && a.logq == 7) k_pass_strided_fwd<5, 7, 256><<<grid, 256, strided_smem(5, 7), c->stream>>>(a);
             else if (fixed && a.loga == 6 && a.logq == 6) k_pass_strided_fwd<6, 6, 256><<<grid, 256, strided_smem(6, 6), c->stream>>>(a);
