@@ -110,6 +110,47 @@ class Sha256Compression:   # BlackBoxFuncCall::Sha256Compression { inputs: [_; 1
     outputs: list
 
 
+# ---- gadget-level operations (not ACIR opcodes): the reference's u32 gadgets, plonky2_ecdsa/biguint/gadgets/*.rs, over its custom
+# gates.  The reference reaches them only through its EcdsaSecp256k1 translator; here a circuit can be built on them directly, the
+# way the reference's gadget tests do.  Witness indices name the targets; outputs are computed by the gates' generators.
+@dataclass
+class MulAddU32:      # x * y + z = low + 2^32 high           (U32ArithmeticGate)
+    x: int
+    y: int
+    z: int
+    low: int
+    high: int
+
+
+@dataclass
+class AddManyU32:     # sum(addends) = result + 2^32 carry     (U32AddManyGate; 2 addends -> U32ArithmeticGate)
+    addends: list
+    result: int
+    carry: int
+
+
+@dataclass
+class SubU32:         # x - y - borrow = result - 2^32 borrow_out   (U32SubtractionGate)
+    x: int
+    y: int
+    borrow: int
+    result: int
+    borrow_out: int
+
+
+@dataclass
+class RangeCheckU32:  # every value < 2^32                      (U32RangeCheckGate)
+    values: list
+
+
+@dataclass
+class CmpLe:          # result = (a <= b) on num_bits-bit values  (ComparisonGate, 2-bit chunks)
+    a: int
+    b: int
+    num_bits: int
+    result: int
+
+
 @dataclass
 class Circuit:
     opcodes: list
@@ -139,6 +180,16 @@ def _encode(circuit):
             words += [6, op.block_id, op.index, op.value]
         elif isinstance(op, MemoryWrite):
             words += [8, op.block_id, op.index, op.value]
+        elif isinstance(op, MulAddU32):
+            words += [101, op.x, op.y, op.z, op.low, op.high]
+        elif isinstance(op, AddManyU32):
+            words += [102, len(op.addends)] + list(op.addends) + [op.result, op.carry]
+        elif isinstance(op, SubU32):
+            words += [103, op.x, op.y, op.borrow, op.result, op.borrow_out]
+        elif isinstance(op, RangeCheckU32):
+            words += [104, len(op.values)] + list(op.values)
+        elif isinstance(op, CmpLe):
+            words += [105, op.a, op.b, op.num_bits, op.result]
         elif isinstance(op, Sha256Compression):
             if (len(op.inputs), len(op.hash_values), len(op.outputs)) != (16, 8, 8):
                 raise TranslationError("Sha256Compression takes 16 inputs, 8 hash values and 8 outputs")

@@ -47,7 +47,8 @@ struct Row {
     std::vector<u64> consts;  // gate-local constants
 };
 
-enum GenKind { GEN_ARITH, GEN_CONST, GEN_SPLIT, GEN_BASE_SPLIT, GEN_BASE_SUM, GEN_RANDOM_ACCESS, GEN_POSEIDON, GEN_EQUAL };
+enum GenKind { GEN_ARITH, GEN_CONST, GEN_SPLIT, GEN_BASE_SPLIT, GEN_BASE_SUM, GEN_RANDOM_ACCESS, GEN_POSEIDON, GEN_EQUAL,
+               GEN_U32_ARITH, GEN_U32_ADD_MANY, GEN_U32_SUB, GEN_U32_RANGE, GEN_COMPARISON };
 struct Gen {
     GenKind kind;
     int row, i;         // gate row, op / copy index
@@ -77,6 +78,8 @@ struct Builder {
     std::map<std::tuple<u64, u64>, std::pair<int, int>> free_arith;   // (c0, c1) -> (row, next op)
     std::map<std::tuple<u64, u64, Target, Target, Target>, Target> arith_cache;
     std::map<int, std::pair<int, int>> free_ra;      // bits -> (row, next copy)
+    std::pair<int, int> free_u32_arith = {0, 0}, free_u32_sub = {0, 0};   // (row, next op)
+    std::map<int, std::pair<int, int>> free_add_many;                     // num_addends -> (row, next op)
     std::vector<Target> public_inputs;
     std::vector<Gen> gens;
     bool built = false;
@@ -274,6 +277,100 @@ struct Builder {
         gens.push_back(g);
         return wire(row, base + 1);
     }
+    // ---- the reference's u32 gadgets (plonky2-backend/src/plonky2_ecdsa/biguint/gadgets/{arithmetic_u32,range_check,multiple_comparison}.rs)
+    // over its custom gates; gate shapes from `new_from_config` with wide_ecc_config (234 wires, 80 routed)
+    static int u32_arith_ops() { return std::min(NUM_WIRES / 38, NUM_ROUTED / 6); }                       // arithmetic_u32.rs:40-43
+    static int u32_sub_ops() { return std::min(NUM_WIRES / 21, NUM_ROUTED / 5); }                         // subtraction_u32.rs:38-42
+    static int add_many_ops(int na) { return std::min(NUM_WIRES / (na + 21), NUM_ROUTED / (na + 3)); }    // add_many_u32.rs:43-48
+    // x * y + z = low + 2^32 high
+    std::pair<Target, Target> mul_add_u32(Target x, Target y, Target z) {
+        const int ops = u32_arith_ops();
+        auto& slot = free_u32_arith;
+        if (slot.second == 0 || slot.second >= ops) {
+            slot.first = add_gate(gate_type(P2G_GATE_U32_ARITHMETIC, ops));
+            slot.second = 0;
+        }
+        const int row = slot.first, i = slot.second++;
+        connect(x, wire(row, 6 * i));
+        connect(y, wire(row, 6 * i + 1));
+        connect(z, wire(row, 6 * i + 2));
+        Gen g = {};
+        g.kind = GEN_U32_ARITH;
+        g.row = row;
+        g.i = i;
+        g.n = ops;
+        gens.push_back(g);
+        return {wire(row, 6 * i + 3), wire(row, 6 * i + 4)};
+    }
+    std::pair<Target, Target> add_u32(Target a, Target b) { return mul_add_u32(a, one(), b); }
+    // sum of the addends = result + 2^32 carry  (arithmetic_u32.rs gadget add_many_u32: 0 / 1 / 2 addends are special-cased)
+    std::pair<Target, Target> add_many_u32(const std::vector<Target>& v) {
+        if (v.empty()) return {zero(), zero()};
+        if (v.size() == 1) return {v[0], zero()};
+        if (v.size() == 2) return add_u32(v[0], v[1]);
+        const int na = (int)v.size();
+        if (na > 16) throw Error{"add_many_u32: more than 16 addends"};
+        const int ops = add_many_ops(na);
+        auto& slot = free_add_many[na];
+        if (slot.second == 0 || slot.second >= ops) {
+            slot.first = add_gate(gate_type(P2G_GATE_U32_ADD_MANY, na, ops));
+            slot.second = 0;
+        }
+        const int row = slot.first, i = slot.second++, q = (na + 3) * i;
+        for (int j = 0; j < na; j++) connect(v[j], wire(row, q + j));
+        connect(zero(), wire(row, q + na));   // carry in
+        Gen g = {};
+        g.kind = GEN_U32_ADD_MANY;
+        g.row = row;
+        g.i = i;
+        g.n = na;
+        g.c0 = ops;
+        gens.push_back(g);
+        return {wire(row, q + na + 1), wire(row, q + na + 2)};
+    }
+    // x - y - borrow = result - 2^32 borrow_out
+    std::pair<Target, Target> sub_u32(Target x, Target y, Target borrow) {
+        const int ops = u32_sub_ops();
+        auto& slot = free_u32_sub;
+        if (slot.second == 0 || slot.second >= ops) {
+            slot.first = add_gate(gate_type(P2G_GATE_U32_SUBTRACTION, ops));
+            slot.second = 0;
+        }
+        const int row = slot.first, i = slot.second++;
+        connect(x, wire(row, 5 * i));
+        connect(y, wire(row, 5 * i + 1));
+        connect(borrow, wire(row, 5 * i + 2));
+        Gen g = {};
+        g.kind = GEN_U32_SUB;
+        g.row = row;
+        g.i = i;
+        g.n = ops;
+        gens.push_back(g);
+        return {wire(row, 5 * i + 3), wire(row, 5 * i + 4)};
+    }
+    void range_check_u32(const std::vector<Target>& vals) {   // range_check.rs: one U32RangeCheckGate for the whole vector
+        if (vals.empty()) return;
+        if (vals.size() > 13) throw Error{"range_check_u32: more than 13 values in one gate"};
+        const int n = (int)vals.size(), row = add_gate(gate_type(P2G_GATE_U32_RANGE_CHECK, n));
+        for (int i = 0; i < n; i++) connect(vals[i], wire(row, i));
+        Gen g = {};
+        g.kind = GEN_U32_RANGE;
+        g.row = row;
+        g.n = n;
+        gens.push_back(g);
+    }
+    Target cmp_le(Target a, Target b, int num_bits) {   // multiple_comparison.rs list_le_circuit for one pair: ComparisonGate, 2-bit chunks
+        const int nc = (num_bits + 1) / 2, row = add_gate(gate_type(P2G_GATE_COMPARISON, num_bits, nc));
+        connect(a, wire(row, 0));
+        connect(b, wire(row, 1));
+        Gen g = {};
+        g.kind = GEN_COMPARISON;
+        g.row = row;
+        g.n = num_bits;
+        g.i = nc;
+        gens.push_back(g);
+        return wire(row, 2);
+    }
     void register_public_input(Target t) { public_inputs.push_back(t); }
 
     // ---- build(): public-input hash, constants, unused gate slots, padding (plonk/circuit_builder.rs build)
@@ -409,6 +506,77 @@ struct Builder {
             if (!get(g.t, &x) || !get(g.t2, &y)) return false;
             set(g.t3, x == y ? 1 : 0);
             set(g.t4, x == y ? 0 : gl_inv(gl_sub(x, y)));
+            return true;
+        }
+        case GEN_U32_ARITH: {   // arithmetic_u32.rs:376-426
+            u64 x, y, z;
+            if (!get(wire(g.row, 6 * g.i), &x) || !get(wire(g.row, 6 * g.i + 1), &y) || !get(wire(g.row, 6 * g.i + 2), &z)) return false;
+            u64 out = gl_add(gl_mul(x, y), z), hi = out >> 32, lo = out & 0xFFFFFFFFULL;
+            set(wire(g.row, 6 * g.i + 3), lo);
+            set(wire(g.row, 6 * g.i + 4), hi);
+            const u64 diff = 0xFFFFFFFFULL - hi;
+            set(wire(g.row, 6 * g.i + 5), diff ? gl_inv(diff) : 0);
+            for (int j = 0; j < 32; j++) set(wire(g.row, 6 * g.n + 32 * g.i + j), (out >> (2 * j)) & 3);
+            return true;
+        }
+        case GEN_U32_ADD_MANY: {   // add_many_u32.rs:329-375
+            const int na = g.n, ops = (int)g.c0, q = (na + 3) * g.i;
+            u64 sum = 0, v;
+            for (int j = 0; j <= na; j++) {
+                if (!get(wire(g.row, q + j), &v)) return false;
+                sum = gl_add(sum, v);
+            }
+            const u64 carry = sum >> 32, res = sum & 0xFFFFFFFFULL;
+            set(wire(g.row, q + na + 1), res);
+            set(wire(g.row, q + na + 2), carry);
+            const int lw = (na + 3) * ops + 18 * g.i;
+            for (int j = 0; j < 16; j++) set(wire(g.row, lw + j), (res >> (2 * j)) & 3);
+            for (int j = 0; j < 2; j++) set(wire(g.row, lw + 16 + j), (carry >> (2 * j)) & 3);
+            return true;
+        }
+        case GEN_U32_SUB: {   // subtraction_u32.rs:298-343
+            u64 x, y, b;
+            if (!get(wire(g.row, 5 * g.i), &x) || !get(wire(g.row, 5 * g.i + 1), &y) || !get(wire(g.row, 5 * g.i + 2), &b)) return false;
+            const u64 init = gl_sub(gl_sub(x, y), b);
+            const u64 bout = init > (1ULL << 32) ? 1 : 0;
+            const u64 res = gl_add(init, bout ? (1ULL << 32) : 0);
+            set(wire(g.row, 5 * g.i + 3), res);
+            set(wire(g.row, 5 * g.i + 4), bout);
+            for (int j = 0; j < 16; j++) set(wire(g.row, 5 * g.n + 16 * g.i + j), (res >> (2 * j)) & 3);
+            return true;
+        }
+        case GEN_U32_RANGE: {   // range_check_u32.rs:198-220
+            for (int i = 0; i < g.n; i++) {
+                u64 v;
+                if (!get(wire(g.row, i), &v)) return false;
+                const u32 v32 = (u32)v;
+                for (int j = 0; j < 16; j++) set(wire(g.row, g.n + 16 * i + j), (v32 >> (2 * j)) & 3);
+            }
+            return true;
+        }
+        case GEN_COMPARISON: {   // comparison.rs:439-537
+            const int nc = g.i, cb = (g.n + nc - 1) / nc;
+            u64 a, b;
+            if (!get(wire(g.row, 0), &a) || !get(wire(g.row, 1), &b)) return false;
+            set(wire(g.row, 2), a <= b ? 1 : 0);
+            const u64 cs = 1ULL << cb;
+            u64 msd = 0;
+            for (int i = 0; i < nc; i++) {
+                const u64 fa = (a >> (cb * i)) & (cs - 1), fb = (b >> (cb * i)) & (cs - 1);
+                set(wire(g.row, 4 + i), fa);
+                set(wire(g.row, 4 + nc + i), fb);
+                set(wire(g.row, 4 + 2 * nc + i), fa == fb ? 1 : gl_inv(gl_sub(fb, fa)));   // equality dummy
+                set(wire(g.row, 4 + 3 * nc + i), fa == fb ? 1 : 0);                        // chunks equal
+                if (fa != fb) {
+                    msd = gl_sub(fb, fa);
+                    set(wire(g.row, 4 + 4 * nc + i), 0);
+                } else {
+                    set(wire(g.row, 4 + 4 * nc + i), msd);
+                }
+            }
+            set(wire(g.row, 3), msd);
+            const u64 t = gl_add(cs, msd);
+            for (int i = 0; i <= cb; i++) set(wire(g.row, 4 + 5 * nc + i), (t >> i) & 1);
             return true;
         }
         case GEN_POSEIDON: {
@@ -615,7 +783,12 @@ void assert_less_or_equal(Builder& b, size_t max_allowed, Target index) {
 //   6 MemoryRead: block_id, index witness, value witness                                        memory_translator.rs:125-137
 //   7 Sha256Compression: 16 input witnesses, 8 hash-value witnesses, 8 output witnesses         sha256_translator.rs:60-111
 //   8 MemoryWrite: block_id, index witness, value witness                                       memory_translator.rs:87-113
-enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6, OP_SHA256_COMPRESSION = 7, OP_MEM_WRITE = 8 };
+// Gadget-level operations (NOT ACIR opcodes: the reference reaches them only through its EcdsaSecp256k1 translator; here they let
+// a circuit be built directly on the reference's u32 gadgets, like its gadget tests do).  Witness ids name the targets.
+// 101 MulAddU32: x, y, z, low, high      102 AddManyU32: n, n addends, result, carry      103 SubU32: x, y, borrow, result, borrow_out
+// 104 RangeCheckU32: n, n values         105 CmpLe: a, b, num_bits, result
+enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6, OP_SHA256_COMPRESSION = 7, OP_MEM_WRITE = 8,
+       OP_MUL_ADD_U32 = 101, OP_ADD_MANY_U32 = 102, OP_SUB_U32 = 103, OP_RANGE_CHECK_U32 = 104, OP_CMP_LE = 105 };
 
 void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size_t npriv, const u64* ops, size_t nwords) {
     Builder& b = T.b;
@@ -706,6 +879,43 @@ void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size
                 Target eq = b.is_equal(idx, b.constant(pos));
                 cells[pos] = b.select(eq, val, cells[pos]);
             }
+            break;
+        }
+        case OP_MUL_ADD_U32: {
+            const u64 x = next(), y = next(), z = next(), lo = next(), hi = next();
+            auto r = b.mul_add_u32(T.target_for_witness((u32)x), T.target_for_witness((u32)y), T.target_for_witness((u32)z));
+            T.witness_target_map[(u32)lo] = r.first;
+            T.witness_target_map[(u32)hi] = r.second;
+            break;
+        }
+        case OP_ADD_MANY_U32: {
+            const u64 n = next();
+            std::vector<Target> v;
+            for (u64 i = 0; i < n; i++) v.push_back(T.target_for_witness((u32)next()));
+            const u64 res = next(), carry = next();
+            auto r = b.add_many_u32(v);
+            T.witness_target_map[(u32)res] = r.first;
+            T.witness_target_map[(u32)carry] = r.second;
+            break;
+        }
+        case OP_SUB_U32: {
+            const u64 x = next(), y = next(), bw = next(), res = next(), bo = next();
+            auto r = b.sub_u32(T.target_for_witness((u32)x), T.target_for_witness((u32)y), T.target_for_witness((u32)bw));
+            T.witness_target_map[(u32)res] = r.first;
+            T.witness_target_map[(u32)bo] = r.second;
+            break;
+        }
+        case OP_RANGE_CHECK_U32: {
+            const u64 n = next();
+            std::vector<Target> v;
+            for (u64 i = 0; i < n; i++) v.push_back(T.target_for_witness((u32)next()));
+            b.range_check_u32(v);
+            break;
+        }
+        case OP_CMP_LE: {
+            const u64 x = next(), y = next(), bits = next(), res = next();
+            if (bits == 0 || bits > 32) throw Error{"CmpLe: 1..32 bits"};
+            T.witness_target_map[(u32)res] = b.cmp_le(T.target_for_witness((u32)x), T.target_for_witness((u32)y), (int)bits);
             break;
         }
         case OP_SHA256_COMPRESSION: {

@@ -85,3 +85,72 @@ def sha256_circuit(acir, message):
         state = outs
     circuit = acir.Circuit(ops, list(range(16 * nblocks + 8)))
     return circuit, wit, state, list(struct.unpack(">8I", hashlib.sha256(message).digest()))
+
+
+def u32_gadget_cases(acir):
+    """Circuits built directly on the reference's u32 gadgets (plonky2_ecdsa/biguint/gadgets/arithmetic_u32.rs, range_check.rs,
+    multiple_comparison.rs) — the operations its EcdsaSecp256k1 translator is made of; values like the gates' own tests
+    (arithmetic_u32.rs:456-, subtraction_u32.rs:380-, comparison.rs:600-): (name, circuit, witness incl. expected outputs)."""
+    import random
+    E, AZ, C = acir.Expression, acir.AssertZero, acir.Circuit
+    M = (1 << 32) - 1
+    rng = random.Random(32)
+    out = []
+    # x*y+z: the all-ones corner is p-1 (high half = u32::MAX, low half must be 0: the gate's canonicity check)
+    trip = [(M, M, M), (0, 0, 0), (M, M, 0), (1, M, 1)] + [tuple(rng.getrandbits(32) for _ in range(3)) for _ in range(5)]
+    ops, wit = [], {}
+    for k, (x, y, z) in enumerate(trip):          # 9 operations: more than the 6 one U32ArithmeticGate row holds
+        b = 5 * k
+        v = x * y + z
+        ops.append(acir.MulAddU32(b, b + 1, b + 2, b + 3, b + 4))
+        wit.update({b: x, b + 1: y, b + 2: z, b + 3: v & M, b + 4: v >> 32})
+    out.append(("mul_add_u32", C(ops, [0, 1, 2], list(range(5, 5 * len(trip)))), wit))
+    ops, wit, w = [], {}, 0
+    for na in (2, 3, 4, 5, 16, 3, 3, 3, 3, 3, 3):   # 2 -> U32ArithmeticGate; 3 five times -> a second U32AddManyGate(3) row
+        vals = [M] * na if na in (4, 16) else [rng.getrandbits(32) for _ in range(na)]
+        s = sum(vals)
+        ids = list(range(w, w + na))
+        ops.append(acir.AddManyU32(ids, w + na, w + na + 1))
+        wit.update({**dict(zip(ids, vals)), w + na: s & M, w + na + 1: s >> 32})
+        w += na + 2
+    out.append(("add_many_u32", C(ops, [0, 1], list(range(2, w))), wit))
+    ops, wit = [], {}
+    subs = [(5, 3, 0), (3, 5, 0), (0, 0, 1), (M, M, 1), (0, M, 1), (M, 0, 0), (7, 7, 0)] + \
+           [(rng.getrandbits(32), rng.getrandbits(32), rng.getrandbits(1)) for _ in range(12)]   # 19 > 11 operations per row
+    for k, (x, y, bw) in enumerate(subs):
+        b = 5 * k
+        d = x - y - bw
+        ops.append(acir.SubU32(b, b + 1, b + 2, b + 3, b + 4))
+        wit.update({b: x, b + 1: y, b + 2: bw, b + 3: d % (1 << 32), b + 4: 1 if d < 0 else 0})
+    out.append(("sub_u32", C(ops, [0, 1, 2], list(range(5, 5 * len(subs)))), wit))
+    vals = [0, 1, M, 1 << 31] + [rng.getrandbits(32) for _ in range(9)]
+    out.append(("range_check_u32", C([acir.RangeCheckU32(list(range(13))), acir.RangeCheckU32([3])], [0], list(range(1, 13))),
+                dict(enumerate(vals))))
+    ops, wit = [], {}
+    cmps = [(3, 5, 32), (5, 3, 32), (5, 5, 32), (0, M, 32), (M, 0, 32), (M, M, 32), (0, 0, 32), (513, 512, 10), (512, 513, 10),
+            (1, 0, 1), (0, 1, 1), (0x12345678, 0x12355678, 32), (6, 5, 3)]
+    for k, (a, b_, bits) in enumerate(cmps):
+        b = 3 * k
+        ops.append(acir.CmpLe(b, b + 1, bits, b + 2))
+        wit.update({b: a, b + 1: b_, b + 2: 1 if a <= b_ else 0})
+    out.append(("cmp_le", C(ops, [0, 1], list(range(3, 3 * len(cmps)))), wit))
+    # a 96-bit add with carry chain then a comparison of the top limbs: gadgets feeding each other and an AssertZero
+    a = [rng.getrandbits(32) for _ in range(3)]
+    b_ = [rng.getrandbits(32) for _ in range(3)]
+    ops, wit, carry = [], {i: a[i] for i in range(3)}, 0
+    wit.update({3 + i: b_[i] for i in range(3)})
+    wit[6] = 0                                   # carry in
+    ops.append(AZ(E([], [(1, 6)], 0)))
+    cid = 6
+    for i in range(3):
+        s = a[i] + b_[i] + carry
+        ops.append(acir.AddManyU32([i, 3 + i, cid], 7 + 2 * i, 8 + 2 * i))
+        wit.update({7 + 2 * i: s & M, 8 + 2 * i: s >> 32})
+        carry, cid = s >> 32, 8 + 2 * i
+    ops.append(acir.RangeCheckU32([7, 9, 11]))
+    ops.append(acir.CmpLe(7, 11, 32, 13))
+    wit[13] = 1 if wit[7] <= wit[11] else 0
+    ops.append(AZ(E([], [(1, 12), (P - 1, 14)], 0)))   # w14 = final carry
+    wit[14] = carry
+    out.append(("biguint_add_96", C(ops, [0, 1, 2, 3, 4, 5], [6]), wit))
+    return out

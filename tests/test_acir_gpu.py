@@ -30,6 +30,23 @@ def test_translated_circuits_prove_on_the_gpu(p2g, corc, case):
         assert pw.to_bytes() == op.prove(wires, pis), name
 
 
+@pytest.mark.parametrize("case", range(6))
+def test_u32_gadget_circuits_prove_on_the_gpu(p2g, corc, case):
+    """The reference's custom u32 / comparison gates on rows filled by their restated witness generators (not synthetic rows):
+    built with the gadgets, witnessed, proved by the CUDA prover, byte-compared with the oracle prover and verified."""
+    from helpers import oracle_cd
+    from oracle.pyref import proof, verifier
+    name, circuit, witness = acir_cases.u32_gadget_cases(p2g.acir)[case]
+    tr = p2g.acir.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    wires, pis = tr.generate_witness(witness)
+    cd = oracle_cd(tr.common)
+    data, _ = tr.unpack()
+    with data:
+        got = data.prove(wires, pis).to_bytes()
+        verifier.verify(proof.parse_uncompressed(got, cd), cd, data.constants_sigmas_cap, data.circuit_digest)
+    assert got == corc.OracleProver(cd, tr.constants_sigmas).prove(wires, pis), name
+
+
 def test_assert_zero_chain_from_real_opcodes(p2g, corc):
     """BASELINE configs[1] shape from real AssertZero opcodes (2^14 rows): translated, witnessed, proved, byte-compared."""
     from helpers import oracle_cd
