@@ -67,9 +67,10 @@ struct Error {
 const int NUM_WIRES = 234, NUM_ROUTED = 80, ARITH_OPS = 20, CONSTS_PER_GATE = 2, SPLIT_LIMBS = 63;
 
 struct Builder {
-    // targets: wires are created lazily as (row, col) -> id
+    // targets: routed wires become targets lazily, (row, col) -> id; the advice wires (col >= 80) can never be copy-constrained, so
+    // they are not targets at all: wire() names them by a negative code and witness generation keeps their values in a dense table
     std::vector<std::pair<int, int>> target_wire;   // (row, col) or (-1, -1) for virtual targets
-    std::map<std::pair<int, int>, Target> wire_target;
+    std::vector<Target> routed_target;               // [row * 80 + col] -> target or -1
     std::vector<Target> parent;                      // union-find over targets (copy constraints)
     std::vector<Row> rows;
     std::vector<GateType> gate_types;
@@ -92,13 +93,14 @@ struct Builder {
         return (Target)parent.size() - 1;
     }
     Target add_virtual_target() { return new_target(); }
+    static Target advice_code(int row, int col) { return -2 - (Target)(row * NUM_WIRES + col); }
     Target wire(int row, int col) {
-        auto it = wire_target.find({row, col});
-        if (it != wire_target.end()) return it->second;
-        Target t = new_target(row, col);
-        wire_target[{row, col}] = t;
-        return t;
+        if (col >= NUM_ROUTED) return advice_code(row, col);
+        Target& slot = routed_target[(size_t)row * NUM_ROUTED + col];
+        if (slot < 0) slot = new_target(row, col);
+        return slot;
     }
+    Target routed_or_none(size_t row, int col) const { return row < rows.size() ? routed_target[row * NUM_ROUTED + col] : -1; }
     Target find(Target t) {
         while (parent[t] != t) {
             parent[t] = parent[parent[t]];
@@ -107,8 +109,7 @@ struct Builder {
         return t;
     }
     void connect(Target a, Target b) {
-        for (Target t : {a, b})
-            if (target_wire[t].first >= 0 && target_wire[t].second >= NUM_ROUTED) throw Error{"connect: wire is not routable"};
+        if (a < 0 || b < 0) throw Error{"connect: wire is not routable"};
         a = find(a);
         b = find(b);
         if (a != b) parent[b] = a;
@@ -122,6 +123,8 @@ struct Builder {
     }
     int add_gate(int gt, std::vector<u64> consts = {}) {
         rows.push_back({gt, std::move(consts)});
+        if (rows.size() > (size_t)1 << 22) throw Error{"circuit has more than 2^22 rows"};
+        routed_target.resize(rows.size() * NUM_ROUTED, -1);
         return (int)rows.size() - 1;
     }
 
@@ -426,15 +429,25 @@ struct Builder {
     // ---- witness generation: plonky2 iop/generator.rs generate_partial_witness restricted to the generators above.
     // values are kept per copy-constraint class (PartitionWitness); a class set twice with different values is an unsatisfied
     // copy constraint -- plonky2 panics there, this returns an error.
-    std::vector<u64> val;
-    std::vector<char> has;
-    void grow() {   // generators touch wires nobody referenced before (Poseidon's internal columns): they become targets now
+    std::vector<u64> val, advice_val;   // per target class; per advice wire [row * 154 + col - 80]
+    std::vector<char> has, advice_has;
+    void grow() {   // generators touch routed wires nobody referenced before: they become targets now
         if (val.size() < parent.size()) {
             val.resize(parent.size(), 0);
             has.resize(parent.size(), 0);
         }
     }
+    static size_t advice_index(Target t) {
+        const size_t code = (size_t)(-2 - t), row = code / NUM_WIRES, col = code % NUM_WIRES;
+        return row * (NUM_WIRES - NUM_ROUTED) + (col - NUM_ROUTED);
+    }
     void set(Target t, u64 v) {
+        if (t < 0) {   // advice wire: written once by the generator of its own gate
+            const size_t k = advice_index(t);
+            advice_has[k] = 1;
+            advice_val[k] = v;
+            return;
+        }
         grow();
         Target r = find(t);
         if (has[r]) {
@@ -445,6 +458,11 @@ struct Builder {
         val[r] = v;
     }
     bool get(Target t, u64* v) {
+        if (t < 0) {
+            const size_t k = advice_index(t);
+            *v = advice_val[k];
+            return advice_has[k] != 0;
+        }
         grow();
         Target r = find(t);
         if (!has[r]) return false;
@@ -999,9 +1017,9 @@ int p2a_constants_sigmas(void* h, const p2g_gate* gates, u32 ngates, const u32* 
         std::unordered_map<Target, std::vector<u32>> classes;   // representative -> wires (row * 80 + col) in row-major order
         for (size_t r = 0; r < n; r++)
             for (int c = 0; c < NUM_ROUTED; c++) {
-                auto it = b.wire_target.find({(int)r, c});
-                if (it == b.wire_target.end()) continue;   // never connected: fixed point
-                classes[b.find(it->second)].push_back((u32)(r * NUM_ROUTED + c));
+                const Target t = b.routed_or_none(r, c);
+                if (t < 0) continue;   // never connected: fixed point
+                classes[b.find(t)].push_back((u32)(r * NUM_ROUTED + c));
             }
         u64* sig = out + (size_t)num_constants * n;
         for (size_t r = 0; r < n; r++)
@@ -1030,6 +1048,8 @@ int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wire
         const size_t n = (size_t)1 << b.degree_bits;
         b.val.assign(b.parent.size(), 0);
         b.has.assign(b.parent.size(), 0);
+        b.advice_val.assign(b.rows.size() * (NUM_WIRES - NUM_ROUTED), 0);
+        b.advice_has.assign(b.rows.size() * (NUM_WIRES - NUM_ROUTED), 0);
         for (auto& g : b.gens) g.done = false;
         for (size_t i = 0; i < nw; i++) {
             if (values[i] >= GL_P) throw Error{"witness value is not canonical"};
@@ -1052,9 +1072,13 @@ int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wire
             if (!pending || !progress) break;
         }
         memset(wires, 0, (size_t)NUM_WIRES * n * 8);
-        for (auto& kv : b.wire_target) {
-            u64 v;
-            if (b.get(kv.second, &v)) wires[(size_t)kv.first.second * n + kv.first.first] = v;
+        for (size_t r = 0; r < b.rows.size(); r++) {
+            for (int c = 0; c < NUM_ROUTED; c++) {
+                const Target t = b.routed_or_none(r, c);
+                u64 v;
+                if (t >= 0 && b.get(t, &v)) wires[(size_t)c * n + r] = v;
+            }
+            for (int c = NUM_ROUTED; c < NUM_WIRES; c++) wires[(size_t)c * n + r] = b.advice_val[r * (NUM_WIRES - NUM_ROUTED) + c - NUM_ROUTED];
         }
         for (size_t i = 0; i < b.public_inputs.size(); i++) {
             u64 v;
