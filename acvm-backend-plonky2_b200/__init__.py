@@ -9,3 +9,4 @@ from . import synth  # noqa: F401,E402
 from .circuit import CircuitConfig, CircuitData, CommonCircuitData, Gate, ProofWithPublicInputs  # noqa: F401,E402
 from . import sharding  # noqa: F401,E402
 from . import acir  # noqa: F401,E402
+from . import ecdsa_inputs  # noqa: F401,E402

@@ -40,6 +40,9 @@ def _acir_lib():
         L.p2a_gate_types.argtypes = [C.c_void_p, C.c_void_p]
         L.p2a_constants_sigmas.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.p2a_witness.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.p2a_read_witnesses.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.p2a_rows_used.argtypes = [C.c_void_p]
+        L.p2a_rows_used.restype = C.c_uint32
         _LIB = L
     return _LIB
 
@@ -108,6 +111,15 @@ class Sha256Compression:   # BlackBoxFuncCall::Sha256Compression { inputs: [_; 1
     inputs: list
     hash_values: list
     outputs: list
+
+
+@dataclass
+class EcdsaSecp256k1:   # BlackBoxFuncCall::EcdsaSecp256k1 { public_key_x: [_; 32], public_key_y: [_; 32], signature: [_; 64], hashed_message: [_; 32], output }
+    public_key_x: list
+    public_key_y: list
+    signature: list
+    hashed_message: list
+    output: int
 
 
 # ---- gadget-level operations (not ACIR opcodes): the reference's u32 gadgets, plonky2_ecdsa/biguint/gadgets/*.rs, over its custom
@@ -180,6 +192,10 @@ def _encode(circuit):
             words += [6, op.block_id, op.index, op.value]
         elif isinstance(op, MemoryWrite):
             words += [8, op.block_id, op.index, op.value]
+        elif isinstance(op, EcdsaSecp256k1):
+            if (len(op.public_key_x), len(op.public_key_y), len(op.signature), len(op.hashed_message)) != (32, 32, 64, 32):
+                raise TranslationError("EcdsaSecp256k1 takes 32 + 32 + 64 + 32 byte witnesses")
+            words += [9] + list(op.public_key_x) + list(op.public_key_y) + list(op.signature) + list(op.hashed_message) + [op.output]
         elif isinstance(op, MulAddU32):
             words += [101, op.x, op.y, op.z, op.low, op.high]
         elif isinstance(op, AddManyU32):
@@ -259,6 +275,19 @@ class CircuitBuilderFromAcirToPlonky2:
         if rc != 0:
             raise TranslationError(L.p2a_last_error().decode())
         return wires, [int(x) for x in pis[:self.common.num_public_inputs]]
+
+    def read_witnesses(self, ids):
+        """{witness index: value} as the last generate_witness() left them -- computed outputs included (the reference reads them
+        through its witness_target_map); witnesses the circuit never mentions are omitted."""
+        L = _acir_lib()
+        a = np.array(list(ids), dtype=np.uint64)
+        vals, known = np.zeros(len(a), dtype=np.uint64), np.zeros(len(a), dtype=np.uint8)
+        L.p2a_read_witnesses(self._h, a.ctypes.data_as(C.c_void_p), len(a), vals.ctypes.data_as(C.c_void_p), known.ctypes.data_as(C.c_void_p))
+        return {int(k): int(v) for k, v, ok in zip(a, vals, known) if ok}
+
+    def rows_used(self):
+        """Rows in use before the power-of-two padding."""
+        return int(_acir_lib().p2a_rows_used(self._h))
 
     def unpack(self, device=0):
         """(CircuitData on the GPU, self): the analogue of `translator.unpack()` -> (circuit_data, witness_target_map)."""

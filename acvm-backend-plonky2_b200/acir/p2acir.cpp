@@ -30,6 +30,7 @@
 
 #include "../csrc/hash.cuh"
 #include "../../include/p2g.h"
+#include "bigint.h"
 
 namespace {
 
@@ -48,7 +49,7 @@ struct Row {
 };
 
 enum GenKind { GEN_ARITH, GEN_CONST, GEN_SPLIT, GEN_BASE_SPLIT, GEN_BASE_SUM, GEN_RANDOM_ACCESS, GEN_POSEIDON, GEN_EQUAL,
-               GEN_U32_ARITH, GEN_U32_ADD_MANY, GEN_U32_SUB, GEN_U32_RANGE, GEN_COMPARISON };
+               GEN_U32_ARITH, GEN_U32_ADD_MANY, GEN_U32_SUB, GEN_U32_RANGE, GEN_COMPARISON, GEN_BIG };
 struct Gen {
     GenKind kind;
     int row, i;         // gate row, op / copy index
@@ -62,6 +63,18 @@ struct Gen {
 
 struct Error {
     std::string msg;
+};
+
+// generators over big integers (plonky2_ecdsa: BigUintDivRemGenerator, NonNative{Addition,Subtraction,Multiplication,Inverse}Generator,
+// GLVDecompositionGenerator): kept in a side table, Gen::i indexes it
+typedef std::vector<Target> BigT;   // BigUintTarget: u32 limbs, least significant first
+enum BigGenKind { BG_DIVREM, BG_NN_ADD, BG_NN_SUB, BG_NN_MUL, BG_NN_INV, BG_GLV };
+struct BigGen {
+    BigGenKind kind;
+    int field;        // 0: secp256k1 base field, 1: scalar field
+    BigT a, b;        // inputs
+    BigT o1, o2;      // outputs (sum / diff / prod / inv / div / k1, overflow / div / rem / k2)
+    Target t1, t2;    // bool outputs (overflow; k1_neg, k2_neg)
 };
 
 const int NUM_WIRES = 234, NUM_ROUTED = 80, ARITH_OPS = 20, CONSTS_PER_GATE = 2, SPLIT_LIMBS = 63;
@@ -83,6 +96,8 @@ struct Builder {
     std::map<int, std::pair<int, int>> free_add_many;                     // num_addends -> (row, next op)
     std::vector<Target> public_inputs;
     std::vector<Gen> gens;
+    std::vector<BigGen> big_gens;
+    std::unordered_map<Target, u64> target_consts;   // plonky2's targets_to_constants (target_as_constant)
     bool built = false;
     int degree_bits = 0;
     Target pi_hash[4];
@@ -135,6 +150,7 @@ struct Builder {
         Target t = add_virtual_target();
         constants[c] = t;
         constant_order.push_back(c);
+        target_consts[t] = c;
         return t;
     }
     Target zero() { return constant(0); }
@@ -237,6 +253,20 @@ struct Builder {
         return bits;
     }
     void range_check(Target x, int nbits) { split_le(x, nbits); }
+    // split_le_base::<4>(x, num_limbs) (gadgets/split_base.rs): one BaseSumGate<4>, the sum wire tied to x
+    std::vector<Target> split_le_base4(Target x, int num_limbs) {
+        const int row = add_gate(gate_type(P2G_GATE_BASE_SUM, 4, (u32)num_limbs));
+        connect(x, wire(row, 0));
+        Gen g = {};
+        g.kind = GEN_BASE_SPLIT;
+        g.row = row;
+        g.n = num_limbs;
+        g.c0 = 4;
+        gens.push_back(g);
+        std::vector<Target> limbs;
+        for (int l = 0; l < num_limbs; l++) limbs.push_back(wire(row, 1 + l));
+        return limbs;
+    }
     // le_sum (gadgets/split_base.rs): one BaseSumGate<2> with exactly bits.size() limbs
     Target le_sum(const std::vector<Target>& bits) {
         if (bits.empty()) return zero();
@@ -286,7 +316,18 @@ struct Builder {
     static int u32_sub_ops() { return std::min(NUM_WIRES / 21, NUM_ROUTED / 5); }                         // subtraction_u32.rs:38-42
     static int add_many_ops(int na) { return std::min(NUM_WIRES / (na + 21), NUM_ROUTED / (na + 3)); }    // add_many_u32.rs:43-48
     // x * y + z = low + 2^32 high
+    bool as_constant(Target t, u64* c) const {
+        auto it = target_consts.find(t);
+        if (it == target_consts.end()) return false;
+        *c = it->second;
+        return true;
+    }
     std::pair<Target, Target> mul_add_u32(Target x, Target y, Target z) {
+        u64 cx, cy, cz;
+        if (as_constant(x, &cx) && as_constant(y, &cy) && as_constant(z, &cz)) {   // arithmetic_u32_special_cases (gadget :112-137)
+            const u64 sum = gl_add(gl_mul(cx, cy), cz);
+            return {constant(sum & 0xFFFFFFFFULL), constant(sum >> 32)};
+        }
         const int ops = u32_arith_ops();
         auto& slot = free_u32_arith;
         if (slot.second == 0 || slot.second >= ops) {
@@ -307,11 +348,20 @@ struct Builder {
     }
     std::pair<Target, Target> add_u32(Target a, Target b) { return mul_add_u32(a, one(), b); }
     // sum of the addends = result + 2^32 carry  (arithmetic_u32.rs gadget add_many_u32: 0 / 1 / 2 addends are special-cased)
+    std::pair<Target, Target> mul_u32(Target a, Target b) { return mul_add_u32(a, b, zero()); }
     std::pair<Target, Target> add_many_u32(const std::vector<Target>& v) {
         if (v.empty()) return {zero(), zero()};
         if (v.size() == 1) return {v[0], zero()};
         if (v.size() == 2) return add_u32(v[0], v[1]);
+        return add_many_gate(v, zero());
+    }
+    std::pair<Target, Target> add_u32s_with_carry(const std::vector<Target>& v, Target carry) {   // gadget :198-224
+        if (v.size() == 1) return add_u32(v[0], carry);
+        return add_many_gate(v, carry);
+    }
+    std::pair<Target, Target> add_many_gate(const std::vector<Target>& v, Target carry_in) {
         const int na = (int)v.size();
+        if (na < 1) throw Error{"add_many_u32: no addends"};
         if (na > 16) throw Error{"add_many_u32: more than 16 addends"};
         const int ops = add_many_ops(na);
         auto& slot = free_add_many[na];
@@ -321,7 +371,7 @@ struct Builder {
         }
         const int row = slot.first, i = slot.second++, q = (na + 3) * i;
         for (int j = 0; j < na; j++) connect(v[j], wire(row, q + j));
-        connect(zero(), wire(row, q + na));   // carry in
+        connect(carry_in, wire(row, q + na));
         Gen g = {};
         g.kind = GEN_U32_ADD_MANY;
         g.row = row;
@@ -469,8 +519,11 @@ struct Builder {
         *v = val[r];
         return true;
     }
+    bool run_big(BigGen& g);
     bool run(Gen& g) {
         switch (g.kind) {
+        case GEN_BIG:
+            return run_big(big_gens[g.i]);
         case GEN_CONST:
             set(wire(g.row, g.i), g.c0);
             return true;
@@ -492,6 +545,10 @@ struct Builder {
         case GEN_BASE_SPLIT: {   // BaseSplitGenerator: sum -> limbs
             u64 s;
             if (!get(wire(g.row, 0), &s)) return false;
+            if (g.c0 == 4) {   // split_le_base::<4>
+                for (int l = 0; l < g.n; l++) set(wire(g.row, 1 + l), l < 32 ? (s >> (2 * l)) & 3 : 0);
+                return true;
+            }
             for (int l = 0; l < g.n; l++) set(wire(g.row, 1 + l), l < 64 ? (s >> l) & 1 : 0);
             return true;
         }
@@ -660,6 +717,8 @@ struct Translator {
     }
 };
 
+#include "ecdsa.h"
+
 // ---- BinaryDigitsTarget (plonky2-backend/src/binary_digits_target.rs): bit vectors, most significant bit first ---------------
 typedef std::vector<Target> Bits;
 Bits rotate_right(Builder& b, const Bits& t, size_t times) {   // :21-41
@@ -801,11 +860,12 @@ void assert_less_or_equal(Builder& b, size_t max_allowed, Target index) {
 //   6 MemoryRead: block_id, index witness, value witness                                        memory_translator.rs:125-137
 //   7 Sha256Compression: 16 input witnesses, 8 hash-value witnesses, 8 output witnesses         sha256_translator.rs:60-111
 //   8 MemoryWrite: block_id, index witness, value witness                                       memory_translator.rs:87-113
+//   9 EcdsaSecp256k1: 32 public_key_x, 32 public_key_y, 64 signature, 32 hashed_message byte witnesses, output   ecdsa_secp256k1_translator.rs:38-60
 // Gadget-level operations (NOT ACIR opcodes: the reference reaches them only through its EcdsaSecp256k1 translator; here they let
 // a circuit be built directly on the reference's u32 gadgets, like its gadget tests do).  Witness ids name the targets.
 // 101 MulAddU32: x, y, z, low, high      102 AddManyU32: n, n addends, result, carry      103 SubU32: x, y, borrow, result, borrow_out
 // 104 RangeCheckU32: n, n values         105 CmpLe: a, b, num_bits, result
-enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6, OP_SHA256_COMPRESSION = 7, OP_MEM_WRITE = 8,
+enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6, OP_SHA256_COMPRESSION = 7, OP_MEM_WRITE = 8, OP_ECDSA_SECP256K1 = 9,
        OP_MUL_ADD_U32 = 101, OP_ADD_MANY_U32 = 102, OP_SUB_U32 = 103, OP_RANGE_CHECK_U32 = 104, OP_CMP_LE = 105 };
 
 void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size_t npriv, const u64* ops, size_t nwords) {
@@ -934,6 +994,12 @@ void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size
             const u64 x = next(), y = next(), bits = next(), res = next();
             if (bits == 0 || bits > 32) throw Error{"CmpLe: 1..32 bits"};
             T.witness_target_map[(u32)res] = b.cmp_le(T.target_for_witness((u32)x), T.target_for_witness((u32)y), (int)bits);
+            break;
+        }
+        case OP_ECDSA_SECP256K1: {
+            u32 ws[161];
+            for (int i = 0; i < 161; i++) ws[i] = (u32)next();
+            ecdsa_secp256k1(T, ws, ws + 32, ws + 64, ws + 128, ws[160]);
             break;
         }
         case OP_SHA256_COMPRESSION: {
@@ -1090,6 +1156,26 @@ int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wire
         g_err = e.msg;
         return -1;
     }
+}
+
+// Values the last p2a_witness run assigned to ACIR witnesses (outputs computed by the generators included): what the reference reads
+// back through its witness_target_map.  known[i] = 0 for a witness the circuit never mentions or that stayed unset.
+void p2a_read_witnesses(void* h, const u64* ids, size_t n, u64* values, uint8_t* known) {
+    Translator* T = (Translator*)h;
+    for (size_t i = 0; i < n; i++) {
+        auto it = T->witness_target_map.find((u32)ids[i]);
+        u64 v = 0;
+        known[i] = it != T->witness_target_map.end() && !T->b.val.empty() && T->b.get(it->second, &v);
+        values[i] = v;
+    }
+}
+// rows in use before the power-of-two padding
+u32 p2a_rows_used(void* h) {
+    Translator* T = (Translator*)h;
+    const int noop = T->b.gate_type(P2G_GATE_NOOP);
+    size_t n = T->b.rows.size();
+    while (n > 0 && T->b.rows[n - 1].gate == noop) n--;
+    return (u32)n;
 }
 
 }  // extern "C"
