@@ -99,3 +99,34 @@ def circuit_and_witness(acir, cases, outputs=None, range_checks=True, assert_val
         w += 161
     private = [k for k in range(first_witness, w) if k not in out_ids]
     return acir.Circuit(ops, [], private), wit, out_ids
+
+
+class RealEcdsaCircuit:
+    """A bench / test workload with SyntheticCircuit's attributes (common, constants_sigmas, wires, public_inputs, config,
+    _wires_t when pinned) built from real opcodes: the Noir signature-check program above on 2^(degree_bits - 17) signatures
+    (one EcdsaSecp256k1 call is 98.9 K rows = 2^17; eight fill 2^20).  Translation and witness generation run on the host."""
+
+    ROWS_LOG2_PER_SIGNATURE = 17
+
+    def __init__(self, degree_bits, acir, config=None, seed=0, pinned=False):
+        import numpy as np
+        if degree_bits < self.ROWS_LOG2_PER_SIGNATURE:
+            raise ValueError("one EcdsaSecp256k1 circuit already has 2^17 rows")
+        self.num_signatures = 1 << (degree_bits - self.ROWS_LOG2_PER_SIGNATURE)
+        cases = [deterministic_case(f"{seed}/{i}") for i in range(self.num_signatures)]
+        circuit, wit, _ = circuit_and_witness(acir, cases, outputs=[1] * self.num_signatures, assert_valid=True)
+        tr = acir.CircuitBuilderFromAcirToPlonky2(config).translate_circuit(circuit)
+        if tr.common.degree_bits() != degree_bits:
+            raise RuntimeError(f"{self.num_signatures} signatures gave 2^{tr.common.degree_bits()} rows, not 2^{degree_bits}")
+        self.config, self.common, self.constants_sigmas = tr.config, tr.common, tr.constants_sigmas
+        self.workload = "ecdsa-real"
+        self.rows_used = tr.rows_used()
+        wires, self.public_inputs = tr.generate_witness(wit)
+        if pinned:
+            import torch
+            self._wires_t = torch.empty(wires.shape, dtype=torch.int64).pin_memory()
+            self.wires = self._wires_t.numpy().view(np.uint64)
+            self.wires[:] = wires
+        else:
+            self.wires = wires
+        tr.close()

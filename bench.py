@@ -112,13 +112,36 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+REAL_WORKLOAD = "ecdsa-real"   # the EcdsaSecp256k1 opcode translated like the reference does (acir/ecdsa.h), not a synthetic gate mix
+
+
+def make_workload(p2g, args, bits, seed, pinned=False):
+    """The circuit + witness of `--workload` at 2^bits rows: a synthetic gate mix (p2g.synth) or, for `ecdsa-real`, the Noir
+    signature-check program on 2^(bits - 17) signatures translated from real opcodes."""
+    cfg = p2g.CircuitConfig.wide_ecc_config(hasher=args.hasher)
+    if args.workload == REAL_WORKLOAD:
+        return p2g.ecdsa_inputs.RealEcdsaCircuit(bits, p2g.acir, config=cfg, seed=seed, pinned=pinned)
+    return p2g.synth.SyntheticCircuit(bits, args.workload, config=cfg, num_public_inputs=4, seed=seed, pinned=pinned)
+
+
+def data_note(args):
+    return "synthetic (deterministic keys and signatures; circuit from the real opcode)" if args.workload == REAL_WORKLOAD else "synthetic"
+
+
+def min_sample_bits(args):
+    return 17 if args.workload == REAL_WORKLOAD else 11
+
+
 def workload_config(args, sc):
     """The `config` object of the JSON line: identical for the product arm and the reference arm (same workload, same circuit)."""
     cfg = sc.config
     return {"workload": f"{args.workload}_2^{args.degree_bits}", "rows": 1 << args.degree_bits, "wires": cfg.num_wires,
             "routed": cfg.num_routed_wires, "hasher": args.hasher, "rate_bits": cfg.rate_bits, "gates": len(sc.common.gates),
             "gate_constraints": sc.common.num_gate_constraints, "fri_arity_bits": list(sc.common.reduction_arity_bits),
-            "public_inputs": 4,
+            "public_inputs": len(sc.public_inputs),
+            **({"source": f"{sc.num_signatures} EcdsaSecp256k1 opcode(s) + 160 RANGE opcodes each, translated like "
+                          "circuit_translation/ecdsa_secp256k1_translator.rs; witness from the restated plonky2_ecdsa generators",
+                "rows_used": sc.rows_used} if args.workload == REAL_WORKLOAD else {}),
             "l2": "inputs larger than L2 (1.96 GB trace, 14.6 GB LDE per proof at 2^20 rows); no explicit flush"}
 
 
@@ -129,8 +152,7 @@ def cpu_proof(p2g, args, bits, seed, sc=None):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import oracle_cd
     if sc is None:
-        cfg = p2g.CircuitConfig.wide_ecc_config(hasher=args.hasher)
-        sc = p2g.synth.SyntheticCircuit(bits, args.workload, config=cfg, num_public_inputs=4, seed=seed)
+        sc = make_workload(p2g, args, bits, seed)
     cd = oracle_cd(sc.common)
     op = corc.OracleProver(cd, sc.constants_sigmas)     # circuit build (preprocessed commitment) is outside the timing
     t0 = time.perf_counter()
@@ -143,9 +165,9 @@ def cpu_proof(p2g, args, bits, seed, sc=None):
 def pick_cpu_sample_bits(p2g, args, target_s):
     if args.cpu_sample_bits:
         return args.cpu_sample_bits
-    dt, _, _ = cpu_proof(p2g, args, 11, 1)
+    bits = min(min_sample_bits(args), args.degree_bits)
+    dt, _, _ = cpu_proof(p2g, args, bits, 1)
     # prover cost is ~linear in rows
-    bits = 11
     while bits < args.degree_bits and dt * 2 <= target_s:
         dt *= 2
         bits += 1
@@ -180,7 +202,7 @@ def run_reference(args, rank, world):
     for i in range(args.warmup):
         cpu_proof(p2g, args, bits, 100 + i)
     cfg = p2g.CircuitConfig.wide_ecc_config(hasher=args.hasher)
-    full_sc = p2g.synth.SyntheticCircuit(args.degree_bits, args.workload, config=cfg, num_public_inputs=4, seed=0xAC1D + 3)
+    full_sc = make_workload(p2g, args, args.degree_bits, 0xAC1D + 3)
     need_gb = 45.0 * (1 << args.degree_bits) / (1 << 20)
     full_ok = host_ram_gb() >= need_gb and not args.no_full_size_cpu
     times, full_s, cores = [], None, 1
@@ -206,7 +228,7 @@ def run_reference(args, rank, world):
     value = 1.0 / per_proof_s
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sum(times) / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64 (Goldilocks field, 64-bit integer)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u64 (Goldilocks field, 64-bit integer)", "data": data_note(args),
             "config": workload_config(args, full_sc),
             "full_size_ms": full_s * 1e3 if full_s is not None else None, "sample_rows_log2": bits,
             "sample_ms": sample_s * 1e3 if sample_s is not None else None,
@@ -266,8 +288,7 @@ def main():
     cfg = p2g.CircuitConfig.wide_ecc_config(hasher=args.hasher)
     if world > 1:   # input generation (untimed): this rank's share of the host cores, not torchrun's OMP_NUM_THREADS=1
         p2g.synth.set_threads(max(1, (os.cpu_count() or world) // world))
-    sc = p2g.synth.SyntheticCircuit(args.degree_bits, args.workload, config=cfg, num_public_inputs=4,
-                                    seed=0xAC1D + 3 + 1000 * rank, pinned=True)
+    sc = make_workload(p2g, args, args.degree_bits, 0xAC1D + 3 + 1000 * rank, pinned=True)
     # circuit build: once, outside the timing.  `inflight` handles = proofs in flight on this GPU (own stream + host thread each)
     F = max(1, args.inflight)
     handles = [p2g.CircuitData(sc.common, sc.constants_sigmas, device=local_rank) for _ in range(F)]
@@ -353,8 +374,7 @@ def main():
                else p2g.sharding.NcclGroup.from_torch_dist(local_rank))
         sc0 = sc if rank == 0 else None
         if rank != 0:   # every rank proves the SAME circuit and witness
-            sc0 = p2g.synth.SyntheticCircuit(args.degree_bits, args.workload, config=cfg, num_public_inputs=4,
-                                             seed=0xAC1D + 3, pinned=True)
+            sc0 = make_workload(p2g, args, args.degree_bits, 0xAC1D + 3, pinned=True)
         sdata = p2g.CircuitData(sc0.common, sc0.constants_sigmas, device=local_rank, shard=grp)
         shard_info = sdata.read(p2g.lib.BUF_SHARD_INFO)
         wh = sc0._wires_t
@@ -399,7 +419,7 @@ def main():
         line = {
             "metric": METRIC, "value": world * K / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64 (Goldilocks field, 64-bit integer)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u64 (Goldilocks field, 64-bit integer)", "data": data_note(args),
             "config": workload_config(args, sc),
             "execution": {"parallelism": f"{world} GPU(s) x {F} proofs in flight per GPU (independent witnesses per GPU)",
                           "inflight_per_gpu": F, "proof_bytes": proof_bytes},

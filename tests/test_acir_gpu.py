@@ -80,3 +80,33 @@ def test_config2_real_sha256_circuit_2_18(p2g, corc):
         got = data.prove(wires, pis).to_bytes()
         verifier.verify(proof.parse_uncompressed(got, cd), cd, data.constants_sigmas_cap, data.circuit_digest)
     assert got == corc.OracleProver(cd, tr.constants_sigmas).prove(wires, pis)
+
+
+def _ecdsa_parity(p2g, corc, n_signatures, want_bits):
+    from helpers import oracle_cd
+    from oracle.pyref import proof, verifier
+    A, EI = p2g.acir, p2g.ecdsa_inputs
+    cases = [EI.deterministic_case(100 + i) for i in range(n_signatures)]
+    circuit, wit, outs = EI.circuit_and_witness(A, cases, outputs=[1] * n_signatures, assert_valid=True)
+    tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    assert tr.common.degree_bits() == want_bits
+    wires, pis = tr.generate_witness(wit)
+    cd = oracle_cd(tr.common)
+    data, _ = tr.unpack()
+    with data:
+        got = data.prove(wires, pis).to_bytes()
+        verifier.verify(proof.parse_uncompressed(got, cd), cd, data.constants_sigmas_cap, data.circuit_digest)
+    assert got == corc.OracleProver(cd, tr.constants_sigmas).prove(wires, pis)
+
+
+def test_config3_real_ecdsa_circuit_2_17(p2g, corc):
+    """BASELINE configs[3] from the real opcode: the Noir program of the reference's `ecdsa_secp256k1` test (160 RANGE-checked byte
+    inputs, one EcdsaSecp256k1 blackbox call, assert(valid)) translated like ecdsa_secp256k1_translator.rs over the plonky2_ecdsa
+    gadgets -> 98.9 K rows = 2^17 on the 234-wire configuration, 18 gate types.  Witness from the restated generators; the CUDA
+    prover's bytes equal the oracle prover's and the oracle verifier accepts them."""
+    _ecdsa_parity(p2g, corc, 1, 17)
+
+
+def test_config3_eight_real_ecdsa_signatures_2_20(p2g, corc):
+    """The same program verifying eight signatures: 2^20 rows from real opcodes (BASELINE's size for configs[3])."""
+    _ecdsa_parity(p2g, corc, 8, 20)
