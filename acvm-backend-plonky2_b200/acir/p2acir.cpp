@@ -18,7 +18,9 @@
 // with the fork's, so its circuit_digest differs from the Rust one; every circuit it builds is a valid plonky2 circuit in the
 // reference's configuration, and proofs of it verify.  Host tooling, not on the hot path.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 #include <string.h>
 
 #include <algorithm>
@@ -519,18 +521,41 @@ struct Builder {
         *v = val[r];
         return true;
     }
+    // gate-local wire access for the generators: advice columns go straight to the dense table
+    void setw(int row, int col, u64 v) {
+        if (col >= NUM_ROUTED) {
+            const size_t k = (size_t)row * (NUM_WIRES - NUM_ROUTED) + (col - NUM_ROUTED);
+            advice_has[k] = 1;
+            advice_val[k] = v;
+        } else {
+            set(wire(row, col), v);
+        }
+    }
+    bool getw(int row, int col, u64* v) {
+        if (col >= NUM_ROUTED) {
+            const size_t k = (size_t)row * (NUM_WIRES - NUM_ROUTED) + (col - NUM_ROUTED);
+            *v = advice_val[k];
+            return advice_has[k] != 0;
+        }
+        const Target t = routed_target[(size_t)row * NUM_ROUTED + col];
+        return t >= 0 && get(t, v);
+    }
+    Target find_const(Target t) const {
+        while (parent[t] != t) t = parent[t];
+        return t;
+    }
     bool run_big(BigGen& g);
     bool run(Gen& g) {
         switch (g.kind) {
         case GEN_BIG:
             return run_big(big_gens[g.i]);
         case GEN_CONST:
-            set(wire(g.row, g.i), g.c0);
+            setw(g.row, g.i, g.c0);
             return true;
         case GEN_ARITH: {
             u64 x, y, z;
-            if (!get(wire(g.row, 4 * g.i), &x) || !get(wire(g.row, 4 * g.i + 1), &y) || !get(wire(g.row, 4 * g.i + 2), &z)) return false;
-            set(wire(g.row, 4 * g.i + 3), gl_add(gl_mul(gl_mul(x, y), g.c0), gl_mul(z, g.c1)));
+            if (!getw(g.row, 4 * g.i, &x) || !getw(g.row, 4 * g.i + 1, &y) || !getw(g.row, 4 * g.i + 2, &z)) return false;
+            setw(g.row, 4 * g.i + 3, gl_add(gl_mul(gl_mul(x, y), g.c0), gl_mul(z, g.c1)));
             return true;
         }
         case GEN_SPLIT: {   // WireSplitGenerator: integer -> the sum wire of each BaseSum row, 63 bits at a time
@@ -538,42 +563,42 @@ struct Builder {
             if (!get(g.t, &x)) return false;
             for (size_t k = 0; k < g.rows.size(); k++) {
                 u64 chunk = (k * g.n >= 64) ? 0 : (x >> (k * g.n)) & (g.n >= 64 ? ~0ULL : (((u64)1 << g.n) - 1));
-                set(wire(g.rows[k], 0), chunk);
+                setw(g.rows[k], 0, chunk);
             }
             return true;
         }
         case GEN_BASE_SPLIT: {   // BaseSplitGenerator: sum -> limbs
             u64 s;
-            if (!get(wire(g.row, 0), &s)) return false;
+            if (!getw(g.row, 0, &s)) return false;
             if (g.c0 == 4) {   // split_le_base::<4>
-                for (int l = 0; l < g.n; l++) set(wire(g.row, 1 + l), l < 32 ? (s >> (2 * l)) & 3 : 0);
+                for (int l = 0; l < g.n; l++) setw(g.row, 1 + l, l < 32 ? (s >> (2 * l)) & 3 : 0);
                 return true;
             }
-            for (int l = 0; l < g.n; l++) set(wire(g.row, 1 + l), l < 64 ? (s >> l) & 1 : 0);
+            for (int l = 0; l < g.n; l++) setw(g.row, 1 + l, l < 64 ? (s >> l) & 1 : 0);
             return true;
         }
         case GEN_BASE_SUM: {   // BaseSumGenerator: limbs -> sum
             u64 s = 0, pw = 1;
             for (int l = 0; l < g.n; l++) {
                 u64 b;
-                if (!get(wire(g.row, 1 + l), &b)) return false;
+                if (!getw(g.row, 1 + l, &b)) return false;
                 s = gl_add(s, gl_mul(b, pw));
                 pw = gl_add(pw, pw);
             }
-            set(wire(g.row, 0), s);
+            setw(g.row, 0, s);
             return true;
         }
         case GEN_RANDOM_ACCESS: {
             const GateType& gt = gate_types[rows[g.row].gate];
             const int bits = gt.params[0], copies = gt.params[1], vec = 1 << bits, base = (2 + vec) * g.i;
             u64 idx;
-            if (!get(wire(g.row, base), &idx)) return false;
+            if (!getw(g.row, base, &idx)) return false;
             if (idx >= (u64)vec) throw Error{"random_access: index out of range"};
             u64 item;
-            if (!get(wire(g.row, base + 2 + (int)idx), &item)) return false;
-            set(wire(g.row, base + 1), item);
+            if (!getw(g.row, base + 2 + (int)idx, &item)) return false;
+            setw(g.row, base + 1, item);
             const int routed_used = (2 + vec) * copies + (int)gt.params[2];
-            for (int b = 0; b < bits; b++) set(wire(g.row, routed_used + g.i * bits + b), (idx >> b) & 1);
+            for (int b = 0; b < bits; b++) setw(g.row, routed_used + g.i * bits + b, (idx >> b) & 1);
             return true;
         }
         case GEN_EQUAL: {
@@ -585,84 +610,84 @@ struct Builder {
         }
         case GEN_U32_ARITH: {   // arithmetic_u32.rs:376-426
             u64 x, y, z;
-            if (!get(wire(g.row, 6 * g.i), &x) || !get(wire(g.row, 6 * g.i + 1), &y) || !get(wire(g.row, 6 * g.i + 2), &z)) return false;
+            if (!getw(g.row, 6 * g.i, &x) || !getw(g.row, 6 * g.i + 1, &y) || !getw(g.row, 6 * g.i + 2, &z)) return false;
             u64 out = gl_add(gl_mul(x, y), z), hi = out >> 32, lo = out & 0xFFFFFFFFULL;
-            set(wire(g.row, 6 * g.i + 3), lo);
-            set(wire(g.row, 6 * g.i + 4), hi);
+            setw(g.row, 6 * g.i + 3, lo);
+            setw(g.row, 6 * g.i + 4, hi);
             const u64 diff = 0xFFFFFFFFULL - hi;
-            set(wire(g.row, 6 * g.i + 5), diff ? gl_inv(diff) : 0);
-            for (int j = 0; j < 32; j++) set(wire(g.row, 6 * g.n + 32 * g.i + j), (out >> (2 * j)) & 3);
+            setw(g.row, 6 * g.i + 5, diff ? gl_inv(diff) : 0);
+            for (int j = 0; j < 32; j++) setw(g.row, 6 * g.n + 32 * g.i + j, (out >> (2 * j)) & 3);
             return true;
         }
         case GEN_U32_ADD_MANY: {   // add_many_u32.rs:329-375
             const int na = g.n, ops = (int)g.c0, q = (na + 3) * g.i;
             u64 sum = 0, v;
             for (int j = 0; j <= na; j++) {
-                if (!get(wire(g.row, q + j), &v)) return false;
+                if (!getw(g.row, q + j, &v)) return false;
                 sum = gl_add(sum, v);
             }
             const u64 carry = sum >> 32, res = sum & 0xFFFFFFFFULL;
-            set(wire(g.row, q + na + 1), res);
-            set(wire(g.row, q + na + 2), carry);
+            setw(g.row, q + na + 1, res);
+            setw(g.row, q + na + 2, carry);
             const int lw = (na + 3) * ops + 18 * g.i;
-            for (int j = 0; j < 16; j++) set(wire(g.row, lw + j), (res >> (2 * j)) & 3);
-            for (int j = 0; j < 2; j++) set(wire(g.row, lw + 16 + j), (carry >> (2 * j)) & 3);
+            for (int j = 0; j < 16; j++) setw(g.row, lw + j, (res >> (2 * j)) & 3);
+            for (int j = 0; j < 2; j++) setw(g.row, lw + 16 + j, (carry >> (2 * j)) & 3);
             return true;
         }
         case GEN_U32_SUB: {   // subtraction_u32.rs:298-343
             u64 x, y, b;
-            if (!get(wire(g.row, 5 * g.i), &x) || !get(wire(g.row, 5 * g.i + 1), &y) || !get(wire(g.row, 5 * g.i + 2), &b)) return false;
+            if (!getw(g.row, 5 * g.i, &x) || !getw(g.row, 5 * g.i + 1, &y) || !getw(g.row, 5 * g.i + 2, &b)) return false;
             const u64 init = gl_sub(gl_sub(x, y), b);
             const u64 bout = init > (1ULL << 32) ? 1 : 0;
             const u64 res = gl_add(init, bout ? (1ULL << 32) : 0);
-            set(wire(g.row, 5 * g.i + 3), res);
-            set(wire(g.row, 5 * g.i + 4), bout);
-            for (int j = 0; j < 16; j++) set(wire(g.row, 5 * g.n + 16 * g.i + j), (res >> (2 * j)) & 3);
+            setw(g.row, 5 * g.i + 3, res);
+            setw(g.row, 5 * g.i + 4, bout);
+            for (int j = 0; j < 16; j++) setw(g.row, 5 * g.n + 16 * g.i + j, (res >> (2 * j)) & 3);
             return true;
         }
         case GEN_U32_RANGE: {   // range_check_u32.rs:198-220
             for (int i = 0; i < g.n; i++) {
                 u64 v;
-                if (!get(wire(g.row, i), &v)) return false;
+                if (!getw(g.row, i, &v)) return false;
                 const u32 v32 = (u32)v;
-                for (int j = 0; j < 16; j++) set(wire(g.row, g.n + 16 * i + j), (v32 >> (2 * j)) & 3);
+                for (int j = 0; j < 16; j++) setw(g.row, g.n + 16 * i + j, (v32 >> (2 * j)) & 3);
             }
             return true;
         }
         case GEN_COMPARISON: {   // comparison.rs:439-537
             const int nc = g.i, cb = (g.n + nc - 1) / nc;
             u64 a, b;
-            if (!get(wire(g.row, 0), &a) || !get(wire(g.row, 1), &b)) return false;
-            set(wire(g.row, 2), a <= b ? 1 : 0);
+            if (!getw(g.row, 0, &a) || !getw(g.row, 1, &b)) return false;
+            setw(g.row, 2, a <= b ? 1 : 0);
             const u64 cs = 1ULL << cb;
             u64 msd = 0;
             for (int i = 0; i < nc; i++) {
                 const u64 fa = (a >> (cb * i)) & (cs - 1), fb = (b >> (cb * i)) & (cs - 1);
-                set(wire(g.row, 4 + i), fa);
-                set(wire(g.row, 4 + nc + i), fb);
-                set(wire(g.row, 4 + 2 * nc + i), fa == fb ? 1 : gl_inv(gl_sub(fb, fa)));   // equality dummy
-                set(wire(g.row, 4 + 3 * nc + i), fa == fb ? 1 : 0);                        // chunks equal
+                setw(g.row, 4 + i, fa);
+                setw(g.row, 4 + nc + i, fb);
+                setw(g.row, 4 + 2 * nc + i, fa == fb ? 1 : gl_inv(gl_sub(fb, fa)));   // equality dummy
+                setw(g.row, 4 + 3 * nc + i, fa == fb ? 1 : 0);                        // chunks equal
                 if (fa != fb) {
                     msd = gl_sub(fb, fa);
-                    set(wire(g.row, 4 + 4 * nc + i), 0);
+                    setw(g.row, 4 + 4 * nc + i, 0);
                 } else {
-                    set(wire(g.row, 4 + 4 * nc + i), msd);
+                    setw(g.row, 4 + 4 * nc + i, msd);
                 }
             }
-            set(wire(g.row, 3), msd);
+            setw(g.row, 3, msd);
             const u64 t = gl_add(cs, msd);
-            for (int i = 0; i <= cb; i++) set(wire(g.row, 4 + 5 * nc + i), (t >> i) & 1);
+            for (int i = 0; i <= cb; i++) setw(g.row, 4 + 5 * nc + i, (t >> i) & 1);
             return true;
         }
         case GEN_POSEIDON: {
             u64 st[12];
             for (int i = 0; i < 12; i++)
-                if (!get(wire(g.row, i), &st[i])) return false;
+                if (!getw(g.row, i, &st[i])) return false;
             u64 swap;
-            if (!get(wire(g.row, 24), &swap)) return false;
+            if (!getw(g.row, 24, &swap)) return false;
             for (int i = 0; i < 4; i++) {
                 u64 delta = gl_mul(swap, gl_sub(st[i + 4], st[i]));
-                set(wire(g.row, 25 + i), delta);
+                setw(g.row, 25 + i, delta);
                 st[i] = gl_add(st[i], delta);
                 st[i + 4] = gl_sub(st[i + 4], delta);
             }
@@ -670,23 +695,23 @@ struct Builder {
             for (int r = 0; r < 4; r++, rnd++) {
                 for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC(12 * rnd + i));
                 if (r != 0)
-                    for (int i = 0; i < 12; i++) set(wire(g.row, 29 + 12 * (r - 1) + i), st[i]);
+                    for (int i = 0; i < 12; i++) setw(g.row, 29 + 12 * (r - 1) + i, st[i]);
                 for (int i = 0; i < 12; i++) st[i] = poseidon_sbox(st[i]);
                 poseidon_mds(st);
             }
             for (int r = 0; r < 22; r++, rnd++) {
                 for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC(12 * rnd + i));
-                set(wire(g.row, 65 + r), st[0]);
+                setw(g.row, 65 + r, st[0]);
                 st[0] = poseidon_sbox(st[0]);
                 poseidon_mds(st);
             }
             for (int r = 0; r < 4; r++, rnd++) {
                 for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC(12 * rnd + i));
-                for (int i = 0; i < 12; i++) set(wire(g.row, 87 + 12 * r + i), st[i]);
+                for (int i = 0; i < 12; i++) setw(g.row, 87 + 12 * r + i, st[i]);
                 for (int i = 0; i < 12; i++) st[i] = poseidon_sbox(st[i]);
                 poseidon_mds(st);
             }
-            for (int i = 0; i < 12; i++) set(wire(g.row, 12 + i), gl_canon(st[i]));
+            for (int i = 0; i < 12; i++) setw(g.row, 12 + i, gl_canon(st[i]));
             return true;
         }
         }
@@ -1112,6 +1137,9 @@ int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wire
     Builder& b = T->b;
     try {
         const size_t n = (size_t)1 << b.degree_bits;
+        const bool trace = getenv("P2A_TRACE") != nullptr;
+        auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; };
+        const double t0 = now();
         b.val.assign(b.parent.size(), 0);
         b.has.assign(b.parent.size(), 0);
         b.advice_val.assign(b.rows.size() * (NUM_WIRES - NUM_ROUTED), 0);
@@ -1137,20 +1165,33 @@ int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wire
             }
             if (!pending || !progress) break;
         }
-        memset(wires, 0, (size_t)NUM_WIRES * n * 8);
-        for (size_t r = 0; r < b.rows.size(); r++) {
-            for (int c = 0; c < NUM_ROUTED; c++) {
-                const Target t = b.routed_or_none(r, c);
-                u64 v;
-                if (t >= 0 && b.get(t, &v)) wires[(size_t)c * n + r] = v;
-            }
-            for (int c = NUM_ROUTED; c < NUM_WIRES; c++) wires[(size_t)c * n + r] = b.advice_val[r * (NUM_WIRES - NUM_ROUTED) + c - NUM_ROUTED];
+        const double t1 = now();
+        // the wire matrix is column-major [wire][row]: transpose the row-major tables in blocks of rows (every row < n has a gate)
+        if (b.rows.size() != n) throw Error{"witness generation: the circuit is not padded"};
+        b.grow();
+        const long BLK = 64, nblk = (long)((n + BLK - 1) / BLK);
+#pragma omp parallel for schedule(static)
+        for (long k = 0; k < nblk; k++) {
+            const size_t r0 = (size_t)k * BLK, r1 = std::min(n, r0 + BLK);
+            for (int c = 0; c < NUM_ROUTED; c++)
+                for (size_t r = r0; r < r1; r++) {
+                    const Target t = b.routed_target[r * NUM_ROUTED + c];
+                    u64 v = 0;
+                    if (t >= 0) {
+                        const Target root = b.find_const(t);
+                        if (b.has[root]) v = b.val[root];
+                    }
+                    wires[(size_t)c * n + r] = v;
+                }
+            for (int c = NUM_ROUTED; c < NUM_WIRES; c++)
+                for (size_t r = r0; r < r1; r++) wires[(size_t)c * n + r] = b.advice_val[r * (NUM_WIRES - NUM_ROUTED) + c - NUM_ROUTED];
         }
         for (size_t i = 0; i < b.public_inputs.size(); i++) {
             u64 v;
             if (!b.get(b.public_inputs[i], &v)) throw Error{"public input has no value"};
             public_inputs[i] = v;
         }
+        if (trace) fprintf(stderr, "p2a_witness: %zu generators %.3f s, wire matrix %.3f s\n", b.gens.size(), t1 - t0, now() - t1);
         return 0;
     } catch (const Error& e) {
         g_err = e.msg;

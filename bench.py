@@ -33,6 +33,9 @@ NCU = {"lde_traffic_over_algorithmic": 6.26 / 2.265, "keccak_traffic_over_algori
        "files": ["profiles/r2_ntt_ncu_raw.csv", "profiles/r2_keccak_ncu_raw.csv", "profiles/r2_quotient_ncu_raw.csv", "profiles/r2_launches_bench.csv"]}
 
 
+REAL_WORKLOAD = "ecdsa-real"   # the EcdsaSecp256k1 opcode translated like the reference does (acir/ecdsa.h), not a synthetic gate mix
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -40,7 +43,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="p2g", choices=["p2g", "reference"])
     ap.add_argument("--degree-bits", type=int, default=20)
-    ap.add_argument("--workload", default="ecdsa")
+    ap.add_argument("--workload", default=REAL_WORKLOAD,
+                    help="ecdsa-real (default): BASELINE configs[3] from real opcodes -- the Noir signature-check program on 2^(bits-17) "
+                         "EcdsaSecp256k1 calls, translated like the reference does; ecdsa / sha256 / assert_zero / range: synthetic "
+                         "gate mixes of those shapes (p2g.synth), any size")
     ap.add_argument("--hasher", default="keccak25")
     ap.add_argument("--inflight", type=int, default=2,
                     help="proofs in flight per GPU (one circuit handle + stream + host thread each); a step is still one proof")
@@ -112,9 +118,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-REAL_WORKLOAD = "ecdsa-real"   # the EcdsaSecp256k1 opcode translated like the reference does (acir/ecdsa.h), not a synthetic gate mix
-
-
 def make_workload(p2g, args, bits, seed, pinned=False):
     """The circuit + witness of `--workload` at 2^bits rows: a synthetic gate mix (p2g.synth) or, for `ecdsa-real`, the Noir
     signature-check program on 2^(bits - 17) signatures translated from real opcodes."""
@@ -164,7 +167,7 @@ def cpu_proof(p2g, args, bits, seed, sc=None):
 
 def pick_cpu_sample_bits(p2g, args, target_s):
     if args.cpu_sample_bits:
-        return args.cpu_sample_bits
+        return max(args.cpu_sample_bits, min_sample_bits(args)) if args.workload == REAL_WORKLOAD else args.cpu_sample_bits
     bits = min(min_sample_bits(args), args.degree_bits)
     dt, _, _ = cpu_proof(p2g, args, bits, 1)
     # prover cost is ~linear in rows

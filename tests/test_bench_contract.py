@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line_with_contract_keys():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-sample-bits", "9", "--no-full-size-cpu"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                        "--workload", "ecdsa", "--cpu-sample-bits", "9", "--no-full-size-cpu"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout
@@ -26,7 +26,7 @@ def test_reference_arm_prints_one_json_line_with_contract_keys():
 def test_reference_arm_times_one_real_full_size_proof():
     """The first timed step is a real proof of the arm's own circuit (here 2^12 rows so the test stays short): value = 1 / its time."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                        "--cpu-sample-bits", "9", "--degree-bits", "12"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                        "--workload", "ecdsa", "--cpu-sample-bits", "9", "--degree-bits", "12"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
     assert d["full_size_ms"] > 0 and abs(d["value"] - 1e3 / d["full_size_ms"]) < 1e-9 * d["value"]
