@@ -41,10 +41,16 @@ def _acir_lib():
         L.p2a_constants_sigmas.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.p2a_witness.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.p2a_read_witnesses.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.p2a_set_threads.argtypes = [C.c_int]
         L.p2a_rows_used.argtypes = [C.c_void_p]
         L.p2a_rows_used.restype = C.c_uint32
         _LIB = L
     return _LIB
+
+
+def set_threads(n):
+    """Worker threads of witness generation (generator groups of heavy opcodes run side by side); 0 = all cores."""
+    _acir_lib().p2a_set_threads(int(n))
 
 
 class TranslationError(Exception):

@@ -130,7 +130,7 @@ struct Ecc {
         Gen e = {};
         e.kind = GEN_BIG;
         e.i = (int)b.big_gens.size() - 1;
-        b.gens.push_back(e);
+        b.push_gen(e);
     }
     BigT virtual_biguint(size_t n) {
         BigT t;
@@ -496,6 +496,10 @@ inline BigT bytes32_to_field_element(Translator& T, const u32* byte_witnesses) {
 inline void ecdsa_secp256k1(Translator& T, const u32* public_key_x, const u32* public_key_y, const u32* signature, const u32* hashed_msg,
                             u32 output) {
     Ecc e(T.b);
+    // witness-generation groups (p2a_witness): the two scalar multiplications are independent of each other
+    const int g_pre = T.b.new_group(), g_mul1 = T.b.new_group({g_pre}), g_mul2 = T.b.new_group({g_pre}),
+              g_post = T.b.new_group({g_mul1, g_mul2});
+    T.b.cur_group = g_pre;
     AffinePoint public_key;
     public_key.x = bytes32_to_field_element(T, public_key_x);
     public_key.y = bytes32_to_field_element(T, public_key_y);
@@ -507,9 +511,13 @@ inline void ecdsa_secp256k1(Translator& T, const u32* public_key_x, const u32* p
     BigT u1 = e.mul_nonnative(FIELD_SCALAR, h, s1);
     BigT u2 = e.mul_nonnative(FIELD_SCALAR, r, s1);
     AffinePoint generator = e.constant_affine_point(Big::from_u64_limbs(SECP256K1_GX64, 4), Big::from_u64_limbs(SECP256K1_GY64, 4));
+    T.b.cur_group = g_mul1;
     AffinePoint r_factor_1 = e.glv_mul(generator, u1);
+    T.b.cur_group = g_mul2;
     AffinePoint r_factor_2 = e.glv_mul(public_key, u2);
+    T.b.cur_group = g_post;
     AffinePoint r_point = e.curve_add(r_factor_1, r_factor_2);
     const Target does_signature_verify = e.cmp_biguint(r, r_point.x);
     T.b.connect(does_signature_verify, T.target_for_witness(output));
+    T.b.cur_group = 0;
 }

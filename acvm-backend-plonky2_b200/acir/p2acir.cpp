@@ -33,6 +33,9 @@
 #include "../csrc/hash.cuh"
 #include "../../include/p2g.h"
 #include "bigint.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace {
 
@@ -60,6 +63,7 @@ struct Gen {
     Target t2, t3, t4;  // GEN_EQUAL: y, equal, inv
     std::vector<int> rows;   // GEN_SPLIT: the BaseSum rows
     int n;              // limbs / bits
+    int group = 0;      // generators of one group run in creation order on one thread
     bool done = false;
 };
 
@@ -98,6 +102,16 @@ struct Builder {
     std::map<int, std::pair<int, int>> free_add_many;                     // num_addends -> (row, next op)
     std::vector<Target> public_inputs;
     std::vector<Gen> gens;
+    int cur_group = 0, num_groups = 1;   // witness-generation groups: 0 = light opcodes and build(); heavy opcodes open their own
+    std::vector<std::vector<int>> group_deps = {{}};   // groups (earlier ones) whose generators must have run first
+    int new_group(std::vector<int> deps = {}) {
+        group_deps.push_back(std::move(deps));
+        return num_groups++;
+    }
+    void push_gen(Gen g) {
+        g.group = cur_group;
+        gens.push_back(std::move(g));
+    }
     std::vector<BigGen> big_gens;
     std::unordered_map<Target, u64> target_consts;   // plonky2's targets_to_constants (target_as_constant)
     bool built = false;
@@ -180,7 +194,7 @@ struct Builder {
         g.i = i;
         g.c0 = c0;
         g.c1 = c1;
-        gens.push_back(g);
+        push_gen(g);
         arith_cache[key] = out;
         return out;
     }
@@ -210,7 +224,7 @@ struct Builder {
         g.t2 = y;
         g.t3 = equal;
         g.t4 = inv;
-        gens.push_back(g);
+        push_gen(g);
         Target diff = sub(x, y);
         Target not_equal_check = mul(equal, diff);
         Target diff_normalized = mul(diff, inv);
@@ -244,13 +258,13 @@ struct Builder {
         sg.t = x;
         sg.rows = grows;
         sg.n = SPLIT_LIMBS;
-        gens.push_back(sg);
+        push_gen(sg);
         for (int g : grows) {
             Gen bg = {};
             bg.kind = GEN_BASE_SPLIT;
             bg.row = g;
             bg.n = SPLIT_LIMBS;
-            gens.push_back(bg);
+            push_gen(bg);
         }
         return bits;
     }
@@ -264,7 +278,7 @@ struct Builder {
         g.row = row;
         g.n = num_limbs;
         g.c0 = 4;
-        gens.push_back(g);
+        push_gen(g);
         std::vector<Target> limbs;
         for (int l = 0; l < num_limbs; l++) limbs.push_back(wire(row, 1 + l));
         return limbs;
@@ -279,7 +293,7 @@ struct Builder {
         g.kind = GEN_BASE_SUM;
         g.row = row;
         g.n = (int)bits.size();
-        gens.push_back(g);
+        push_gen(g);
         return wire(row, 0);
     }
     // random_access (gadgets/random_access.rs): RandomAccessGate::new_from_config(bits): copies = min(routed / (2 + 2^bits), ...)
@@ -309,7 +323,7 @@ struct Builder {
         g.row = row;
         g.i = cp;
         g.n = bits;
-        gens.push_back(g);
+        push_gen(g);
         return wire(row, base + 1);
     }
     // ---- the reference's u32 gadgets (plonky2-backend/src/plonky2_ecdsa/biguint/gadgets/{arithmetic_u32,range_check,multiple_comparison}.rs)
@@ -345,7 +359,7 @@ struct Builder {
         g.row = row;
         g.i = i;
         g.n = ops;
-        gens.push_back(g);
+        push_gen(g);
         return {wire(row, 6 * i + 3), wire(row, 6 * i + 4)};
     }
     std::pair<Target, Target> add_u32(Target a, Target b) { return mul_add_u32(a, one(), b); }
@@ -380,7 +394,7 @@ struct Builder {
         g.i = i;
         g.n = na;
         g.c0 = ops;
-        gens.push_back(g);
+        push_gen(g);
         return {wire(row, q + na + 1), wire(row, q + na + 2)};
     }
     // x - y - borrow = result - 2^32 borrow_out
@@ -400,7 +414,7 @@ struct Builder {
         g.row = row;
         g.i = i;
         g.n = ops;
-        gens.push_back(g);
+        push_gen(g);
         return {wire(row, 5 * i + 3), wire(row, 5 * i + 4)};
     }
     void range_check_u32(const std::vector<Target>& vals) {   // range_check.rs: one U32RangeCheckGate for the whole vector
@@ -412,7 +426,7 @@ struct Builder {
         g.kind = GEN_U32_RANGE;
         g.row = row;
         g.n = n;
-        gens.push_back(g);
+        push_gen(g);
     }
     Target cmp_le(Target a, Target b, int num_bits) {   // multiple_comparison.rs list_le_circuit for one pair: ComparisonGate, 2-bit chunks
         const int nc = (num_bits + 1) / 2, row = add_gate(gate_type(P2G_GATE_COMPARISON, num_bits, nc));
@@ -423,7 +437,7 @@ struct Builder {
         g.row = row;
         g.n = num_bits;
         g.i = nc;
-        gens.push_back(g);
+        push_gen(g);
         return wire(row, 2);
     }
     void register_public_input(Target t) { public_inputs.push_back(t); }
@@ -443,7 +457,7 @@ struct Builder {
             Gen g = {};
             g.kind = GEN_POSEIDON;
             g.row = row;
-            gens.push_back(g);
+            push_gen(g);
             for (int i = 0; i < 12; i++) state[i] = wire(row, 12 + i);
         }
         const int pi_row = add_gate(gate_type(P2G_GATE_PUBLIC_INPUT));
@@ -465,7 +479,7 @@ struct Builder {
                 g.row = row;
                 g.i = (int)(i - off);
                 g.c0 = constant_order[i];
-                gens.push_back(g);
+                push_gen(g);
             }
         }
         // pad with NoopGate to a power of two (at least 2^2 rows so that the LDE has 2^cap_height leaves)
@@ -475,74 +489,120 @@ struct Builder {
         while (rows.size() < n) add_gate(noop);
         degree_bits = 0;
         while (((size_t)1 << degree_bits) < n) degree_bits++;
+        cur_group = 0;
+        finalize();
         built = true;
     }
 
     // ---- witness generation: plonky2 iop/generator.rs generate_partial_witness restricted to the generators above.
-    // values are kept per copy-constraint class (PartitionWitness); a class set twice with different values is an unsatisfied
-    // copy constraint -- plonky2 panics there, this returns an error.
-    std::vector<u64> val, advice_val;   // per target class; per advice wire [row * 154 + col - 80]
-    std::vector<char> has, advice_has;
-    void grow() {   // generators touch routed wires nobody referenced before: they become targets now
-        if (val.size() < parent.size()) {
-            val.resize(parent.size(), 0);
-            has.resize(parent.size(), 0);
+    // Values are kept per copy-constraint class (PartitionWitness); a class set twice with different values is an unsatisfied
+    // copy constraint -- plonky2 panics there, this returns an error.  Wires that are no target (the advice columns, and routed
+    // wires nothing was ever connected to) live in a dense per-cell table.  Nothing below creates targets or touches the
+    // union-find, so generators of different groups can run on different threads: a class is claimed with a compare-exchange on
+    // its flag (0 empty, 2 being written, 1 ready).
+    std::vector<Target> root;          // flattened union-find (finalize())
+    std::vector<Target> routed_root;   // [row * 80 + col] -> class root or -1
+    template <typename E>
+    struct ZeroBuf {   // calloc'ed: the pages are zero-filled by the kernel when first touched (by whichever thread gets there)
+        E* p = nullptr;
+        size_t n = 0;
+        ~ZeroBuf() { free(p); }
+        void reset(size_t count) {
+            free(p);
+            n = count;
+            p = (E*)calloc(count ? count : 1, sizeof(E));
+            if (!p) throw Error{"witness generation: out of memory"};
+        }
+        bool empty() const { return n == 0; }
+        E& operator[](size_t i) { return p[i]; }
+        const E& operator[](size_t i) const { return p[i]; }
+    };
+    ZeroBuf<u64> val, cell_val;    // per class root; per wire [row * 234 + col]
+    ZeroBuf<unsigned char> has, cell_has;
+    std::vector<std::vector<u32>> group_gens;   // generator indices per group, creation order; group 0 = everything light
+    std::vector<int> group_order;               // groups sorted by dependency level: the order the worker threads take them in
+    std::vector<u32> const_gens;
+    void finalize() {
+        root.resize(parent.size());
+        for (Target t = 0; t < (Target)parent.size(); t++) root[t] = find(t);
+        routed_root.assign(routed_target.size(), -1);
+        for (size_t k = 0; k < routed_target.size(); k++)
+            if (routed_target[k] >= 0) routed_root[k] = root[routed_target[k]];
+        group_gens.assign(num_groups, {});
+        std::vector<int> level(num_groups, 0);
+        for (int g = 0; g < num_groups; g++)
+            for (int d : group_deps[g]) level[g] = std::max(level[g], level[d] + 1);   // deps point to earlier groups
+        group_order.resize(num_groups);
+        for (int g = 0; g < num_groups; g++) group_order[g] = g;
+        std::stable_sort(group_order.begin(), group_order.end(), [&](int x, int y) { return level[x] < level[y]; });
+        const_gens.clear();
+        for (size_t i = 0; i < gens.size(); i++) {
+            if (gens[i].kind == GEN_CONST) const_gens.push_back((u32)i);
+            else group_gens[gens[i].group].push_back((u32)i);
         }
     }
-    static size_t advice_index(Target t) {
-        const size_t code = (size_t)(-2 - t), row = code / NUM_WIRES, col = code % NUM_WIRES;
-        return row * (NUM_WIRES - NUM_ROUTED) + (col - NUM_ROUTED);
+    void reset_witness() {
+        val.reset(parent.size());
+        has.reset(parent.size());
+        cell_val.reset(rows.size() * NUM_WIRES);
+        cell_has.reset(rows.size() * NUM_WIRES);
+        for (auto& g : gens) g.done = false;
     }
-    void set(Target t, u64 v) {
-        if (t < 0) {   // advice wire: written once by the generator of its own gate
-            const size_t k = advice_index(t);
-            advice_has[k] = 1;
-            advice_val[k] = v;
+    void set_class(Target r, u64 v) {
+        unsigned char expected = 0;
+        if (__atomic_compare_exchange_n(&has.p[r], &expected, (unsigned char)2, false, __ATOMIC_ACQUIRE, __ATOMIC_ACQUIRE)) {
+            val[r] = v;
+            __atomic_store_n(&has.p[r], (unsigned char)1, __ATOMIC_RELEASE);
             return;
         }
-        grow();
-        Target r = find(t);
-        if (has[r]) {
-            if (val[r] != v) throw Error{"witness generation: a copy-constrained target was set twice with different values (unsatisfiable witness)"};
-            return;
+        while (__atomic_load_n(&has.p[r], __ATOMIC_ACQUIRE) != 1) {
         }
-        has[r] = 1;
-        val[r] = v;
+        if (val[r] != v) throw Error{"witness generation: a copy-constrained target was set twice with different values (unsatisfiable witness)"};
     }
-    bool get(Target t, u64* v) {
-        if (t < 0) {
-            const size_t k = advice_index(t);
-            *v = advice_val[k];
-            return advice_has[k] != 0;
-        }
-        grow();
-        Target r = find(t);
-        if (!has[r]) return false;
+    bool get_class(Target r, u64* v) const {
+        if (__atomic_load_n(&has.p[r], __ATOMIC_ACQUIRE) != 1) return false;
         *v = val[r];
         return true;
     }
-    // gate-local wire access for the generators: advice columns go straight to the dense table
+    void set(Target t, u64 v) {
+        if (t < 0) {   // advice wire named through wire()
+            const size_t k = (size_t)(-2 - t);
+            cell_val[k] = v;
+            cell_has[k] = 1;
+            return;
+        }
+        set_class(root[t], v);
+    }
+    bool get(Target t, u64* v) const {
+        if (t < 0) {
+            const size_t k = (size_t)(-2 - t);
+            *v = cell_val[k];
+            return cell_has[k] != 0;
+        }
+        return get_class(root[t], v);
+    }
+    // gate-local wire access for the generators
     void setw(int row, int col, u64 v) {
-        if (col >= NUM_ROUTED) {
-            const size_t k = (size_t)row * (NUM_WIRES - NUM_ROUTED) + (col - NUM_ROUTED);
-            advice_has[k] = 1;
-            advice_val[k] = v;
-        } else {
-            set(wire(row, col), v);
+        const Target r = col < NUM_ROUTED ? routed_root[(size_t)row * NUM_ROUTED + col] : -1;
+        if (r >= 0) {
+            set_class(r, v);
+            return;
         }
+        const size_t k = (size_t)row * NUM_WIRES + col;
+        cell_val[k] = v;
+        cell_has[k] = 1;
     }
-    bool getw(int row, int col, u64* v) {
-        if (col >= NUM_ROUTED) {
-            const size_t k = (size_t)row * (NUM_WIRES - NUM_ROUTED) + (col - NUM_ROUTED);
-            *v = advice_val[k];
-            return advice_has[k] != 0;
-        }
-        const Target t = routed_target[(size_t)row * NUM_ROUTED + col];
-        return t >= 0 && get(t, v);
+    bool getw(int row, int col, u64* v) const {
+        const Target r = col < NUM_ROUTED ? routed_root[(size_t)row * NUM_ROUTED + col] : -1;
+        if (r >= 0) return get_class(r, v);
+        const size_t k = (size_t)row * NUM_WIRES + col;
+        *v = cell_val[k];
+        return cell_has[k] != 0;
     }
-    Target find_const(Target t) const {
-        while (parent[t] != t) t = parent[t];
-        return t;
+    u64 wire_value(size_t row, int col) const {   // full_witness(): unset wires read as zero
+        const Target r = col < NUM_ROUTED ? routed_root[row * NUM_ROUTED + col] : -1;
+        if (r >= 0) return has[r] == 1 ? val[r] : 0;
+        return cell_val[row * NUM_WIRES + col];
     }
     bool run_big(BigGen& g);
     bool run(Gen& g) {
@@ -1030,7 +1090,9 @@ void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size
         case OP_SHA256_COMPRESSION: {
             u32 ws[32];
             for (int i = 0; i < 32; i++) ws[i] = (u32)next();
+            b.cur_group = b.new_group();   // heavy opcode: its generators form a group of their own (p2a_witness)
             sha256_compression(T, ws, ws + 16, ws + 24);
+            b.cur_group = 0;
             break;
         }
         default: throw Error{"Opcode not supported yet: " + std::to_string(op)};
@@ -1105,23 +1167,23 @@ int p2a_constants_sigmas(void* h, const p2g_gate* gates, u32 ngates, const u32* 
             subgroup[r] = x;
             x = gl_mul(x, w);
         }
-        std::unordered_map<Target, std::vector<u32>> classes;   // representative -> wires (row * 80 + col) in row-major order
-        for (size_t r = 0; r < n; r++)
-            for (int c = 0; c < NUM_ROUTED; c++) {
-                const Target t = b.routed_or_none(r, c);
-                if (t < 0) continue;   // never connected: fixed point
-                classes[b.find(t)].push_back((u32)(r * NUM_ROUTED + c));
-            }
         u64* sig = out + (size_t)num_constants * n;
-        for (size_t r = 0; r < n; r++)
-            for (int c = 0; c < NUM_ROUTED; c++) sig[(size_t)c * n + r] = gl_mul(k_is[c], subgroup[r]);
-        for (auto& kv : classes) {
-            const std::vector<u32>& ws = kv.second;
-            for (size_t i = 0; i < ws.size(); i++) {
-                const u32 from = ws[i], to = ws[(i + 1) % ws.size()];
-                sig[(size_t)(from % NUM_ROUTED) * n + from / NUM_ROUTED] = gl_mul(k_is[to % NUM_ROUTED], subgroup[to / NUM_ROUTED]);
-            }
+#pragma omp parallel for schedule(static)
+        for (int c = 0; c < NUM_ROUTED; c++)
+            for (size_t r = 0; r < n; r++) sig[(size_t)c * n + r] = gl_mul(k_is[c], subgroup[r]);
+        // walk the routed wires in row-major order, chaining each to the previous wire of its class; close every cycle at the end
+        const u32 NONE = 0xFFFFFFFFu;
+        std::vector<u32> first(b.parent.size(), NONE), last(b.parent.size(), NONE);
+        auto link = [&](u32 from, u32 to) { sig[(size_t)(from % NUM_ROUTED) * n + from / NUM_ROUTED] = gl_mul(k_is[to % NUM_ROUTED], subgroup[to / NUM_ROUTED]); };
+        for (size_t pos = 0; pos < b.routed_root.size(); pos++) {
+            const Target t = b.routed_root[pos];
+            if (t < 0) continue;   // never connected: fixed point
+            if (first[t] == NONE) first[t] = (u32)pos;
+            else link(last[t], (u32)pos);
+            last[t] = (u32)pos;
         }
+        for (size_t t = 0; t < first.size(); t++)
+            if (first[t] != NONE) link(last[t], first[t]);
         return 0;
     } catch (const Error& e) {
         g_err = e.msg;
@@ -1140,58 +1202,87 @@ int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wire
         const bool trace = getenv("P2A_TRACE") != nullptr;
         auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; };
         const double t0 = now();
-        b.val.assign(b.parent.size(), 0);
-        b.has.assign(b.parent.size(), 0);
-        b.advice_val.assign(b.rows.size() * (NUM_WIRES - NUM_ROUTED), 0);
-        b.advice_has.assign(b.rows.size() * (NUM_WIRES - NUM_ROUTED), 0);
-        for (auto& g : b.gens) g.done = false;
+        b.reset_witness();
         for (size_t i = 0; i < nw; i++) {
             if (values[i] >= GL_P) throw Error{"witness value is not canonical"};
             auto it = T->witness_target_map.find((u32)ids[i]);
             if (it == T->witness_target_map.end()) continue;   // a witness the circuit never mentions (Brillig intermediates)
             b.set(it->second, values[i]);
         }
-        // run the generators to a fixed point (plonky2 keeps watch lists; a handful of sweeps suffice for forward-built circuits)
-        for (int sweep = 0; sweep < 64; sweep++) {
-            bool progress = false, pending = false;
+        for (u32 i : b.const_gens) b.gens[i].done = b.run(b.gens[i]);
+        // Rounds over the groups: one thread walks a group's generators in creation order (the order plonky2's queue would
+        // reach them in), different groups run side by side; a generator whose inputs another group has not produced yet stays
+        // pending for the next round.  Whatever is still pending after the rounds is swept sequentially to a fixed point.
+        std::string first_error;
+        size_t pending = 0;
+        int rounds = 0;
+        for (; rounds < 12; rounds++) {
+            long progress = 0;
+            pending = 0;
+            // work queue in dependency-level order; a thread that takes a group first waits for the groups it depends on (they
+            // were handed out earlier, so some other thread is running them)
+            std::vector<unsigned char> group_done(b.num_groups, 0);
+            long next_slot = 0;
+#pragma omp parallel reduction(+ : progress, pending)
+            for (;;) {
+                const long slot = __atomic_fetch_add(&next_slot, 1, __ATOMIC_RELAXED);
+                if (slot >= (long)b.group_order.size()) break;
+                const int gi = b.group_order[slot];
+                for (int d : b.group_deps[gi])
+                    while (!__atomic_load_n(&group_done[d], __ATOMIC_ACQUIRE)) {
+                    }
+                try {
+                    for (u32 i : b.group_gens[gi]) {
+                        Gen& g = b.gens[i];
+                        if (g.done) continue;
+                        if (b.run(g)) {
+                            g.done = true;
+                            progress++;
+                        } else {
+                            pending++;
+                        }
+                    }
+                } catch (const Error& e) {
+#pragma omp critical
+                    if (first_error.empty()) first_error = e.msg;
+                }
+                __atomic_store_n(&group_done[gi], (unsigned char)1, __ATOMIC_RELEASE);
+            }
+            if (!first_error.empty()) throw Error{first_error};
+            if (!pending || !progress) break;
+        }
+        for (int sweep = 0; pending && sweep < 64; sweep++) {
+            bool progress = false;
+            pending = 0;
             for (auto& g : b.gens) {
                 if (g.done) continue;
                 if (b.run(g)) {
                     g.done = true;
                     progress = true;
                 } else {
-                    pending = true;
+                    pending++;
                 }
             }
-            if (!pending || !progress) break;
+            if (!progress) break;
         }
         const double t1 = now();
         // the wire matrix is column-major [wire][row]: transpose the row-major tables in blocks of rows (every row < n has a gate)
         if (b.rows.size() != n) throw Error{"witness generation: the circuit is not padded"};
-        b.grow();
         const long BLK = 64, nblk = (long)((n + BLK - 1) / BLK);
 #pragma omp parallel for schedule(static)
         for (long k = 0; k < nblk; k++) {
             const size_t r0 = (size_t)k * BLK, r1 = std::min(n, r0 + BLK);
-            for (int c = 0; c < NUM_ROUTED; c++)
-                for (size_t r = r0; r < r1; r++) {
-                    const Target t = b.routed_target[r * NUM_ROUTED + c];
-                    u64 v = 0;
-                    if (t >= 0) {
-                        const Target root = b.find_const(t);
-                        if (b.has[root]) v = b.val[root];
-                    }
-                    wires[(size_t)c * n + r] = v;
-                }
-            for (int c = NUM_ROUTED; c < NUM_WIRES; c++)
-                for (size_t r = r0; r < r1; r++) wires[(size_t)c * n + r] = b.advice_val[r * (NUM_WIRES - NUM_ROUTED) + c - NUM_ROUTED];
+            for (int c = 0; c < NUM_WIRES; c++)
+                for (size_t r = r0; r < r1; r++) wires[(size_t)c * n + r] = b.wire_value(r, c);
         }
         for (size_t i = 0; i < b.public_inputs.size(); i++) {
             u64 v;
             if (!b.get(b.public_inputs[i], &v)) throw Error{"public input has no value"};
             public_inputs[i] = v;
         }
-        if (trace) fprintf(stderr, "p2a_witness: %zu generators %.3f s, wire matrix %.3f s\n", b.gens.size(), t1 - t0, now() - t1);
+        if (trace)
+            fprintf(stderr, "p2a_witness: %zu generators in %d groups, %d rounds, %.3f s (%zu left unset); wire matrix %.3f s\n", b.gens.size(),
+                    b.num_groups, rounds + 1, t1 - t0, pending, now() - t1);
         return 0;
     } catch (const Error& e) {
         g_err = e.msg;
@@ -1206,9 +1297,17 @@ void p2a_read_witnesses(void* h, const u64* ids, size_t n, u64* values, uint8_t*
     for (size_t i = 0; i < n; i++) {
         auto it = T->witness_target_map.find((u32)ids[i]);
         u64 v = 0;
-        known[i] = it != T->witness_target_map.end() && !T->b.val.empty() && T->b.get(it->second, &v);
+        known[i] = it != T->witness_target_map.end() && !T->b.has.empty() && T->b.get(it->second, &v);
         values[i] = v;
     }
+}
+// worker threads for witness generation and the preprocessed-polynomial fill (0 = OpenMP's default)
+void p2a_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+    (void)n;
+#endif
 }
 // rows in use before the power-of-two padding
 u32 p2a_rows_used(void* h) {

@@ -98,3 +98,23 @@ def test_ecdsa_circuit_from_the_opcode_proves_and_verifies(p2g, corc):
                 break
         _, badwit, _ = EI.circuit_and_witness(A, [(q, r, s, h ^ 1)], outputs=[1], assert_valid=True)
         tr.generate_witness(badwit)
+
+
+def test_witness_generation_is_the_same_on_one_thread_and_on_many(p2g):
+    """The generators of the two scalar multiplications of every EcdsaSecp256k1 opcode (and of different opcodes) run on different
+    threads, claiming copy classes with a compare-exchange: the wire matrix must not depend on the schedule."""
+    import numpy as np
+    A, EI = p2g.acir, p2g.ecdsa_inputs
+    circuit, wit, outs = EI.circuit_and_witness(A, [EI.deterministic_case(i) for i in (11, 12)], range_checks=True)
+    tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    try:
+        A.set_threads(1)
+        w1, _ = tr.generate_witness(wit)
+        o1 = tr.read_witnesses(outs)
+        A.set_threads(0)
+        for _ in range(2):
+            wn, _ = tr.generate_witness(wit)
+            assert np.array_equal(w1, wn) and tr.read_witnesses(outs) == o1
+    finally:
+        A.set_threads(0)
+    assert list(o1.values()) == [1, 1]
