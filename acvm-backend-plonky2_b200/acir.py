@@ -169,6 +169,19 @@ class CmpLe:          # result = (a <= b) on num_bits-bit values  (ComparisonGat
     result: int
 
 
+GADGET_KINDS = {"add_biguint": 1, "sub_biguint": 2, "mul_biguint": 3, "cmp_biguint": 4, "div_rem_biguint": 5, "add_nonnative": 6,
+                "sub_nonnative": 7, "mul_nonnative": 8, "neg_nonnative": 9, "inv_nonnative": 10, "add_many_nonnative": 11, "list_le": 12,
+                "glv_mul": 13, "curve_add": 14, "curve_double": 15}
+BASE_FIELD, SCALAR_FIELD = 0, 1
+
+
+@dataclass
+class Gadget:         # a plonky2_ecdsa gadget on u32-limb witnesses (least significant limb first); see p2acir.cpp opcode 110
+    name: str         # one of GADGET_KINDS
+    lists: list       # operand and result witness-id lists, in the gadget's order
+    param: int = 0    # non-native gadgets: BASE_FIELD / SCALAR_FIELD; list_le: bits per element
+
+
 @dataclass
 class Circuit:
     opcodes: list
@@ -198,6 +211,10 @@ def _encode(circuit):
             words += [6, op.block_id, op.index, op.value]
         elif isinstance(op, MemoryWrite):
             words += [8, op.block_id, op.index, op.value]
+        elif isinstance(op, Gadget):
+            words += [110, GADGET_KINDS[op.name], op.param, len(op.lists)]
+            for l in op.lists:
+                words += [len(l)] + list(l)
         elif isinstance(op, EcdsaSecp256k1):
             if (len(op.public_key_x), len(op.public_key_y), len(op.signature), len(op.hashed_message)) != (32, 32, 64, 32):
                 raise TranslationError("EcdsaSecp256k1 takes 32 + 32 + 64 + 32 byte witnesses")

@@ -59,9 +59,24 @@ inline bool Builder::run_big(BigGen& g) {
         if (t.size() < v.d.size()) throw Error{"witness generation: big integer does not fit its target"};
         for (size_t i = 0; i < t.size(); i++) set(t[i], v.limb(i));
     };
+    const Big m = field_order(g.field);
+    if (g.kind == BG_NN_ADD_MANY) {   // nonnative.rs:527-552; g.b holds the end offset of each summand inside g.a
+        Big sum;
+        size_t lo = 0;
+        for (Target end : g.b) {
+            Big v;
+            if (!get_big(BigT(g.a.begin() + lo, g.a.begin() + end), &v)) return false;
+            sum = big_add(sum, big_mod(v, m));
+            lo = (size_t)end;
+        }
+        Big q, r;
+        big_divrem(sum, m, &q, &r);
+        set_big(g.o1, r);
+        set(g.t1, q.limb(0));
+        return true;
+    }
     Big a, b;
     if (!get_big(g.a, &a) || !get_big(g.b, &b)) return false;
-    const Big m = field_order(g.field);
     switch (g.kind) {
     case BG_DIVREM: {   // biguint.rs:311-318
         if (b.is_zero()) throw Error{"witness generation: division by zero"};
@@ -103,6 +118,7 @@ inline bool Builder::run_big(BigGen& g) {
         set_big(g.o1, inv);
         return true;
     }
+    case BG_NN_ADD_MANY: return false;   // handled above
     case BG_GLV: {   // glv.rs:272-285
         Big k1, k2;
         bool n1, n2;
@@ -252,6 +268,31 @@ struct Ecc {
         BigT sum_expected = add_biguint(x, y);
         BigT modulus = constant_biguint(field_order(f));
         BigT mod_times_overflow = mul_biguint_by_bool(modulus, overflow);
+        BigT sum_actual = add_biguint(sum, mod_times_overflow);
+        connect_biguint(sum_expected, sum_actual);
+        b.connect(cmp_biguint(sum, modulus), b.one());
+        return sum;
+    }
+    BigT add_many_nonnative(int f, const std::vector<BigT>& to_add) {   // :250-284 (not used by the ECDSA translator)
+        if (to_add.size() == 1) return to_add[0];
+        BigT sum = virtual_biguint(8);
+        const Target overflow = b.add_virtual_target();
+        BigGen g = {};
+        g.kind = BG_NN_ADD_MANY;
+        g.field = f;
+        for (const BigT& t : to_add) {   // the summands, concatenated; b records where each ends
+            g.a.insert(g.a.end(), t.begin(), t.end());
+            g.b.push_back((Target)g.a.size());
+        }
+        g.o1 = sum;
+        g.t1 = overflow;
+        add_big_gen(g);
+        b.range_check_u32(sum);
+        b.range_check_u32({overflow});
+        BigT sum_expected = constant_biguint(Big());
+        for (const BigT& t : to_add) sum_expected = add_biguint(sum_expected, t);
+        BigT modulus = constant_biguint(field_order(f));
+        BigT mod_times_overflow = mul_biguint(modulus, BigT{overflow});
         BigT sum_actual = add_biguint(sum, mod_times_overflow);
         connect_biguint(sum_expected, sum_actual);
         b.connect(cmp_biguint(sum, modulus), b.one());

@@ -74,7 +74,7 @@ struct Error {
 // generators over big integers (plonky2_ecdsa: BigUintDivRemGenerator, NonNative{Addition,Subtraction,Multiplication,Inverse}Generator,
 // GLVDecompositionGenerator): kept in a side table, Gen::i indexes it
 typedef std::vector<Target> BigT;   // BigUintTarget: u32 limbs, least significant first
-enum BigGenKind { BG_DIVREM, BG_NN_ADD, BG_NN_SUB, BG_NN_MUL, BG_NN_INV, BG_GLV };
+enum BigGenKind { BG_DIVREM, BG_NN_ADD, BG_NN_ADD_MANY, BG_NN_SUB, BG_NN_MUL, BG_NN_INV, BG_GLV };
 struct BigGen {
     BigGenKind kind;
     int field;        // 0: secp256k1 base field, 1: scalar field
@@ -950,8 +950,79 @@ void assert_less_or_equal(Builder& b, size_t max_allowed, Target index) {
 // a circuit be built directly on the reference's u32 gadgets, like its gadget tests do).  Witness ids name the targets.
 // 101 MulAddU32: x, y, z, low, high      102 AddManyU32: n, n addends, result, carry      103 SubU32: x, y, borrow, result, borrow_out
 // 104 RangeCheckU32: n, n values         105 CmpLe: a, b, num_bits, result
+// 110 Gadget: kind, param, number of lists, then (length, witness ids...) per list -- the biguint / non-native / comparison gadgets of
+//     plonky2_ecdsa on u32-limb witnesses (least significant limb first), as its gadget tests drive them.  kind: 1 add_biguint [a, b, out]
+//     2 sub_biguint [a, b, out]  3 mul_biguint [a, b, out]  4 cmp_biguint [a, b, [result]]  5 div_rem_biguint [a, b, div, rem]
+//     6 add_nonnative  7 sub_nonnative  8 mul_nonnative [a, b, out]  9 neg_nonnative  10 inv_nonnative [a, out]
+//     11 add_many_nonnative [summand..., out]  12 list_le [a, b, [result]] (param = bits per element)
+//     13 glv_mul [px, py, k, outx, outy]  14 curve_add [p1x, p1y, p2x, p2y, outx, outy]  15 curve_double [px, py, outx, outy]
+//     param for 6..11: 0 = secp256k1 base field, 1 = scalar field
 enum { OP_ASSERT_ZERO = 1, OP_RANGE = 2, OP_AND = 3, OP_XOR = 4, OP_MEM_INIT = 5, OP_MEM_READ = 6, OP_SHA256_COMPRESSION = 7, OP_MEM_WRITE = 8, OP_ECDSA_SECP256K1 = 9,
-       OP_MUL_ADD_U32 = 101, OP_ADD_MANY_U32 = 102, OP_SUB_U32 = 103, OP_RANGE_CHECK_U32 = 104, OP_CMP_LE = 105 };
+       OP_MUL_ADD_U32 = 101, OP_ADD_MANY_U32 = 102, OP_SUB_U32 = 103, OP_RANGE_CHECK_U32 = 104, OP_CMP_LE = 105, OP_GADGET = 110 };
+
+// gadget-level operations on limb witnesses (opcode 110): what the reference's gadget tests exercise
+void gadget(Translator& T, int kind, int param, const std::vector<std::vector<u32>>& lists) {
+    Ecc e(T.b);
+    auto in = [&](size_t k) {
+        if (k >= lists.size()) throw Error{"Gadget: missing operand list"};
+        BigT t;
+        for (u32 w : lists[k]) t.push_back(T.target_for_witness(w));
+        return t;
+    };
+    auto out = [&](size_t k, const BigT& v) {   // bind the result limbs to witness ids; missing high limbs must be zero
+        if (k >= lists.size()) throw Error{"Gadget: missing result list"};
+        if (lists[k].size() > v.size()) throw Error{"Gadget: result list longer than the result (" + std::to_string(v.size()) + " limbs)"};
+        for (size_t i = 0; i < v.size(); i++) {
+            if (i < lists[k].size()) T.witness_target_map[lists[k][i]] = v[i];
+            else T.b.assert_zero(v[i]);
+        }
+    };
+    const int f = param ? FIELD_SCALAR : FIELD_BASE;
+    switch (kind) {
+    case 1: out(2, e.add_biguint(in(0), in(1))); break;
+    case 2: out(2, e.sub_biguint(in(0), in(1))); break;
+    case 3: out(2, e.mul_biguint(in(0), in(1))); break;
+    case 4: out(2, BigT{e.cmp_biguint(in(0), in(1))}); break;
+    case 5: {
+        auto qr = e.div_rem_biguint(in(0), in(1));
+        out(2, qr.first);
+        out(3, qr.second);
+        break;
+    }
+    case 6: out(2, e.add_nonnative(f, in(0), in(1))); break;
+    case 7: out(2, e.sub_nonnative(f, in(0), in(1))); break;
+    case 8: out(2, e.mul_nonnative(f, in(0), in(1))); break;
+    case 9: out(1, e.neg_nonnative(f, in(0))); break;
+    case 10: out(1, e.inv_nonnative(f, in(0))); break;
+    case 11: {
+        std::vector<BigT> summands;
+        for (size_t k = 0; k + 1 < lists.size(); k++) summands.push_back(in(k));
+        if (summands.empty()) throw Error{"Gadget: add_many_nonnative without summands"};
+        out(lists.size() - 1, e.add_many_nonnative(f, summands));
+        break;
+    }
+    case 12: out(2, BigT{e.list_le(in(0), in(1), param)}); break;
+    case 13: {
+        AffinePoint r = e.glv_mul({in(0), in(1)}, in(2));
+        out(3, r.x);
+        out(4, r.y);
+        break;
+    }
+    case 14: {
+        AffinePoint r = e.curve_add({in(0), in(1)}, {in(2), in(3)});
+        out(4, r.x);
+        out(5, r.y);
+        break;
+    }
+    case 15: {
+        AffinePoint r = e.curve_double({in(0), in(1)});
+        out(2, r.x);
+        out(3, r.y);
+        break;
+    }
+    default: throw Error{"Gadget: unknown kind " + std::to_string(kind)};
+    }
+}
 
 void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size_t npriv, const u64* ops, size_t nwords) {
     Builder& b = T.b;
@@ -1079,6 +1150,16 @@ void translate(Translator& T, const u64* pub, size_t npub, const u64* priv, size
             const u64 x = next(), y = next(), bits = next(), res = next();
             if (bits == 0 || bits > 32) throw Error{"CmpLe: 1..32 bits"};
             T.witness_target_map[(u32)res] = b.cmp_le(T.target_for_witness((u32)x), T.target_for_witness((u32)y), (int)bits);
+            break;
+        }
+        case OP_GADGET: {
+            const u64 kind = next(), param = next(), nlists = next();
+            std::vector<std::vector<u32>> lists(nlists);
+            for (auto& l : lists) {
+                const u64 len = next();
+                for (u64 i = 0; i < len; i++) l.push_back((u32)next());
+            }
+            gadget(T, (int)kind, (int)param, lists);
             break;
         }
         case OP_ECDSA_SECP256K1: {
