@@ -169,6 +169,16 @@ class CmpLe:          # result = (a <= b) on num_bits-bit values  (ComparisonGat
     result: int
 
 
+@dataclass
+class BrilligCall:    # Opcode::BrilligCall { .. }: unconstrained code, "ignored since it has no impact in the circuit" (mod.rs:97-103)
+    id: int = 0
+
+
+@dataclass
+class Directive:      # Opcode::Directive(_): ignored as well (mod.rs:104)
+    name: str = ""
+
+
 GADGET_KINDS = {"add_biguint": 1, "sub_biguint": 2, "mul_biguint": 3, "cmp_biguint": 4, "div_rem_biguint": 5, "add_nonnative": 6,
                 "sub_nonnative": 7, "mul_nonnative": 8, "neg_nonnative": 9, "inv_nonnative": 10, "add_many_nonnative": 11, "list_le": 12,
                 "glv_mul": 13, "curve_add": 14, "curve_double": 15}
@@ -211,6 +221,8 @@ def _encode(circuit):
             words += [6, op.block_id, op.index, op.value]
         elif isinstance(op, MemoryWrite):
             words += [8, op.block_id, op.index, op.value]
+        elif isinstance(op, (BrilligCall, Directive)):
+            continue
         elif isinstance(op, Gadget):
             words += [110, GADGET_KINDS[op.name], op.param, len(op.lists)]
             for l in op.lists:

@@ -161,3 +161,15 @@ def test_range_check_u32_refuses_a_33_bit_value(p2g, corc):
     wires, pis = tr.generate_witness({0: 7, 1: 1 << 32})     # the generator truncates like the reference's `as u32`...
     with pytest.raises(AssertionError):                      # ...so the gate's constraints do not vanish on the trace
         _check_trace(p2g, corc, tr, wires, pis)
+
+
+def test_brillig_calls_and_directives_are_ignored_like_the_reference_does(p2g):
+    """mod.rs:97-104: unconstrained opcodes leave no trace in the circuit."""
+    A = p2g.acir
+    az = A.AssertZero(A.Expression([(1, 0, 1)], [(P - 1, 2)], 0))
+    plain = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(A.Circuit([az], [0], [1]))
+    mixed = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(A.Circuit([A.BrilligCall(0), az, A.Directive("ToLeRadix")], [0], [1]))
+    assert plain.common.degree_bits() == mixed.common.degree_bits() and np.array_equal(plain.constants_sigmas, mixed.constants_sigmas)
+    w1, p1 = plain.generate_witness({0: 3, 1: 4, 2: 12})
+    w2, p2 = mixed.generate_witness({0: 3, 1: 4, 2: 12})
+    assert np.array_equal(w1, w2) and p1 == p2 == [3]
