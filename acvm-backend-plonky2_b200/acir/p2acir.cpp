@@ -96,7 +96,20 @@ struct Builder {
     std::map<u64, Target> constants;                 // value -> target
     std::vector<u64> constant_order;
     std::map<std::tuple<u64, u64>, std::pair<int, int>> free_arith;   // (c0, c1) -> (row, next op)
-    std::map<std::tuple<u64, u64, Target, Target, Target>, Target> arith_cache;
+    struct ArithKey {
+        u64 c0, c1;
+        Target x, y, z;
+        bool operator==(const ArithKey& o) const { return c0 == o.c0 && c1 == o.c1 && x == o.x && y == o.y && z == o.z; }
+    };
+    struct ArithKeyHash {
+        size_t operator()(const ArithKey& k) const {
+            u64 h = k.c0 * 0x9E3779B97F4A7C15ULL ^ (k.c1 + 0x7F4A7C15ULL) * 0xC2B2AE3D27D4EB4FULL;
+            h ^= ((u64)(u32)k.x << 32 | (u32)k.y) * 0x165667B19E3779F9ULL;
+            h ^= (u64)(u32)k.z * 0xD6E8FEB86659FD93ULL;
+            return (size_t)(h ^ (h >> 29));
+        }
+    };
+    std::unordered_map<ArithKey, Target, ArithKeyHash> arith_cache;
     std::map<int, std::pair<int, int>> free_ra;      // bits -> (row, next copy)
     std::pair<int, int> free_u32_arith = {0, 0}, free_u32_sub = {0, 0};   // (row, next op)
     std::map<int, std::pair<int, int>> free_add_many;                     // num_addends -> (row, next op)
@@ -173,10 +186,9 @@ struct Builder {
     Target one() { return constant(1); }
     // ---- arithmetic: c0 * x * y + c1 * z   (gadgets/arithmetic.rs arithmetic / add_base_arithmetic_operation)
     Target arithmetic(u64 c0, u64 c1, Target x, Target y, Target z) {
-        auto key = std::make_tuple(c0, c1, find(x), find(y), find(z));
-        auto key2 = std::make_tuple(c0, c1, find(y), find(x), find(z));
+        // plonky2's base_arithmetic_results: the same operation (same constants, same operands in the same order) is computed once
+        const ArithKey key = {c0, c1, find(x), find(y), find(z)};
         auto hit = arith_cache.find(key);
-        if (hit == arith_cache.end()) hit = arith_cache.find(key2);
         if (hit != arith_cache.end()) return hit->second;
         auto& slot = free_arith[std::make_tuple(c0, c1)];
         if (slot.second == 0 || slot.second >= ARITH_OPS) {   // no open row for these constants
