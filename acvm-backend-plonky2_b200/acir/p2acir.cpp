@@ -102,14 +102,40 @@ struct Builder {
         bool operator==(const ArithKey& o) const { return c0 == o.c0 && c1 == o.c1 && x == o.x && y == o.y && z == o.z; }
     };
     struct ArithKeyHash {
-        size_t operator()(const ArithKey& k) const {
-            u64 h = k.c0 * 0x9E3779B97F4A7C15ULL ^ (k.c1 + 0x7F4A7C15ULL) * 0xC2B2AE3D27D4EB4FULL;
-            h ^= ((u64)(u32)k.x << 32 | (u32)k.y) * 0x165667B19E3779F9ULL;
-            h ^= (u64)(u32)k.z * 0xD6E8FEB86659FD93ULL;
+        size_t operator()(const ArithKey& k) const {   // multiply-xorshift rounds over the five fields
+            u64 h = ((u64)(u32)k.x << 32 | (u32)k.y) * 0x9E3779B97F4A7C15ULL;
+            h ^= h >> 32;
+            h = (h + (u32)k.z) * 0xD6E8FEB86659FD93ULL;
+            h ^= h >> 32;
+            h = (h + k.c0 + (k.c1 << 1 | k.c1 >> 63)) * 0xC2B2AE3D27D4EB4FULL;
             return (size_t)(h ^ (h >> 29));
         }
     };
-    std::unordered_map<ArithKey, Target, ArithKeyHash> arith_cache;
+    struct ArithCache {   // open addressing, linear probing: one cache line per lookup instead of a node chase (millions of entries)
+        struct Slot {
+            ArithKey key;
+            Target out;   // -1 = empty
+        };
+        std::vector<Slot> slots;
+        size_t count = 0;
+        Slot* locate(const ArithKey& k) {   // the slot holding k, or the empty slot where it belongs
+            if (slots.empty()) slots.assign(1 << 12, Slot{{0, 0, 0, 0, 0}, -1});
+            const size_t mask = slots.size() - 1;
+            size_t i = ArithKeyHash()(k) & mask;
+            while (slots[i].out >= 0 && !(slots[i].key == k)) i = (i + 1) & mask;
+            return &slots[i];
+        }
+        void insert(Slot* at, const ArithKey& k, Target out) {
+            at->key = k;
+            at->out = out;
+            if (++count * 5 < slots.size() * 3) return;
+            std::vector<Slot> old;
+            old.swap(slots);
+            slots.assign(old.size() * 2, Slot{{0, 0, 0, 0, 0}, -1});
+            for (const Slot& s : old)
+                if (s.out >= 0) *locate(s.key) = s;
+        }
+    } arith_cache;
     std::map<int, std::pair<int, int>> free_ra;      // bits -> (row, next copy)
     std::pair<int, int> free_u32_arith = {0, 0}, free_u32_sub = {0, 0};   // (row, next op)
     std::map<int, std::pair<int, int>> free_add_many;                     // num_addends -> (row, next op)
@@ -188,8 +214,7 @@ struct Builder {
     Target arithmetic(u64 c0, u64 c1, Target x, Target y, Target z) {
         // plonky2's base_arithmetic_results: the same operation (same constants, same operands in the same order) is computed once
         const ArithKey key = {c0, c1, find(x), find(y), find(z)};
-        auto hit = arith_cache.find(key);
-        if (hit != arith_cache.end()) return hit->second;
+        if (ArithCache::Slot* hit = arith_cache.locate(key); hit->out >= 0) return hit->out;
         auto& slot = free_arith[std::make_tuple(c0, c1)];
         if (slot.second == 0 || slot.second >= ARITH_OPS) {   // no open row for these constants
             slot.first = add_gate(gate_type(P2G_GATE_ARITHMETIC, ARITH_OPS), {c0, c1});
@@ -207,7 +232,7 @@ struct Builder {
         g.c0 = c0;
         g.c1 = c1;
         push_gen(g);
-        arith_cache[key] = out;
+        arith_cache.insert(arith_cache.locate(key), key, out);
         return out;
     }
     Target mul(Target x, Target y) { return arithmetic(1, 0, x, y, x); }
