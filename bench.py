@@ -131,6 +131,13 @@ def data_note(args):
     return "synthetic (deterministic keys and signatures; circuit from the real opcode)" if args.workload == REAL_WORKLOAD else "synthetic"
 
 
+def sample_note(args, bits):
+    """What a CPU sample at 2^bits rows is, in words."""
+    if args.workload == REAL_WORKLOAD:
+        return f"the same program on {1 << (bits - 17)} signature(s), 2^{bits} rows"
+    return f"the same gate mix at 2^{bits} rows"
+
+
 def min_sample_bits(args):
     return 17 if args.workload == REAL_WORKLOAD else 11
 
@@ -222,7 +229,7 @@ def run_reference(args, rank, world):
     if full_s is not None:
         per_proof_s = full_s
         how = (f"step 1 = ONE REAL 2^{args.degree_bits}-row proof ({full_s:.1f} s: value = 1 / that, measured, same circuit as the "
-               f"product arm); steps 2..{args.steps} and the warm-up = the same gate mix at 2^{bits} rows "
+               f"product arm); steps 2..{args.steps} and the warm-up = {sample_note(args, bits)} "
                f"({(sample_s or 0):.2f} s each)")
     else:
         per_proof_s = sample_s * nominal
@@ -470,7 +477,7 @@ def main():
             dt, cores, _ = cpu_proof(p2g, args, bits, 300)
             scale = float(1 << (args.degree_bits - bits))
             line["cpu_baseline"] = {"value": 1.0 / (dt * scale), "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"one oracle (C/OpenMP port of plonky2's prover, -march=native) proof, same gate mix, 2^{bits} rows in "
+                                    "sample": f"one oracle (C/OpenMP port of plonky2's prover, -march=native) proof, {sample_note(args, bits)}, in "
                                               f"{dt:.2f} s, time scaled x{int(scale)} (extrapolated; `bench.py --impl reference` times a real "
                                               f"2^{args.degree_bits}-row proof)"}
         else:
