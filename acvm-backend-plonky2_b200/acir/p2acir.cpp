@@ -1427,6 +1427,50 @@ void p2a_set_threads(int n) {
     (void)n;
 #endif
 }
+// self-test hook for acir/bigint.h (include/p2acir.h)
+int p2a_bigint_selftest(int op, const u32* a, size_t na, const u32* b, size_t nb, const u32* m, size_t nm, u32* q, size_t* nq, u32* r,
+                        size_t* nr, u32* flags) {
+    try {
+        auto load = [](const u32* p, size_t n) {
+            Big v;
+            v.d.assign(p, p + n);
+            v.trim();
+            return v;
+        };
+        auto store = [](const Big& v, u32* p, size_t* n) {
+            if (v.d.size() > 40) throw Error{"bigint selftest: result too long"};
+            std::copy(v.d.begin(), v.d.end(), p);
+            *n = v.d.size();
+        };
+        const Big A = load(a, na), B = load(b, nb), M = load(m, nm);
+        Big Q, R;
+        *flags = 0;
+        switch (op) {
+        case 0:
+            if (B.is_zero()) throw Error{"bigint selftest: division by zero"};
+            big_divrem(A, B, &Q, &R);
+            break;
+        case 1: Q = big_mul(A, B); break;
+        case 2:
+            if (M.is_zero()) throw Error{"bigint selftest: zero modulus"};
+            Q = big_powmod(A, B, M);
+            break;
+        case 3: {
+            bool n1, n2;
+            glv_decompose(big_mod(A, field_order(FIELD_SCALAR)), &Q, &R, &n1, &n2);
+            *flags = (n1 ? 1 : 0) | (n2 ? 2 : 0);
+            break;
+        }
+        default: throw Error{"bigint selftest: unknown op"};
+        }
+        store(Q, q, nq);
+        store(R, r, nr);
+        return 0;
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return -1;
+    }
+}
 // rows in use before the power-of-two padding
 u32 p2a_rows_used(void* h) {
     Translator* T = (Translator*)h;
