@@ -22,9 +22,12 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libp2acir.so")
-    src = os.path.join(_HERE, "acir", "p2acir.cpp")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", os.path.join(_HERE, "acir"), "-s"])
+    srcs = [os.path.join(_HERE, "acir", f) for f in os.listdir(os.path.join(_HERE, "acir")) if f.endswith((".cpp", ".h"))]
+    stale = lambda: force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs)   # noqa: E731
+    if stale():
+        with _lib.build_lock():          # ranks of one box may get here together: one builds, the others wait and re-check
+            if stale():
+                subprocess.check_call(["make", "-C", os.path.join(_HERE, "acir"), "-s"] + (["-B"] if force else []))
     return so
 
 

@@ -66,6 +66,23 @@ EXPORTS = ["p2g_version", "p2g_device_count", "p2g_last_error", "p2g_host_alloc"
            "p2g_poseidon_permute", "p2g_keccak256", "p2g_eval_gate_constraints", "p2g_test_field_ops"]
 
 
+class build_lock:
+    """Serialises `make` across the processes of one box (torchrun ranks importing the package at the same moment): an
+    exclusive flock on a file next to the libraries; the ranks that waited find the library up to date."""
+
+    def __enter__(self):
+        import fcntl
+        self._f = open(os.path.join(_HERE, ".build.lock"), "w")
+        fcntl.flock(self._f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self._f, fcntl.LOCK_UN)
+        self._f.close()
+        return False
+
+
 def build(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into libp2g.so (nvcc cross-compiles without a GPU)."""
     csrc = os.path.join(_HERE, "csrc")

@@ -32,6 +32,9 @@ tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
 t1 = time.perf_counter()
 data, _ = tr.unpack()                      # p2g_circuit_create: the preprocessed commitment (plonky2's build())
 t2 = time.perf_counter()
+data2, _ = tr.unpack()                     # again, with the CUDA context, kernels and twiddle tables already in place
+t2b = time.perf_counter()
+data2.close()
 wires, pis = tr.generate_witness(wit)      # generate_partial_witness + full_witness
 t3 = time.perf_counter()
 first = data.prove(wires, pis, compressed=True)   # the CLI writes the compressed proof (prove_action.rs:75-78)
@@ -42,9 +45,10 @@ for _ in range(5):
     pw = data.prove(wires, pis)
     ts.append(time.perf_counter() - t)
 print(json.dumps({"program": what, "rows_log2": tr.common.degree_bits(), "rows_used": tr.rows_used(), "gate_types": len(tr.common.gates),
-                  "translate_s": round(t1 - t0, 3), "circuit_build_s": round(t2 - t1, 3), "witness_generation_s": round(t3 - t2, 3),
+                  "translate_s": round(t1 - t0, 3), "circuit_build_s": round(t2 - t1, 3), "circuit_build_warm_s": round(t2b - t2, 3),
+                  "witness_generation_s": round(t3 - t2b, 3),
                   "first_prove_s": round(t4 - t3, 3), "prove_ms_e2e_pageable": round(1e3 * min(ts), 2),
                   "device_total_ms": round(pw.timings["total_ms"], 2),
                   "stages_ms": {k: round(pw.timings[k], 2) for k in ("wires_commit_ms", "zs_pp_ms", "quotient_ms", "openings_ms", "fri_ms")},
                   "proof_bytes": len(pw.to_bytes()),
-                  "cli_equivalent_s": round((t3 - t0) + min(ts), 3)}))
+                  "cli_equivalent_s": round((t2 - t0) + (t3 - t2b) + min(ts), 3)}))
