@@ -4,11 +4,13 @@
 //   * the translator  plonky2-backend/src/circuit_translation/mod.rs:72-190 (CircuitBuilderFromAcirToPlonky2::translate_circuit)
 //     with assert_zero_translator.rs:30-116 (AssertZero), mod.rs:131-137 (RANGE -> builder.range_check), mod.rs:213-232 +
 //     binary_digits_target.rs:120-186 (AND / XOR on bit decompositions), memory_translator.rs:145-171 (MemoryInit) and :125-137
-//     (memory read -> RandomAccessGate);
+//     (memory read -> RandomAccessGate), :87-113 (memory write), sha256_translator.rs:60-273 (Sha256Compression) and, in ecdsa.h,
+//     ecdsa_secp256k1_translator.rs with the whole plonky2_ecdsa gadget stack under it (u32 / biguint / non-native / curve / GLV);
 //   * the part of plonky2's CircuitBuilder those translators drive (arithmetic / add / mul / mul_const / sub, constant, connect,
 //     assert_zero, split_le, le_sum, random_access, register_public_input, build()) and its witness generators
 //     (generate_partial_witness: ArithmeticBaseGenerator, BaseSplitGenerator / BaseSumGenerator, WireSplitGenerator,
-//     RandomAccessGenerator, PoseidonGenerator).
+//     RandomAccessGenerator, PoseidonGenerator, EqualityGenerator), plus the generators of the reference's five custom gates and
+//     of its big-integer gadgets.  The C ABI is declared in include/p2acir.h.
 // It emits exactly what crosses the C ABI of include/p2g.h: the gate list, the per-row gate assignment + gate constants, the
 // sigma permutation of the copy constraints, and -- from the ACIR witness map -- the full wire matrix and the public inputs.
 //
@@ -543,6 +545,9 @@ struct Builder {
     struct ZeroBuf {   // calloc'ed: the pages are zero-filled by the kernel when first touched (by whichever thread gets there)
         E* p = nullptr;
         size_t n = 0;
+        ZeroBuf() {}
+        ZeroBuf(const ZeroBuf&) = delete;
+        ZeroBuf& operator=(const ZeroBuf&) = delete;
         ~ZeroBuf() { free(p); }
         void reset(size_t count) {
             free(p);
