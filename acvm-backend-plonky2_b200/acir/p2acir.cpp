@@ -213,7 +213,46 @@ struct Builder {
     Target zero() { return constant(0); }
     Target one() { return constant(1); }
     // ---- arithmetic: c0 * x * y + c1 * z   (gadgets/arithmetic.rs arithmetic / add_base_arithmetic_operation)
+    // plonky2 gadgets/arithmetic.rs arithmetic_special_cases: results that need no ArithmeticGate operation
+    bool arithmetic_special_case(u64 c0, u64 c1, Target x, Target y, Target z, Target* out) {
+        const Target zero_t = zero();
+        u64 xc = 0, yc = 0, zc = 0;
+        const bool x_const = as_constant(x, &xc), y_const = as_constant(y, &yc), z_const = as_constant(z, &zc);
+        const bool first_zero = c0 == 0 || x == zero_t || y == zero_t, second_zero = c1 == 0 || z == zero_t;
+        // both terms constant: their (constant) sum
+        bool first_known = first_zero, second_known = second_zero;
+        u64 first = 0, second = 0;
+        if (!first_zero && x_const && y_const) {
+            first_known = true;
+            first = gl_mul(gl_mul(xc, yc), c0);
+        }
+        if (!second_zero && z_const) {
+            second_known = true;
+            second = gl_mul(zc, c1);
+        }
+        if (first_known && second_known) {
+            *out = constant(gl_add(first, second));
+            return true;
+        }
+        if (first_zero && c1 == 1) {
+            *out = z;
+            return true;
+        }
+        if (second_zero) {
+            if (x_const && gl_mul(xc, c0) == 1) {
+                *out = y;
+                return true;
+            }
+            if (y_const && gl_mul(yc, c0) == 1) {
+                *out = x;
+                return true;
+            }
+        }
+        return false;
+    }
     Target arithmetic(u64 c0, u64 c1, Target x, Target y, Target z) {
+        Target special;
+        if (arithmetic_special_case(c0, c1, x, y, z, &special)) return special;
         // plonky2's base_arithmetic_results: the same operation (same constants, same operands in the same order) is computed once
         const ArithKey key = {c0, c1, find(x), find(y), find(z)};
         if (ArithCache::Slot* hit = arith_cache.locate(key); hit->out >= 0) return hit->out;

@@ -102,7 +102,7 @@ def test_assert_zero_chain_packs_rows_like_the_builder(p2g, corc):
     kinds = sorted(g.kind for g in tr.common.gates)
     C = p2g.circuit
     assert kinds == sorted([C.NOOP, C.CONSTANT, C.PUBLIC_INPUT, C.ARITHMETIC, C.POSEIDON])
-    assert tr.common.degree_bits() == 9          # 7 builder operations per opcode at 20 per row + 300 distinct constants at 2 per row
+    assert tr.common.degree_bits() == 8          # 6 gate operations per opcode (x * 1 and x + 0 need none) at 20 per row + 300 distinct constants at 2 per row
     wires, pis = tr.generate_witness(wit)
     assert pis == [1]
     _check_trace(p2g, corc, tr, wires, pis)
