@@ -45,6 +45,7 @@ def _acir_lib():
         L.p2a_witness.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.p2a_read_witnesses.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.p2a_set_threads.argtypes = [C.c_int]
+        L.p2a_fill_advice.argtypes = [C.c_void_p, C.c_void_p]
         L.p2a_rows_used.argtypes = [C.c_void_p]
         L.p2a_rows_used.restype = C.c_uint32
         _LIB = L
@@ -322,6 +323,13 @@ class CircuitBuilderFromAcirToPlonky2:
         vals, known = np.zeros(len(a), dtype=np.uint64), np.zeros(len(a), dtype=np.uint8)
         L.p2a_read_witnesses(self._h, a.ctypes.data_as(C.c_void_p), len(a), vals.ctypes.data_as(C.c_void_p), known.ctypes.data_as(C.c_void_p))
         return {int(k): int(v) for k, v, ok in zip(a, vals, known) if ok}
+
+    def fill_advice_host(self, wires):
+        """The host twin of CircuitData.fill_advice (csrc/advice.cuh compiled for the CPU): recomputes the advice columns of a
+        [234, N] uint64 matrix in place from its routed columns.  Test infrastructure."""
+        assert wires.dtype == np.uint64 and wires.flags.c_contiguous and wires.shape == (self.config.num_wires, self.common.degree())
+        _acir_lib().p2a_fill_advice(self._h, wires.ctypes.data_as(C.c_void_p))
+        return wires
 
     def rows_used(self):
         """Rows in use before the power-of-two padding."""

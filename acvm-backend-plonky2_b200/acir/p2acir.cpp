@@ -34,6 +34,7 @@
 
 #include "../csrc/hash.cuh"
 #include "../../include/p2g.h"
+#include "../csrc/advice.cuh"
 #include "bigint.h"
 #ifdef _OPENMP
 #include <omp.h>
@@ -1470,6 +1471,22 @@ void p2a_set_threads(int n) {
 #else
     (void)n;
 #endif
+}
+// csrc/advice.cuh on the host: recompute, in place, the advice columns (>= 80) of a wire matrix [234][2^degree_bits] of this circuit
+// from its routed columns -- the CPU twin of p2g_fill_advice_device, checked in tests/ against the generators above
+void p2a_fill_advice(void* h, u64* wires) {
+    Translator* T = (Translator*)h;
+    const Builder& b = T->b;
+    const size_t n = (size_t)1 << b.degree_bits;
+#pragma omp parallel for schedule(static)
+    for (long r = 0; r < (long)n; r++) {
+        const GateType& gt = b.gate_types[b.rows[r].gate];
+        auto get = [&](u32 col) -> u64 { return col < (u32)NUM_WIRES ? wires[(size_t)col * n + r] : 0; };
+        auto put = [&](u32 col, u64 v) {
+            if (col >= (u32)NUM_ROUTED && col < (u32)NUM_WIRES) wires[(size_t)col * n + r] = v;
+        };
+        fill_advice_row(gt.kind, gt.params, get, put);
+    }
 }
 // self-test hook for acir/bigint.h (include/p2acir.h)
 int p2a_bigint_selftest(int op, const u32* a, size_t na, const u32* b, size_t nb, const u32* m, size_t nm, u32* q, size_t* nq, u32* r,

@@ -353,6 +353,17 @@ class CircuitData:
         return self._run(_lib.lib().p2g_prove, w.ctypes.data_as(C.c_void_p), public_inputs, forced_pow_witness, timings,
                          0 if compressed else None)
 
+    def fill_advice(self, wires):
+        """Device-side witness fill (p2g_fill_advice_device): `wires` is a CUDA tensor [num_wires, N] on this circuit's device
+        whose routed columns (the first num_routed_wires) hold the witness; the advice columns are computed in place."""
+        shape = (self.common.config.num_wires, self.common.degree())
+        if not getattr(wires, "is_cuda", False) or tuple(wires.shape) != shape or not wires.is_contiguous() or wires.element_size() != 8:
+            raise ValueError(f"wires must be a contiguous 64-bit CUDA tensor of shape {shape}")
+        if wires.device.index != self.device:
+            raise ValueError("wires live on another device")
+        _lib.check(_lib.lib().p2g_fill_advice_device(self._h, C.c_void_p(wires.data_ptr())))
+        return wires
+
     def verifier_data_bytes(self):
         """`verifier_data().to_bytes(&BackendGateSerializer)`: the file `write_vk` writes (write_vk_action.rs:76-79), from this
         handle (the CircuitConfig fields the prover does not read default to wide_ecc_config)."""

@@ -11,6 +11,7 @@
 #include "internal.h"
 #include "nccl_dyn.h"
 #include "quotient.h"
+#include "advice.cuh"
 
 #include <chrono>
 #include <stdio.h>
@@ -405,6 +406,7 @@ struct p2g_circuit {
     int logn = 0, loglde = 0, hs = 0, h = 0;
     size_t n = 0, lde = 0;
     dbuf<u64> sigma_values;  // [R][N], natural row order (Z computation)
+    dbuf<uint8_t> row_gate;  // [N] index into `gates` of the row's gate, from the selector columns (p2g_fill_advice_device)
     dbuf<u64> wires_values;  // [W][N] staging for p2g_prove (host trace upload)
     PolyBatch cs, wires, zpp, quot;
     dbuf<u64> xs, l0s;
@@ -765,6 +767,37 @@ struct Writer {
     void digest(const digest_t& d, int hs) { put(&d, hs); }
 };
 
+// ---- device-side witness fill (advice.cuh) ---------------------------------------------------------------------------------------
+// the gate of every row: the selector column of the gate's group holds the gate's index, the others hold UNUSED (plonky2
+// plonk/circuit_builder.rs selector_polynomials)
+__global__ void k_row_gate(const u64* __restrict__ consts, size_t n, int num_selectors, uint8_t* __restrict__ row_gate) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    u32 g = 255;
+    for (int s = 0; s < num_selectors; s++) {
+        const u64 v = consts[(size_t)s * n + r];
+        if (v != 0xFFFFFFFFULL) g = (u32)v;
+    }
+    row_gate[r] = (uint8_t)g;
+}
+struct AdviceGates {
+    int num_gates, num_routed, num_wires, pad_;
+    u32 kind[P2G_MAX_GATES];
+    u32 params[P2G_MAX_GATES][4];
+};
+__global__ void __launch_bounds__(128) k_fill_advice(const __grid_constant__ AdviceGates T, const uint8_t* __restrict__ row_gate,
+                                                     u64* __restrict__ wires, size_t n) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const u32 g = row_gate[r];
+    if (g >= (u32)T.num_gates) return;
+    auto get = [&](u32 col) -> u64 { return col < (u32)T.num_wires ? wires[(size_t)col * n + r] : 0; };
+    auto put = [&](u32 col, u64 v) {
+        if (col >= (u32)T.num_routed && col < (u32)T.num_wires) wires[(size_t)col * n + r] = v;
+    };
+    fill_advice_row(T.kind[g], T.params[g], get, put);
+}
+
 void validate_desc(const p2g_circuit_desc* d) {
     auto bad = [](const char* m) { throw p2g_error(P2G_EBADARG, std::string("p2g_circuit_create: ") + m); };
     if (!d) bad("null descriptor");
@@ -925,6 +958,10 @@ static int circuit_create_impl(const p2g_circuit_desc* desc, int device, int ran
         CUDA_CHECK(cudaMemcpyAsync(vals.p, desc->constants_sigmas, (size_t)P * n * 8, cudaMemcpyHostToDevice, c->stream));
         C->sigma_values.alloc((size_t)R * n);
         CUDA_CHECK(cudaMemcpyAsync(C->sigma_values.p, vals.p + (size_t)Cc * n, (size_t)R * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        C->row_gate.alloc(n);
+        k_row_gate<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(vals.p, n, (int)desc->num_selectors, C->row_gate.p);
+        CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
         C->cs.ncols = P;
         commit_from_values(C, C->cs, vals.p, n);
         C->cs_cap = read_cap(C, C->cs.tree);
@@ -1948,6 +1985,29 @@ extern "C" int p2g_prove_columns(p2g_circuit* c, const uint64_t* const* wire_col
 extern "C" int p2g_prove_device(p2g_circuit* c, const uint64_t* d_wires, const uint64_t* public_inputs, size_t num_public_inputs,
                                 const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len, p2g_timings* timings) {
     return prove_entry(c, d_wires, true, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings);
+}
+
+// Completes the advice columns (>= num_routed_wires) of a device-resident trace in place from its routed columns (advice.cuh).
+extern "C" int p2g_fill_advice_device(p2g_circuit* C, uint64_t* d_wires) {
+    return guard([&] {
+        if (!C || !d_wires) throw p2g_error(P2G_EBADARG, "p2g_fill_advice_device: null argument");
+        std::lock_guard<std::mutex> lk(C->mu);
+        DevCtx* c = C->ctx;
+        CUDA_CHECK(cudaSetDevice(c->device));
+        const p2g_circuit_desc& d = C->d;
+        AdviceGates T = {};
+        T.num_gates = (int)d.num_gates;
+        T.num_routed = (int)d.num_routed_wires;
+        T.num_wires = (int)d.num_wires;
+        for (u32 g = 0; g < d.num_gates; g++) {
+            T.kind[g] = C->gates[g].kind;
+            for (int k = 0; k < 4; k++) T.params[g][k] = C->gates[g].params[k];
+        }
+        k_fill_advice<<<(unsigned)((C->n + 127) / 128), 128, 0, c->stream>>>(T, C->row_gate.p, d_wires, C->n);
+        CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
 }
 
 extern "C" int p2g_circuit_read(p2g_circuit* C, int what, void* out, size_t* len) {

@@ -55,6 +55,9 @@ int p2a_constants_sigmas(void* circuit, const p2g_gate* gates, uint32_t num_gate
 int p2a_witness(void* circuit, const uint64_t* ids, const uint64_t* values, size_t n, uint64_t* wires, uint64_t* public_inputs);
 /* the values the last p2a_witness left on ACIR witnesses (outputs computed by generators included); known[i] = 0 if unset */
 void p2a_read_witnesses(void* circuit, const uint64_t* ids, size_t n, uint64_t* values, uint8_t* known);
+/* the host twin of p2g_fill_advice_device (csrc/advice.cuh): recomputes, in place, the advice columns (>= 80) of a wire matrix of
+ * this circuit from its routed columns; used by the tests to check that function against the witness generators */
+void p2a_fill_advice(void* circuit, uint64_t* wires);
 /* worker threads of p2a_witness / p2a_constants_sigmas (0 = all cores) */
 void p2a_set_threads(int n);
 

@@ -161,6 +161,14 @@ int p2g_prove(p2g_circuit* c, const uint64_t* wires, const uint64_t* public_inpu
 int p2g_prove_device(p2g_circuit* c, const uint64_t* d_wires, const uint64_t* public_inputs, size_t num_public_inputs,
                      const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len, p2g_timings* timings);
 
+/* Device-side witness fill, first step (csrc/advice.cuh): completes, in place, the ADVICE columns -- wires at or
+ * above num_routed_wires, which no copy constraint reaches -- of a device-resident trace d_wires [num_wires][N] from its routed
+ * columns: the 2-bit limbs of the u32 gates (arithmetic_u32.rs:376-426, add_many_u32.rs:329-375, subtraction_u32.rs:298-343,
+ * range_check_u32.rs:198-220), the tails of ComparisonGate (comparison.rs:439-537) and RandomAccessGate, the internal state of
+ * PoseidonGate.  What plonky2's generator queue would have written there; the routed columns (all that a host-side witness
+ * generator still has to produce and upload: 80 of 234) are read, never written.  Follow with p2g_prove_device. */
+int p2g_fill_advice_device(p2g_circuit* c, uint64_t* d_wires);
+
 /* Same proof in plonky2's *compressed* layout, CompressedProofWithPublicInputs::to_bytes -- byte for byte what the reference
  * CLI writes to the proof file (prove_action.rs:75-78 `proof.compress(..)`, `to_bytes()`; the committed golden proofs under
  * example_programs/ are in this format).  Covers SURVEY 8(f) row f3.  wires_on_device: 0 = host pointer, 1 = device pointer. */

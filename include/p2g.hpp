@@ -320,6 +320,9 @@ class CircuitData {
         pw.proof_bytes.resize(len);
         return pw;
     }
+    // Device-side witness fill: d_wires [num_wires][N] on this circuit's device holds the routed columns; the advice columns
+    // (>= num_routed_wires) are computed in place (p2g_fill_advice_device).  Follow with p2g_prove_device.
+    void fill_advice_device(uint64_t* d_wires) { check(p2g_fill_advice_device(h_, d_wires)); }
     // verifier_data().to_bytes(&BackendGateSerializer): the file `write_vk` writes (write_vk_action.rs:76-79)
     std::vector<uint8_t> verifier_data_bytes(const p2g_vk_config* cfg = nullptr) const {
         size_t len = 0;

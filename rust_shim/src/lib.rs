@@ -123,6 +123,10 @@ extern "C" {
                              timings: *mut c_void) -> c_int;
     pub fn p2g_prove_compressed(c: *mut P2gCircuit, wires: *const u64, wires_on_device: c_int, public_inputs: *const u64, n_pi: usize,
                                 forced_pow_witness: *const u64, out: *mut u8, out_len: *mut usize, timings: *mut c_void) -> c_int;
+    pub fn p2g_prove_device(c: *mut P2gCircuit, d_wires: *const u64, public_inputs: *const u64, n_pi: usize, forced_pow_witness: *const u64,
+                            out: *mut u8, out_len: *mut usize, timings: *mut c_void) -> c_int;
+    /// device-side witness fill: the advice columns (>= num_routed_wires) of a device-resident trace, from its routed columns
+    pub fn p2g_fill_advice_device(c: *mut P2gCircuit, d_wires: *mut u64) -> c_int;
     pub fn p2g_proof_size_bound(c: *const P2gCircuit) -> usize;
     pub fn p2g_vk_bytes(c: *const P2gCircuit, cfg: *const c_void /* p2g_vk_config, NULL = wide_ecc_config */, out: *mut u8, out_len: *mut usize) -> c_int;
     // one proof across several GPUs: host callback, or the library's own NCCL communicator

@@ -1,0 +1,63 @@
+"""Device-side witness fill (csrc/advice.cuh, p2g_fill_advice_device): the advice columns (wires >= 80) of a
+trace are recomputed from its routed columns by one thread per row.  The expected values come from an independent restatement --
+the witness generators of acir/p2acir.cpp (arithmetic_u32.rs:376, add_many_u32.rs:329, subtraction_u32.rs:298,
+range_check_u32.rs:198, comparison.rs:439, plonky2's RandomAccessGenerator and PoseidonGenerator) -- on circuits translated from
+opcodes.  CPU: the same function compiled for the host; GPU: the kernel, through the C ABI, followed by p2g_prove_device."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import acir_cases  # noqa: E402
+
+ROUTED = 80
+
+
+def _circuits(p2g):
+    """(name, translated circuit, wires, public inputs) covering every gate that has advice wires."""
+    A, EI = p2g.acir, p2g.ecdsa_inputs
+    out = []
+    for name, circuit, wit in acir_cases.u32_gadget_cases(A):
+        out.append((name, circuit, wit))
+    by_name = {c[0]: c for c in acir_cases.cases(A)}
+    for name in ("memory_write", "memory_read_irregular_block", "and_32", "3x_plus_9y_equals_12"):   # RandomAccess, Poseidon (public inputs)
+        _, circuit, wit, _ = by_name[name]
+        out.append((name, circuit, wit))
+    circuit, wit, _ = EI.circuit_and_witness(A, [EI.deterministic_case(21)], outputs=[1], assert_valid=True)
+    out.append(("ecdsa", circuit, wit))
+    res = []
+    for name, circuit, wit in out:
+        tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+        wires, pis = tr.generate_witness(wit)
+        res.append((name, tr, wires, pis))
+    return res
+
+
+def test_host_twin_reproduces_the_generators_advice_wires(p2g):
+    C = p2g.circuit
+    seen = set()
+    for name, tr, wires, _ in _circuits(p2g):
+        stripped = wires.copy()
+        stripped[ROUTED:] = 0
+        assert name in ("3x_plus_9y_equals_12",) or wires[ROUTED:].any(), name        # there is something to recompute
+        tr.fill_advice_host(stripped)
+        bad = np.argwhere(stripped != wires)
+        assert bad.size == 0, (name, bad[:5])
+        seen |= {g.kind for g in tr.common.gates}
+    assert {C.U32_ARITHMETIC, C.U32_ADD_MANY, C.U32_SUBTRACTION, C.U32_RANGE_CHECK, C.COMPARISON, C.RANDOM_ACCESS, C.POSEIDON} <= seen
+
+
+@pytest.mark.gpu
+def test_device_fill_reproduces_the_generators_advice_wires_and_the_proof(p2g):
+    import torch
+    for name, tr, wires, pis in _circuits(p2g):
+        data, _ = tr.unpack()
+        with data:
+            full = torch.from_numpy(wires.view(np.int64)).cuda()
+            stripped = full.clone()
+            stripped[ROUTED:] = 0
+            data.fill_advice(stripped)
+            assert torch.equal(stripped, full), name
+            assert data.prove(stripped, pis).to_bytes() == data.prove(wires, pis).to_bytes(), name
