@@ -392,6 +392,23 @@ class CircuitData:
                                                                                    out, ln, tm)
         return self._run(fn, None, public_inputs, forced_pow_witness, timings, None)
 
+    def prove_routed_columns(self, routed_columns, public_inputs=(), forced_pow_witness=None, timings=True, compressed=False):
+        """prove_columns with only the ROUTED wire columns (the first num_routed_wires of `MatrixWitness.wire_values`): the advice
+        columns -- two thirds of the trace -- are computed on the device (p2g_prove_routed_columns)."""
+        R, n = self.common.config.num_routed_wires, self.common.degree()
+        if len(routed_columns) != R:
+            raise ValueError(f"expected {R} routed wire columns, got {len(routed_columns)}")
+        cols = []
+        for c in routed_columns:
+            a = np.ascontiguousarray(c, dtype=np.uint64)
+            if a.shape != (n,):
+                raise ValueError(f"every wire column must have shape ({n},), got {a.shape}")
+            cols.append(a)
+        ptrs = (C.c_void_p * R)(*[a.ctypes.data for a in cols])
+        fn = lambda h, _w, pis, npi, fp, out, ln, tm: _lib.lib().p2g_prove_routed_columns(h, ptrs, pis, npi, fp, 1 if compressed else 0,
+                                                                                          out, ln, tm)
+        return self._run(fn, None, public_inputs, forced_pow_witness, timings, None)
+
     def read(self, what, dtype=np.uint64):
         """Intermediates of the last proof (enum p2g_buffer), for parity tests."""
         ln = C.c_size_t(0)

@@ -469,6 +469,8 @@ struct p2g_circuit {
         cudaEvent_t last = nullptr;
         bool active = false;
         bool canon = false;   // reduce the uploaded words mod p before anything reads them (p2g_prove_columns)
+        int fill_from = -1;   // >= 0: only the columns below it are uploaded; the chunks from it on (null events) are computed on
+                              // the device by k_fill_advice once the uploaded ones are in place (p2g_prove_routed_columns)
         double bytes = 0;
         // pageable caller memory: chunks are first copied (multi-threaded) into a ring of pinned staging buffers, so the DMA
         // runs at full PCIe rate instead of the driver's single-threaded bounce copy
@@ -609,6 +611,52 @@ bool column_block(const p2g_circuit* C, int ncols, int* c0, int* c1) {
     return true;
 }
 // uploaded chunk [a, e) of the staging buffer: reduce mod p in place when the caller handed over raw GoldilocksField words
+// ---- device-side witness fill (advice.cuh) ---------------------------------------------------------------------------------------
+// the gate of every row: the selector column of the gate's group holds the gate's index, the others hold UNUSED (plonky2
+// plonk/circuit_builder.rs selector_polynomials)
+__global__ void k_row_gate(const u64* __restrict__ consts, size_t n, int num_selectors, uint8_t* __restrict__ row_gate) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    u32 g = 255;
+    for (int s = 0; s < num_selectors; s++) {
+        const u64 v = consts[(size_t)s * n + r];
+        if (v != 0xFFFFFFFFULL) g = (u32)v;
+    }
+    row_gate[r] = (uint8_t)g;
+}
+struct AdviceGates {
+    int num_gates, num_routed, num_wires, pad_;
+    u32 kind[P2G_MAX_GATES];
+    u32 params[P2G_MAX_GATES][4];
+};
+__global__ void __launch_bounds__(128) k_fill_advice(const __grid_constant__ AdviceGates T, const uint8_t* __restrict__ row_gate,
+                                                     u64* __restrict__ wires, size_t n) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const u32 g = row_gate[r];
+    if (g >= (u32)T.num_gates) return;
+    auto get = [&](u32 col) -> u64 { return col < (u32)T.num_wires ? wires[(size_t)col * n + r] : 0; };
+    auto put = [&](u32 col, u64 v) {
+        if (col >= (u32)T.num_routed && col < (u32)T.num_wires) wires[(size_t)col * n + r] = v;
+    };
+    fill_advice_row(T.kind[g], T.params[g], get, put);
+}
+
+static void launch_fill_advice(p2g_circuit* C, u64* d_wires) {   // on the handle's stream; the caller orders it after the routed columns
+    const p2g_circuit_desc& d = C->d;
+    AdviceGates T = {};
+    T.num_gates = (int)d.num_gates;
+    T.num_routed = (int)d.num_routed_wires;
+    T.num_wires = (int)d.num_wires;
+    for (u32 g = 0; g < d.num_gates; g++) {
+        T.kind[g] = C->gates[g].kind;
+        for (int k = 0; k < 4; k++) T.params[g][k] = C->gates[g].params[k];
+    }
+    k_fill_advice<<<(unsigned)((C->n + 127) / 128), 128, 0, C->ctx->stream>>>(T, C->row_gate.p, d_wires, C->n);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch(C->ctx);
+}
+
 void canon_chunk(p2g_circuit* C, const p2g_circuit::Upload* up, const u64* d_values, size_t values_cs, int a, int e) {
     if (!up || !up->canon || e <= a) return;
     const size_t cnt = (size_t)(e - a) * values_cs;
@@ -710,8 +758,17 @@ void commit_from_values(p2g_circuit* C, PolyBatch& b, const u64* d_values, size_
         if (b.lde.n != (size_t)b.ncols * C->lde_l) b.lde.alloc((size_t)b.ncols * C->lde_l);
         for (auto& ch : up->chunks) {
             int a = std::get<0>(ch), e = std::get<1>(ch);
-            CUDA_CHECK(cudaStreamWaitEvent(c->stream, std::get<2>(ch), 0));
-            canon_chunk(C, up, d_values, values_cs, a, e);
+            const bool filled = up->fill_from >= 0 && a >= up->fill_from;
+            // the routed chunks before this one have been waited for and reduced on this stream: their advice columns can be computed
+            if (filled && a == up->fill_from) {
+                // wires no generator sets read as zero (full_witness): clear the advice region of the staging matrix, which still
+                // holds the previous proof's columns, then let every row's gate write its own
+                CUDA_CHECK(cudaMemsetAsync(const_cast<u64*>(d_values) + (size_t)up->fill_from * values_cs, 0,
+                                           (size_t)(b.ncols - up->fill_from) * values_cs * 8, c->stream));
+                launch_fill_advice(C, const_cast<u64*>(d_values));
+            }
+            if (std::get<2>(ch)) CUDA_CHECK(cudaStreamWaitEvent(c->stream, std::get<2>(ch), 0));
+            if (!filled) canon_chunk(C, up, d_values, values_cs, a, e);
             ntt_ifft(c, d_values + (size_t)a * values_cs, values_cs, b.coeffs.p + (size_t)a * C->n, C->n, C->logn, e - a);
             ntt_lde(c, b.coeffs.p + (size_t)a * C->n, C->n, b.lde.p + (size_t)a * C->lde_l, C->lde_l, C->logn, C->d.rate_bits, e - a,
                     GL_GEN, C->z0, C->nzl);
@@ -766,37 +823,6 @@ struct Writer {
     void u8v(uint8_t x) { put(&x, 1); }
     void digest(const digest_t& d, int hs) { put(&d, hs); }
 };
-
-// ---- device-side witness fill (advice.cuh) ---------------------------------------------------------------------------------------
-// the gate of every row: the selector column of the gate's group holds the gate's index, the others hold UNUSED (plonky2
-// plonk/circuit_builder.rs selector_polynomials)
-__global__ void k_row_gate(const u64* __restrict__ consts, size_t n, int num_selectors, uint8_t* __restrict__ row_gate) {
-    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    u32 g = 255;
-    for (int s = 0; s < num_selectors; s++) {
-        const u64 v = consts[(size_t)s * n + r];
-        if (v != 0xFFFFFFFFULL) g = (u32)v;
-    }
-    row_gate[r] = (uint8_t)g;
-}
-struct AdviceGates {
-    int num_gates, num_routed, num_wires, pad_;
-    u32 kind[P2G_MAX_GATES];
-    u32 params[P2G_MAX_GATES][4];
-};
-__global__ void __launch_bounds__(128) k_fill_advice(const __grid_constant__ AdviceGates T, const uint8_t* __restrict__ row_gate,
-                                                     u64* __restrict__ wires, size_t n) {
-    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const u32 g = row_gate[r];
-    if (g >= (u32)T.num_gates) return;
-    auto get = [&](u32 col) -> u64 { return col < (u32)T.num_wires ? wires[(size_t)col * n + r] : 0; };
-    auto put = [&](u32 col, u64 v) {
-        if (col >= (u32)T.num_routed && col < (u32)T.num_wires) wires[(size_t)col * n + r] = v;
-    };
-    fill_advice_row(T.kind[g], T.params[g], get, put);
-}
 
 void validate_desc(const p2g_circuit_desc* d) {
     auto bad = [](const char* m) { throw p2g_error(P2G_EBADARG, std::string("p2g_circuit_create: ") + m); };
@@ -1802,11 +1828,16 @@ static void prove_impl(p2g_circuit* C, const u64* d_wires, const u64* public_inp
 // holds it) -- exactly one of the two
 static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u64* public_inputs, size_t n_pi,
                        const u64* forced_pow, uint8_t* out, size_t* out_len, p2g_timings* tm, bool compressed = false,
-                       const u64* const* cols = nullptr) {
+                       const u64* const* cols = nullptr, bool routed_only = false) {
     return guard([&] {
         if (!C || (!wires && !cols) || !out_len || (n_pi && !public_inputs)) throw p2g_error(P2G_EBADARG, "p2g_prove: null argument");
+        // routed_only: cols holds the num_routed_wires routed columns; the advice columns are computed on the device
+        const int cols_given = routed_only ? (int)C->d.num_routed_wires : (int)C->d.num_wires;
+        if (routed_only && (!cols || C->world != 1))
+            throw p2g_error(P2G_EBADARG, "p2g_prove_routed_columns: needs column pointers and a single-GPU handle (sharded: "
+                                         "p2g_fill_advice_device + p2g_prove_device)");
         if (cols)
-            for (u32 i = 0; i < C->d.num_wires; i++)
+            for (int i = 0; i < cols_given; i++)
                 if (!cols[i]) throw p2g_error(P2G_EBADARG, "p2g_prove_columns: null column pointer");
         if (n_pi != C->d.num_public_inputs) throw p2g_error(P2G_EBADARG, "p2g_prove: public input count");
         for (size_t i = 0; i < n_pi; i++)
@@ -1852,7 +1883,7 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
             };
             // is the caller's buffer page-locked?  (cudaHostAlloc / p2g_host_alloc / cudaHostRegister)
             bool pinned = true;
-            for (int i = 0; i < (cols ? W : 1); i++) {
+            for (int i = 0; i < (cols ? cols_given : 1); i++) {
                 cudaPointerAttributes attr;
                 if (cudaPointerGetAttributes(&attr, cols ? cols[i] : wires) == cudaSuccess) {
                     if (attr.type == cudaMemoryTypeDevice)
@@ -1937,14 +1968,20 @@ static int prove_entry(p2g_circuit* C, const u64* wires, bool on_device, const u
             ev_start = up.start;
             int c0, c1;
             column_block(C, W, &c0, &c1);
-            step = std::max(step, (c1 - c0 + 7) / 8);                                         // ... and at most 8 chunks for small traces
-            for (int a = c0; a < c1; a += step) {
-                int e = std::min(c1, a + step);
+            const int c_up = routed_only ? R : c1;   // routed_only (single GPU: c0 = 0, c1 = W): the upload stops at the routed columns
+            step = std::max(step, (c_up - c0 + 7) / 8);                                       // ... and at most 8 chunks for small traces
+            for (int a = c0; a < c_up; a += step) {
+                int e = std::min(c_up, a + step);
                 copy_cols(a, e);
                 cudaEvent_t ev = next_event();
                 CUDA_CHECK(cudaEventRecord(ev, up.copy));
                 up.chunks.emplace_back(a, e, ev);
                 up.last = ev;
+            }
+            up.fill_from = -1;
+            if (routed_only) {
+                up.fill_from = R;
+                for (int a = R; a < W; a += step) up.chunks.emplace_back(a, std::min(W, a + step), (cudaEvent_t) nullptr);
             }
             if (c0 > 0 || c1 < R) {   // sharded: routed columns outside the block -- only the rows of this rank's Z / partial products
                 if (c0 > 0) copy_block(0, std::min(c0, R), C->row0, C->row1);
@@ -1982,6 +2019,15 @@ extern "C" int p2g_prove_columns(p2g_circuit* c, const uint64_t* const* wire_col
     return prove_entry(c, nullptr, false, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings,
                        compressed != 0, wire_columns);
 }
+// p2g_prove_columns with two thirds of the trace left at home: only the num_routed_wires routed columns are passed and uploaded;
+// the advice columns are computed on the device (k_fill_advice) as soon as the routed ones are in place, inside the same chunked
+// upload / inverse NTT / LDE pipeline.
+extern "C" int p2g_prove_routed_columns(p2g_circuit* c, const uint64_t* const* routed_columns, const uint64_t* public_inputs,
+                                        size_t num_public_inputs, const uint64_t* forced_pow_witness, int compressed, uint8_t* out,
+                                        size_t* out_len, p2g_timings* timings) {
+    return prove_entry(c, nullptr, false, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings,
+                       compressed != 0, routed_columns, true);
+}
 extern "C" int p2g_prove_device(p2g_circuit* c, const uint64_t* d_wires, const uint64_t* public_inputs, size_t num_public_inputs,
                                 const uint64_t* forced_pow_witness, uint8_t* out, size_t* out_len, p2g_timings* timings) {
     return prove_entry(c, d_wires, true, public_inputs, num_public_inputs, forced_pow_witness, out, out_len, timings);
@@ -1994,18 +2040,7 @@ extern "C" int p2g_fill_advice_device(p2g_circuit* C, uint64_t* d_wires) {
         std::lock_guard<std::mutex> lk(C->mu);
         DevCtx* c = C->ctx;
         CUDA_CHECK(cudaSetDevice(c->device));
-        const p2g_circuit_desc& d = C->d;
-        AdviceGates T = {};
-        T.num_gates = (int)d.num_gates;
-        T.num_routed = (int)d.num_routed_wires;
-        T.num_wires = (int)d.num_wires;
-        for (u32 g = 0; g < d.num_gates; g++) {
-            T.kind[g] = C->gates[g].kind;
-            for (int k = 0; k < 4; k++) T.params[g][k] = C->gates[g].params[k];
-        }
-        k_fill_advice<<<(unsigned)((C->n + 127) / 128), 128, 0, c->stream>>>(T, C->row_gate.p, d_wires, C->n);
-        CUDA_CHECK(cudaGetLastError());
-        count_launch(c);
+        launch_fill_advice(C, d_wires);
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
     });
 }

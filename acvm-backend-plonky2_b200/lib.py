@@ -60,7 +60,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 
 # every symbol include/p2g.h declares (tests/test_abi.py checks the header against this list and the built library)
 EXPORTS = ["p2g_version", "p2g_device_count", "p2g_last_error", "p2g_host_alloc", "p2g_host_free", "p2g_circuit_create", "p2g_circuit_destroy",
-           "p2g_circuit_cap", "p2g_prove", "p2g_prove_device", "p2g_fill_advice_device", "p2g_prove_compressed", "p2g_prove_columns", "p2g_proof_size_bound", "p2g_circuit_create_sharded",
+           "p2g_circuit_cap", "p2g_prove", "p2g_prove_device", "p2g_fill_advice_device", "p2g_prove_compressed", "p2g_prove_columns", "p2g_prove_routed_columns", "p2g_proof_size_bound", "p2g_circuit_create_sharded",
            "p2g_nccl_unique_id", "p2g_circuit_create_sharded_nccl", "p2g_vk_bytes",
            "p2g_circuit_read", "p2g_ifft", "p2g_lde", "p2g_coset_ifft_leaforder", "p2g_merkle_cap",
            "p2g_poseidon_permute", "p2g_keccak256", "p2g_eval_gate_constraints", "p2g_test_field_ops"]
@@ -120,6 +120,8 @@ def lib():
         L.p2g_fill_advice_device.argtypes = [C.c_void_p, C.c_void_p]
         L.p2g_prove_compressed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                            C.POINTER(C.c_size_t), C.POINTER(TimingsS)]
+        L.p2g_prove_routed_columns.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
+                                               C.POINTER(C.c_size_t), C.c_void_p]
         L.p2g_prove_columns.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                                         C.POINTER(C.c_size_t), C.c_void_p]
         L.p2g_circuit_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]

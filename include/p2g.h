@@ -169,6 +169,14 @@ int p2g_prove_device(p2g_circuit* c, const uint64_t* d_wires, const uint64_t* pu
  * generator still has to produce and upload: 80 of 234) are read, never written.  Follow with p2g_prove_device. */
 int p2g_fill_advice_device(p2g_circuit* c, uint64_t* d_wires);
 
+/* p2g_prove_columns with two thirds of the trace left at home: routed_columns holds only the num_routed_wires ROUTED columns of
+ * MatrixWitness.wire_values (N words each, any representative < 2^64); they are uploaded through the same chunked pipeline and
+ * the advice columns are computed on the device as soon as they are in place (what p2g_fill_advice_device does, inside the
+ * pipeline).  Single-GPU handles; same bytes as p2g_prove_columns on the full witness. */
+int p2g_prove_routed_columns(p2g_circuit* c, const uint64_t* const* routed_columns, const uint64_t* public_inputs,
+                             size_t num_public_inputs, const uint64_t* forced_pow_witness, int compressed, uint8_t* out,
+                             size_t* out_len, p2g_timings* timings);
+
 /* Same proof in plonky2's *compressed* layout, CompressedProofWithPublicInputs::to_bytes -- byte for byte what the reference
  * CLI writes to the proof file (prove_action.rs:75-78 `proof.compress(..)`, `to_bytes()`; the committed golden proofs under
  * example_programs/ are in this format).  Covers SURVEY 8(f) row f3.  wires_on_device: 0 = host pointer, 1 = device pointer. */

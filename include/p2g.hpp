@@ -320,6 +320,21 @@ class CircuitData {
         pw.proof_bytes.resize(len);
         return pw;
     }
+    // prove_columns with only the ROUTED columns (the first num_routed_wires of MatrixWitness.wire_values): the advice columns are
+    // computed on the device inside the upload pipeline (p2g_prove_routed_columns); same bytes as prove_columns on the full witness
+    ProofWithPublicInputs prove_routed_columns(const std::vector<const uint64_t*>& routed_columns, const std::vector<uint64_t>& public_inputs,
+                                               const uint64_t* forced_pow_witness = nullptr, bool compressed = false) {
+        if (routed_columns.size() != common.config.num_routed_wires) throw std::invalid_argument("one column pointer per routed wire expected");
+        ProofWithPublicInputs pw;
+        pw.public_inputs = public_inputs;
+        pw.compressed = compressed;
+        pw.proof_bytes.resize(p2g_proof_size_bound(h_));
+        size_t len = pw.proof_bytes.size();
+        check(p2g_prove_routed_columns(h_, routed_columns.data(), public_inputs.data(), public_inputs.size(), forced_pow_witness,
+                                       compressed ? 1 : 0, pw.proof_bytes.data(), &len, &pw.timings));
+        pw.proof_bytes.resize(len);
+        return pw;
+    }
     // Device-side witness fill: d_wires [num_wires][N] on this circuit's device holds the routed columns; the advice columns
     // (>= num_routed_wires) are computed in place (p2g_fill_advice_device).  Follow with p2g_prove_device.
     void fill_advice_device(uint64_t* d_wires) { check(p2g_fill_advice_device(h_, d_wires)); }

@@ -123,6 +123,10 @@ extern "C" {
                              timings: *mut c_void) -> c_int;
     pub fn p2g_prove_compressed(c: *mut P2gCircuit, wires: *const u64, wires_on_device: c_int, public_inputs: *const u64, n_pi: usize,
                                 forced_pow_witness: *const u64, out: *mut u8, out_len: *mut usize, timings: *mut c_void) -> c_int;
+    /// p2g_prove_columns with only the num_routed_wires routed columns; the advice columns are computed on the device
+    pub fn p2g_prove_routed_columns(c: *mut P2gCircuit, routed_columns: *const *const u64, public_inputs: *const u64, n_pi: usize,
+                                    forced_pow_witness: *const u64, compressed: c_int, out: *mut u8, out_len: *mut usize,
+                                    timings: *mut c_void) -> c_int;
     pub fn p2g_prove_device(c: *mut P2gCircuit, d_wires: *const u64, public_inputs: *const u64, n_pi: usize, forced_pow_witness: *const u64,
                             out: *mut u8, out_len: *mut usize, timings: *mut c_void) -> c_int;
     /// device-side witness fill: the advice columns (>= num_routed_wires) of a device-resident trace, from its routed columns

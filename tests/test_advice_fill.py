@@ -55,9 +55,17 @@ def test_device_fill_reproduces_the_generators_advice_wires_and_the_proof(p2g):
     for name, tr, wires, pis in _circuits(p2g):
         data, _ = tr.unpack()
         with data:
+            # inside the upload pipeline, on a fresh handle (its staging matrix has never held this trace): only the 80 routed
+            # columns cross the boundary (pageable, one array per column)
+            routed = [np.array(wires[c]) for c in range(ROUTED)]
+            got = data.prove_routed_columns(routed, pis).to_bytes()
+            want = data.prove(wires, pis).to_bytes()
+            assert got == want, name
+            assert data.prove_routed_columns(routed, pis, compressed=True).to_bytes() == data.prove(wires, pis, compressed=True).to_bytes()
+            # the stand-alone entry point on a device-resident trace
             full = torch.from_numpy(wires.view(np.int64)).cuda()
             stripped = full.clone()
             stripped[ROUTED:] = 0
             data.fill_advice(stripped)
             assert torch.equal(stripped, full), name
-            assert data.prove(stripped, pis).to_bytes() == data.prove(wires, pis).to_bytes(), name
+            assert data.prove(stripped, pis).to_bytes() == want, name
