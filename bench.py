@@ -329,6 +329,8 @@ def main():
         """steps -> list of proofs: `steps` proofs in total, spread over the F handles, each driven by its own host thread.
         columns: w is a list of separately allocated pageable wire columns (p2g_prove_columns)."""
         def one(h):
+            if columns == "routed":
+                return h.prove_routed_columns(w, sc.public_inputs)
             return h.prove_columns(w, sc.public_inputs) if columns else h.prove(w, sc.public_inputs)
 
         def run(steps):
@@ -362,13 +364,26 @@ def main():
     ms_e2e, outs_e2e = timed(prove_steps(wires_host), args.steps)
     # the same call from ordinary (pageable) memory laid out as plonky2 holds the witness -- one heap allocation per wire column
     # (MatrixWitness.wire_values), handed over as column pointers: what the Rust shim does, with no flat copy and no pinning
-    ms_pageable = None
+    ms_pageable = ms_routed = None
     if world == 1 and not args.no_pageable:
         cols = [sc.wires[i].copy() for i in range(sc.wires.shape[0])]
         prove_steps(cols, True)(F)
         ms_pageable, outs_pg = timed(prove_steps(cols, True), max(2, args.steps // 2))
         ms_pageable /= max(2, args.steps // 2)
         assert outs_pg[0].to_bytes() == outs_e2e[0].to_bytes()
+        # ... and with only the routed columns handed over (p2g_prove_routed_columns): the advice columns, two thirds of the trace,
+        # are computed on the device inside the upload pipeline.  An extra: a failure here must not cost the bench line.
+        ms_routed = None
+        try:
+            rcols = cols[:cfg.num_routed_wires]
+            prove_steps(rcols, "routed")(F)
+            ms_routed, outs_rt = timed(prove_steps(rcols, "routed"), max(2, args.steps // 2))
+            ms_routed /= max(2, args.steps // 2)
+            if outs_rt[0].to_bytes() != outs_e2e[0].to_bytes():
+                ms_routed = None
+        except Exception as e:  # noqa: BLE001
+            print(f"bench.py: routed-columns measurement skipped: {e}", file=sys.stderr)
+            ms_routed = None
         del cols
     # per-kernel / per-stage device timings (CUDA events on the library's stream): with several proofs in flight the stage
     # events of one proof span kernels of the others, so they are taken from two proofs run alone right after the timed region
@@ -436,6 +451,7 @@ def main():
             "e2e": {"value": world * K / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": proof_bytes, "host_memory": "pinned (p2g_host_alloc), one [wires][rows] block",
                     "pageable_columns_ms_per_step": ms_pageable,
+                    "pageable_routed_columns_ms_per_step": ms_routed,
                     "pageable_columns_note": "p2g_prove_columns from ordinary memory, one allocation per wire column (MatrixWitness.wire_values "
                                              "as the Rust shim passes it), staged through the library's pinned ring; measured at N = 1"},
             "gpu_launches": int(launches),
