@@ -43,6 +43,7 @@ def _acir_lib():
         L.p2a_gate_types.argtypes = [C.c_void_p, C.c_void_p]
         L.p2a_constants_sigmas.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.p2a_witness.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.p2a_witness_routed.argtypes = L.p2a_witness.argtypes
         L.p2a_read_witnesses.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.p2a_set_threads.argtypes = [C.c_int]
         L.p2a_fill_advice.argtypes = [C.c_void_p, C.c_void_p]
@@ -301,16 +302,19 @@ class CircuitBuilderFromAcirToPlonky2:
             raise TranslationError(L.p2a_last_error().decode())
         return self
 
-    def generate_witness(self, witness_map):
+    def generate_witness(self, witness_map, routed_only=False):
         """plonky2 `generate_partial_witness(..).full_witness()` for an ACIR witness map {witness index: value} (what
-        prove_action.rs:99-117 feeds in): returns (wires [234, N], public_inputs)."""
+        prove_action.rs:99-117 feeds in): returns (wires [234, N], public_inputs).  routed_only=True returns just the routed
+        columns [80, N] -- the generators skip the advice wires, which CircuitData.prove_routed_columns computes on the device."""
         L = _acir_lib()
         ids = np.array(list(witness_map.keys()), dtype=np.uint64)
         vals = np.array([int(v) % P for v in witness_map.values()], dtype=np.uint64)
-        wires = np.zeros((self.config.num_wires, self.common.degree()), dtype=np.uint64)
+        ncols = self.config.num_routed_wires if routed_only else self.config.num_wires
+        wires = np.zeros((ncols, self.common.degree()), dtype=np.uint64)
         pis = np.zeros(max(1, self.common.num_public_inputs), dtype=np.uint64)
-        rc = L.p2a_witness(self._h, ids.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p), len(ids),
-                           wires.ctypes.data_as(C.c_void_p), pis.ctypes.data_as(C.c_void_p))
+        fn = L.p2a_witness_routed if routed_only else L.p2a_witness
+        rc = fn(self._h, ids.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p), len(ids),
+                wires.ctypes.data_as(C.c_void_p), pis.ctypes.data_as(C.c_void_p))
         if rc != 0:
             raise TranslationError(L.p2a_last_error().decode())
         return wires, [int(x) for x in pis[:self.common.num_public_inputs]]

@@ -664,7 +664,9 @@ struct Builder {
         return get_class(root[t], v);
     }
     // gate-local wire access for the generators
+    bool skip_advice = false;   // p2a_witness_routed: the advice columns are left to the device (csrc/advice.cuh)
     void setw(int row, int col, u64 v) {
+        if (col >= NUM_ROUTED && skip_advice) return;
         const Target r = col < NUM_ROUTED ? routed_root[(size_t)row * NUM_ROUTED + col] : -1;
         if (r >= 0) {
             set_class(r, v);
@@ -1357,10 +1359,12 @@ int p2a_constants_sigmas(void* h, const p2g_gate* gates, u32 ngates, const u32* 
 // Witness generation: ACIR witness map (ids + canonical values) -> wires [234][N] (unset wires are zero, as
 // in plonky2's full_witness) and the public inputs in registration order.  Returns 0, or -1 (message in p2a_last_error) when a
 // copy constraint is contradicted -- where the reference panics inside witness generation, before the prover.
-int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wires, u64* public_inputs) {
+static int witness_impl(void* h, const u64* ids, const u64* values, size_t nw, u64* wires, u64* public_inputs, bool routed_only) {
     Translator* T = (Translator*)h;
     Builder& b = T->b;
     try {
+        b.skip_advice = routed_only;
+        const int out_cols = routed_only ? NUM_ROUTED : NUM_WIRES;
         const size_t n = (size_t)1 << b.degree_bits;
         const bool trace = getenv("P2A_TRACE") != nullptr;
         auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; };
@@ -1435,7 +1439,7 @@ int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wire
 #pragma omp parallel for schedule(static)
         for (long k = 0; k < nblk; k++) {
             const size_t r0 = (size_t)k * BLK, r1 = std::min(n, r0 + BLK);
-            for (int c = 0; c < NUM_WIRES; c++)
+            for (int c = 0; c < out_cols; c++)
                 for (size_t r = r0; r < r1; r++) wires[(size_t)c * n + r] = b.wire_value(r, c);
         }
         for (size_t i = 0; i < b.public_inputs.size(); i++) {
@@ -1451,6 +1455,15 @@ int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wire
         g_err = e.msg;
         return -1;
     }
+}
+
+int p2a_witness(void* h, const u64* ids, const u64* values, size_t nw, u64* wires, u64* public_inputs) {
+    return witness_impl(h, ids, values, nw, wires, public_inputs, false);
+}
+// The same, producing only the routed columns [80][2^degree_bits]: the generators do not write the advice wires (the limbs of the u32
+// gates, ...), which p2g_prove_routed_columns / p2g_fill_advice_device compute on the device
+int p2a_witness_routed(void* h, const u64* ids, const u64* values, size_t nw, u64* routed_wires, u64* public_inputs) {
+    return witness_impl(h, ids, values, nw, routed_wires, public_inputs, true);
 }
 
 // Values the last p2a_witness run assigned to ACIR witnesses (outputs computed by the generators included): what the reference reads

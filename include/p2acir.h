@@ -53,6 +53,10 @@ int p2a_constants_sigmas(void* circuit, const p2g_gate* gates, uint32_t num_gate
 /* generate_partial_witness + full_witness: ACIR witness map (ids, values) -> wires [234][2^degree_bits] (unset wires = 0) and the
  * public inputs in registration order.  -1 when a copy constraint is contradicted (the reference panics there). */
 int p2a_witness(void* circuit, const uint64_t* ids, const uint64_t* values, size_t n, uint64_t* wires, uint64_t* public_inputs);
+/* the same, producing only the routed columns [80][2^degree_bits]: the advice wires are not generated (the device computes them,
+ * p2g_prove_routed_columns / p2g_fill_advice_device) */
+int p2a_witness_routed(void* circuit, const uint64_t* ids, const uint64_t* values, size_t n, uint64_t* routed_wires,
+                       uint64_t* public_inputs);
 /* the values the last p2a_witness left on ACIR witnesses (outputs computed by generators included); known[i] = 0 if unset */
 void p2a_read_witnesses(void* circuit, const uint64_t* ids, size_t n, uint64_t* values, uint8_t* known);
 /* the host twin of p2g_fill_advice_device (csrc/advice.cuh): recomputes, in place, the advice columns (>= 80) of a wire matrix of

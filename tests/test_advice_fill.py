@@ -49,6 +49,22 @@ def test_host_twin_reproduces_the_generators_advice_wires(p2g):
     assert {C.U32_ARITHMETIC, C.U32_ADD_MANY, C.U32_SUBTRACTION, C.U32_RANGE_CHECK, C.COMPARISON, C.RANDOM_ACCESS, C.POSEIDON} <= seen
 
 
+def test_routed_only_witness_generation(p2g):
+    """generate_witness(routed_only=True): the generators skip the advice wires; the 80 columns equal those of the full witness,
+    and the host twin of the device fill completes them to the full witness."""
+    A, EI = p2g.acir, p2g.ecdsa_inputs
+    circuit, wit, outs = EI.circuit_and_witness(A, [EI.deterministic_case(22)], outputs=[1], assert_valid=True)
+    tr = A.CircuitBuilderFromAcirToPlonky2().translate_circuit(circuit)
+    full, pis = tr.generate_witness(wit)
+    routed, pis2 = tr.generate_witness(wit, routed_only=True)
+    assert routed.shape == (ROUTED, full.shape[1]) and pis == pis2 and np.array_equal(routed, full[:ROUTED])
+    assert tr.read_witnesses(outs) == {outs[0]: 1}
+    rebuilt = np.zeros_like(full)
+    rebuilt[:ROUTED] = routed
+    tr.fill_advice_host(rebuilt)
+    assert np.array_equal(rebuilt, full)
+
+
 @pytest.mark.gpu
 def test_device_fill_reproduces_the_generators_advice_wires_and_the_proof(p2g):
     import torch
