@@ -603,6 +603,45 @@ struct Builder {
     ZeroBuf<unsigned char> has, cell_has;
     std::vector<std::vector<u32>> group_gens;   // generator indices per group, creation order; group 0 = everything light
     std::vector<int> group_order;               // groups sorted by dependency level: the order the worker threads take them in
+    // Field inversions whose result no other generator reads (the u32 arithmetic gate's canonicity inverse, the comparison gate's
+    // equality dummies): queued per group while the generators run and done at the end with one batched inversion (Montgomery's
+    // trick: three multiplications each) -- they were a third of the run.
+    struct DeferredInv {
+        int row, col;
+        u64 value;   // non-zero
+    };
+    std::vector<std::vector<DeferredInv>> deferred_inv;   // [group]
+    void defer_inverse(const Gen& g, int col, u64 value) { deferred_inv[g.group].push_back({g.row, col, value}); }
+    void flush_deferred_inverses() {
+        std::vector<DeferredInv> all;
+        for (auto& v : deferred_inv) {
+            all.insert(all.end(), v.begin(), v.end());
+            v.clear();
+        }
+        const long n = (long)all.size(), CH = 4096;
+        std::string err;
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long lo = 0; lo < n; lo += CH) {
+            const long hi = std::min(n, lo + CH);
+            std::vector<u64> prefix(hi - lo);
+            u64 acc = 1;
+            for (long i = lo; i < hi; i++) {
+                prefix[i - lo] = acc;
+                acc = gl_mul(acc, all[i].value);
+            }
+            u64 inv = gl_inv(acc);
+            try {
+                for (long i = hi; i-- > lo;) {
+                    setw(all[i].row, all[i].col, gl_mul(inv, prefix[i - lo]));
+                    inv = gl_mul(inv, all[i].value);
+                }
+            } catch (const Error& e) {
+#pragma omp critical
+                err = e.msg;
+            }
+        }
+        if (!err.empty()) throw Error{err};
+    }
     std::vector<u32> const_gens;
     void finalize() {
         root.resize(parent.size());
@@ -628,6 +667,7 @@ struct Builder {
         has.reset(parent.size());
         cell_val.reset(rows.size() * NUM_WIRES);
         cell_has.reset(rows.size() * NUM_WIRES);
+        deferred_inv.assign(num_groups, {});
         for (auto& g : gens) g.done = false;
     }
     void set_class(Target r, u64 v) {
@@ -759,7 +799,8 @@ struct Builder {
             setw(g.row, 6 * g.i + 3, lo);
             setw(g.row, 6 * g.i + 4, hi);
             const u64 diff = 0xFFFFFFFFULL - hi;
-            setw(g.row, 6 * g.i + 5, diff ? gl_inv(diff) : 0);
+            if (diff) defer_inverse(g, 6 * g.i + 5, diff);
+            else setw(g.row, 6 * g.i + 5, 0);
             for (int j = 0; j < 32; j++) setw(g.row, 6 * g.n + 32 * g.i + j, (out >> (2 * j)) & 3);
             return true;
         }
@@ -809,7 +850,8 @@ struct Builder {
                 const u64 fa = (a >> (cb * i)) & (cs - 1), fb = (b >> (cb * i)) & (cs - 1);
                 setw(g.row, 4 + i, fa);
                 setw(g.row, 4 + nc + i, fb);
-                setw(g.row, 4 + 2 * nc + i, fa == fb ? 1 : gl_inv(gl_sub(fb, fa)));   // equality dummy
+                if (fa == fb) setw(g.row, 4 + 2 * nc + i, 1);   // equality dummy
+                else defer_inverse(g, 4 + 2 * nc + i, gl_sub(fb, fa));
                 setw(g.row, 4 + 3 * nc + i, fa == fb ? 1 : 0);                        // chunks equal
                 if (fa != fb) {
                     msd = gl_sub(fb, fa);
@@ -1432,6 +1474,7 @@ static int witness_impl(void* h, const u64* ids, const u64* values, size_t nw, u
             }
             if (!progress) break;
         }
+        b.flush_deferred_inverses();
         const double t1 = now();
         // the wire matrix is column-major [wire][row]: transpose the row-major tables in blocks of rows (every row < n has a gate)
         if (b.rows.size() != n) throw Error{"witness generation: the circuit is not padded"};
