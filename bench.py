@@ -298,6 +298,7 @@ def main():
     cfg = p2g.CircuitConfig.wide_ecc_config(hasher=args.hasher)
     if world > 1:   # input generation (untimed): this rank's share of the host cores, not torchrun's OMP_NUM_THREADS=1
         p2g.synth.set_threads(max(1, (os.cpu_count() or world) // world))
+        p2g.acir.set_threads(max(1, (os.cpu_count() or world) // world))
     sc = make_workload(p2g, args, args.degree_bits, 0xAC1D + 3 + 1000 * rank, pinned=True)
     # circuit build: once, outside the timing.  `inflight` handles = proofs in flight on this GPU (own stream + host thread each)
     F = max(1, args.inflight)
