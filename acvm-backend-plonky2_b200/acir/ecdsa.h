@@ -111,7 +111,7 @@ inline bool Builder::run_big(BigGen& g) {
     case BG_NN_INV: {   // nonnative.rs:689-703
         const Big x = big_mod(a, m);
         if (x.is_zero()) throw Error{"witness generation: inverse of zero (the reference's curve formulas are incomplete)"};
-        const Big inv = big_powmod(x, big_sub(m, Big(2)), m);
+        const Big inv = big_invmod_odd(x, m);
         Big q, r;
         big_divrem(big_mul(x, inv), m, &q, &r);
         set_big(g.o2, q);

@@ -1572,6 +1572,10 @@ int p2a_bigint_selftest(int op, const u32* a, size_t na, const u32* b, size_t nb
             if (M.is_zero()) throw Error{"bigint selftest: zero modulus"};
             Q = big_powmod(A, B, M);
             break;
+        case 4:
+            if (M.is_zero() || !(M.d[0] & 1)) throw Error{"bigint selftest: odd modulus expected"};
+            Q = big_invmod_odd(A, M);
+            break;
         case 3: {
             bool n1, n2;
             glv_decompose(big_mod(A, field_order(FIELD_SCALAR)), &Q, &R, &n1, &n2);

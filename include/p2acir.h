@@ -67,7 +67,7 @@ void p2a_set_threads(int n);
 
 /* self-test hook for the big-integer arithmetic behind the non-native generators (acir/bigint.h): limbs are u32, least significant
  * first.  op 0: q = a / b, r = a % b;  op 1: q = a * b;  op 2: q = a^b mod m;  op 3: GLV decomposition of a (mod the secp256k1
- * group order): q = |k1|, r = |k2|, flags bit 0 = k1 < 0, bit 1 = k2 < 0.  Outputs hold up to 40 limbs; returns 0 or -1. */
+ * group order): q = |k1|, r = |k2|, flags bit 0 = k1 < 0, bit 1 = k2 < 0;  op 4: q = a^-1 mod m (m odd, gcd(a, m) = 1).  Outputs hold up to 40 limbs; returns 0 or -1. */
 int p2a_bigint_selftest(int op, const uint32_t* a, size_t na, const uint32_t* b, size_t nb, const uint32_t* m, size_t nm,
                         uint32_t* q, size_t* nq, uint32_t* r, size_t* nr, uint32_t* flags);
 

@@ -68,6 +68,11 @@ def test_bigint_against_python_integers(p2g):
         x, e = rng.getrandbits(300), rng.getrandbits(256)
         assert _call(L, 2, x, e, N)[0] == pow(x, e, N)
     assert _call(L, 2, 12345, N - 2, N)[0] == pow(12345, -1, N)
+    PF = 2 ** 256 - 2 ** 32 - 977
+    for mod in (N, PF, 0xFFFFFFFF00000001, 97):      # binary extended Euclid against Python's modular inverse
+        for x in [1, 2, mod - 1, mod - 2, mod + 5, (mod * 3 + 7)] + [rng.getrandbits(300) for _ in range(100)]:
+            if x % mod:
+                assert _call(L, 4, x, 0, mod)[0] == pow(x, -1, mod), (hex(x), hex(mod))
     # GLV: |k1|, |k2| < 2^128, and k1 + s k2 = k with the signs applied
     S = sum(v << (64 * i) for i, v in enumerate([16069571880186789234, 1310022930574435960, 11900229862571533402, 6008836872998760672]))
     for k in [0, 1, N - 1, N // 2, N // 2 + 1] + [rng.randrange(N) for _ in range(200)]:
