@@ -152,3 +152,53 @@ def test_curve_gadgets_on_curve_points(p2g, corc):
     m = EI.point_mul(k, p2)
     P.add("glv_mul", [P.value(p2[0], 8), P.value(p2[1], 8), P.value(k, 8), P.result(m[0], 8), P.result(m[1], 8)])
     run(p2g, corc, P, prove=False)     # 2^16 rows: constraints and outputs are checked, the proof is left to the ECDSA tests
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_gadget_programs(p2g, corc, seed):
+    """Randomised programs over the biguint / non-native gadgets with operands of random limb counts (1..8): outputs against Python
+    integers, every gate and copy constraint on the trace (no proof: the circuits differ only in size from the ones proved above)."""
+    rng = random.Random(1000 + seed)
+    P = Program(p2g.acir)
+
+    def rnd(nl):   # a value that really uses nl limbs about half of the time
+        v = rng.getrandbits(32 * nl)
+        return v if rng.random() < 0.5 else v >> rng.randrange(0, 32 * nl)
+
+    for _ in range(14):
+        kind = rng.choice(["add", "sub", "mul", "cmp", "divrem", "nn_add", "nn_sub", "nn_mul", "nn_inv"])
+        na, nb = rng.randrange(1, 9), rng.randrange(1, 9)
+        x, y = rnd(na), rnd(nb)
+        if kind == "add":
+            P.add("add_biguint", [P.value(x, na), P.value(y, nb), P.result(x + y, max(na, nb) + 1)])
+        elif kind == "sub":
+            if x < y:
+                x, y, na, nb = y, x, nb, na
+            P.add("sub_biguint", [P.value(x, na), P.value(y, nb), P.result(x - y, max(na, nb))])
+        elif kind == "mul":
+            P.add("mul_biguint", [P.value(x, na), P.value(y, nb), P.result(x * y, na + nb + 1)])
+        elif kind == "cmp":
+            if rng.random() < 0.3:
+                y, nb = x, na
+            P.add("cmp_biguint", [P.value(x, na), P.value(y, nb), P.result(int(x <= y), 1)])
+        elif kind == "divrem":
+            y = y or 1
+            if nb > na + 1:
+                nb = na
+                y = (y % (1 << (32 * nb))) or 1
+            P.add("div_rem_biguint", [P.value(x, na), P.value(y, nb), P.result(x // y, na - nb + 1 if nb <= na + 1 else 0),
+                                      P.result(x % y, nb)]) if x // y < 1 << (32 * max(0, na - nb + 1)) else None
+        else:
+            field = rng.randrange(2)
+            mod = SECP_N if field else SECP_P
+            x, y = rng.randrange(mod), rng.randrange(mod)
+            if kind == "nn_add":
+                P.add("add_nonnative", [P.value(x, 8), P.value(y, 8), P.result((x + y) % mod if x + y != mod else mod, 8)], field)
+            elif kind == "nn_sub":
+                P.add("sub_nonnative", [P.value(x, 8), P.value(y, 8), P.result((x - y) % mod, 8)], field)
+            elif kind == "nn_mul":
+                P.add("mul_nonnative", [P.value(x, 8), P.value(y, 8), P.result(x * y % mod, 8)], field)
+            else:
+                x = x or 1
+                P.add("inv_nonnative", [P.value(x, 8), P.result(pow(x, -1, mod), 8)], field)
+    run(p2g, corc, P, prove=False)
