@@ -91,7 +91,6 @@ const int NUM_WIRES = 234, NUM_ROUTED = 80, ARITH_OPS = 20, CONSTS_PER_GATE = 2,
 struct Builder {
     // targets: routed wires become targets lazily, (row, col) -> id; the advice wires (col >= 80) can never be copy-constrained, so
     // they are not targets at all: wire() names them by a negative code and witness generation keeps their values in a dense table
-    std::vector<std::pair<int, int>> target_wire;   // (row, col) or (-1, -1) for virtual targets
     std::vector<Target> routed_target;               // [row * 80 + col] -> target or -1
     std::vector<Target> parent;                      // union-find over targets (copy constraints)
     std::vector<Row> rows;
@@ -161,7 +160,6 @@ struct Builder {
     Target pi_hash[4];
 
     Target new_target(int row = -1, int col = -1) {
-        target_wire.emplace_back(row, col);
         parent.push_back((Target)parent.size());
         return (Target)parent.size() - 1;
     }
@@ -197,7 +195,7 @@ struct Builder {
     int add_gate(int gt, std::vector<u64> consts = {}) {
         rows.push_back({gt, std::move(consts)});
         if (rows.size() > (size_t)1 << 22) throw Error{"circuit has more than 2^22 rows"};
-        routed_target.resize(rows.size() * NUM_ROUTED, -1);
+        if (routed_target.size() < rows.size() * NUM_ROUTED) routed_target.resize((rows.size() + 4095) * NUM_ROUTED, -1);
         return (int)rows.size() - 1;
     }
 
@@ -644,6 +642,7 @@ struct Builder {
     }
     std::vector<u32> const_gens;
     void finalize() {
+        routed_target.resize(rows.size() * NUM_ROUTED, -1);   // it grows in blocks of rows
         root.resize(parent.size());
         for (Target t = 0; t < (Target)parent.size(); t++) root[t] = find(t);
         routed_root.assign(routed_target.size(), -1);
