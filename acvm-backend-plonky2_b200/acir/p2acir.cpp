@@ -1543,6 +1543,20 @@ void p2a_fill_advice(void* h, u64* wires) {
         fill_advice_row(gt.kind, gt.params, get, put);
     }
 }
+// the same for any trace: gate table (kind + params[4] per gate), the gate index of every row, wires [num_wires][n]
+void p2a_fill_advice_rows(const u32* kind_and_params, u32 num_gates, const uint8_t* row_gate, u64* wires, size_t n, u32 num_wires,
+                          u32 num_routed) {
+#pragma omp parallel for schedule(static)
+    for (long r = 0; r < (long)n; r++) {
+        const u32 g = row_gate[r];
+        if (g >= num_gates) continue;
+        auto get = [&](u32 col) -> u64 { return col < num_wires ? wires[(size_t)col * n + r] : 0; };
+        auto put = [&](u32 col, u64 v) {
+            if (col >= num_routed && col < num_wires) wires[(size_t)col * n + r] = v;
+        };
+        fill_advice_row(kind_and_params[5 * g], kind_and_params + 5 * g + 1, get, put);
+    }
+}
 // self-test hook for acir/bigint.h (include/p2acir.h)
 int p2a_bigint_selftest(int op, const u32* a, size_t na, const u32* b, size_t nb, const u32* m, size_t nm, u32* q, size_t* nq, u32* r,
                         size_t* nr, u32* flags) {

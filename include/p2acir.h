@@ -62,6 +62,9 @@ void p2a_read_witnesses(void* circuit, const uint64_t* ids, size_t n, uint64_t* 
 /* the host twin of p2g_fill_advice_device (csrc/advice.cuh): recomputes, in place, the advice columns (>= 80) of a wire matrix of
  * this circuit from its routed columns; used by the tests to check that function against the witness generators */
 void p2a_fill_advice(void* circuit, uint64_t* wires);
+/* the same for any trace: the gate table as (kind, params[4]) per gate, the gate index of every row, wires [num_wires][n] */
+void p2a_fill_advice_rows(const uint32_t* kind_and_params, uint32_t num_gates, const uint8_t* row_gate, uint64_t* wires, size_t n,
+                          uint32_t num_wires, uint32_t num_routed);
 /* worker threads of p2a_witness / p2a_constants_sigmas (0 = all cores) */
 void p2a_set_threads(int n);
 

@@ -14,7 +14,7 @@ N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 def test_header_symbols_are_exported_and_header_is_c(p2g, tmp_path):
     src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "p2acir.h")).read(), flags=re.S)
     names = sorted(set(re.findall(r"\b(p2a_[a-z0-9_]+)\s*\(", src)))
-    assert len(names) == 13
+    assert len(names) == 14
     L = C.CDLL(p2g.acir.build())
     assert not [n for n in names if not hasattr(L, n)]
     c = tmp_path / "t.c"

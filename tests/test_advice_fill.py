@@ -49,6 +49,37 @@ def test_host_twin_reproduces_the_generators_advice_wires(p2g):
     assert {C.U32_ARITHMETIC, C.U32_ADD_MANY, C.U32_SUBTRACTION, C.U32_RANGE_CHECK, C.COMPARISON, C.RANDOM_ACCESS, C.POSEIDON} <= seen
 
 
+@pytest.mark.parametrize("workload,bits", [("all_gates", 10), ("ecdsa", 12), ("sha256", 11)])
+def test_host_twin_on_the_synthetic_circuits(p2g, workload, bits):
+    """A third source of expected values: the circuit synthesiser (synth/synth.cpp) fills its rows with its own per-gate witness
+    code and other gate shapes (e.g. ComparisonGate and RandomAccessGate of other sizes, Poseidon rows with swap = 1)."""
+    import ctypes as C
+    sc = p2g.synth.SyntheticCircuit(bits, workload, num_public_inputs=4, seed=77)
+    com = sc.common
+    table = np.array([[g.kind, *g.params[:4]] for g in com.gates], dtype=np.uint32).reshape(-1)
+    # the synthesiser puts random filler on the wires a row's gate does not constrain, so only what the fill writes is compared:
+    # the advice region starts as a sentinel (not a field element)
+    SENTINEL = np.uint64(0xFFFFFFFFFFFFFFFF)
+    stripped = sc.wires.copy()
+    stripped[ROUTED:] = SENTINEL
+    L = p2g.acir._acir_lib()
+    L.p2a_fill_advice_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]
+    L.p2a_fill_advice_rows(table.ctypes.data_as(C.c_void_p), len(com.gates), sc.row_gate.ctypes.data_as(C.c_void_p),
+                           stripped.ctypes.data_as(C.c_void_p), com.degree(), com.config.num_wires, com.config.num_routed_wires)
+    written = stripped != SENTINEL
+    written[:ROUTED] = False
+    bad = np.argwhere(written & (stripped != sc.wires))
+    assert bad.size == 0, [(int(c), int(r), com.gates[sc.row_gate[r]].id) for c, r in bad[:5]]
+    # Poseidon rows (135 wires) always have advice wires; the small test shapes of the other gates may fit below wire 80
+    C_ = p2g.circuit
+    per_row = written.sum(axis=0)
+    for gi, g in enumerate(com.gates):
+        rows = np.nonzero(sc.row_gate == gi)[0]
+        if len(rows) and g.kind == C_.POSEIDON:
+            assert per_row[rows].min() == 135 - ROUTED, g.id
+    assert written.any()
+
+
 def test_routed_only_witness_generation(p2g):
     """generate_witness(routed_only=True): the generators skip the advice wires; the 80 columns equal those of the full witness,
     and the host twin of the device fill completes them to the full witness."""
